@@ -1,0 +1,133 @@
+/*
+ * hrnet_b200 -- C ABI of the B200-native HRNet inference hot path.
+ *
+ * Drop-in boundary: the reference calls its network exactly once per
+ * <= max_batch_size chunk as `self.model(images)` (SimpleHRNet.py:286,294,421,429), copies the
+ * heat-maps to the host (:296,:431) and decodes them in a Python double loop (:299-308,:434-443).
+ * The reference already swaps `self.model` for an opaque engine at this seam when
+ * `enable_tensorrt=True` (SimpleHRNet.py:143-147).  This library is the engine that plugs into
+ * the same seam: plain pointers and sizes, no torch / C++ types in any signature, bound from
+ * Python with ctypes (INTEGRATION.md shows the reference-side stub).
+ *
+ * Conventions
+ *   - every entry point returns 0 on success or a negative HRNET_E_* code; the message of the
+ *     last failure on the calling thread is available through hrnet_last_error().
+ *   - the library never allocates device memory and never synchronises unless stated: the caller
+ *     (PyTorch in this repo) owns the packed weights, the activation workspace and every
+ *     input / output buffer; pointers are BORROWED and must stay valid while bound.
+ *   - all device work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as
+ *     void*); branch-level concurrency uses internal streams forked from / joined to it.
+ *   - a plan is not thread-safe; use one plan per (process, device).
+ */
+#ifndef HRNET_B200_H_
+#define HRNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRNET_OK 0
+#define HRNET_E_INVALID (-1)   /* bad argument / unsupported configuration */
+#define HRNET_E_CUDA (-2)      /* a CUDA runtime / driver call failed */
+#define HRNET_E_STATE (-3)     /* call order violated (e.g. forward before bind) */
+#define HRNET_E_NOMEM (-4)     /* caller-provided buffer too small */
+
+#define HRNET_ARCH_HRNET 0      /* models_/hrnet.py:74  HRNet(c, nof_joints)            */
+#define HRNET_ARCH_POSERESNET 1 /* models_/poseresnet.py:16 PoseResNet(resnet_size, ..) */
+
+/* plan flags */
+#define HRNET_FLAG_FORCE_SIMT 1u   /* debug: run every conv on the SIMT cross-check kernel          */
+#define HRNET_FLAG_NO_GRAPH 2u     /* debug: launch kernels directly instead of replaying a graph   */
+#define HRNET_FLAG_FUSE_F16 4u     /* store exchange-unit partial terms in fp16 instead of fp32     */
+#define HRNET_FLAG_SERIAL 8u       /* debug: run all branches on the caller's stream                */
+
+typedef struct HrnetPlan HrnetPlan;
+
+/* Mirrors the constructor arguments that select the network in SimpleHRNet.__init__
+ * (SimpleHRNet.py:21-37: c, nof_joints, model_name, resolution, max_batch_size). */
+typedef struct HrnetDesc {
+  int32_t arch;        /* HRNET_ARCH_*                                              */
+  int32_t c;           /* HRNet width (32 / 48) or PoseResNet size (50 / 101 / 152) */
+  int32_t nof_joints;  /* <= 32                                                     */
+  int32_t height;      /* network input height, multiple of 32                      */
+  int32_t width;       /* network input width, multiple of 32                       */
+  int32_t max_batch;   /* largest n accepted by hrnet_forward                       */
+  uint32_t flags;      /* HRNET_FLAG_*                                              */
+} HrnetDesc;
+
+/* One weight-carrying layer of the plan; tells the host-side packer which state_dict entries
+ * (reference naming) go where in the packed weight buffer. */
+typedef struct HrnetParamInfo {
+  char conv_key[96];    /* "<key>.weight" is the conv weight, "<key>.bias" its bias if has_bias   */
+  char bn_key[96];      /* "<key>.{weight,bias,running_mean,running_var}"; empty = no BatchNorm   */
+  int32_t cout, cin, kh, kw;
+  int32_t kind;         /* 0 conv [cout,cin,kh,kw]; 1 transposed-conv sub-pixel phase (see sub_a/b) */
+  int32_t sub_a, sub_b; /* kind 1: output parity (row, col) this 2x2 sub-kernel produces          */
+  int32_t has_bias;
+  int32_t w_f32;        /* weights stored fp32 instead of fp16                                     */
+  uint64_t w_offset;    /* bytes: packed as [cout][kh][kw][cin]                                    */
+  uint64_t scale_offset;/* bytes: fp32 [cout]  gamma / sqrt(var + 1e-5)      (1 without BN)        */
+  uint64_t bias_offset; /* bytes: fp32 [cout]  beta - mean * scale           (conv bias without BN)*/
+} HrnetParamInfo;
+
+/* ---- plan construction: host only, no CUDA calls (usable on a CPU-only box) ------------------ */
+int hrnet_plan_create(const HrnetDesc* desc, HrnetPlan** out);
+void hrnet_plan_destroy(HrnetPlan* plan);
+const char* hrnet_last_error(void);
+
+/* Bytes the caller must provide: activation workspace and packed weights (both 1024 B aligned). */
+int hrnet_plan_workspace_bytes(const HrnetPlan* plan, size_t* act_bytes, size_t* weight_bytes);
+int hrnet_plan_num_params(const HrnetPlan* plan);
+int hrnet_plan_param_info(const HrnetPlan* plan, int index, HrnetParamInfo* out);
+/* JSON description of tensors / ops (used by the CPU graph-emulation test and for debugging).
+ * Writes at most cap bytes (NUL-terminated); *needed receives the full length incl. NUL. */
+int hrnet_plan_describe(const HrnetPlan* plan, char* buf, size_t cap, size_t* needed);
+
+/* ---- binding and execution: need a CUDA device ---------------------------------------------- */
+/* Creates the TMA descriptors over the caller's buffers.  Must be repeated if either moves. */
+int hrnet_plan_bind(HrnetPlan* plan, void* weights_dev, size_t weight_bytes, void* workspace_dev, size_t act_bytes);
+
+/* The hot path: `self.model(images)` + the argmax decode.
+ *   in_nchw_f32 : [n,3,H,W] fp32, ImageNet-normalised RGB, device (what the reference feeds self.model)
+ *   heatmaps    : [n,J,H/4,W/4] fp32 device, or NULL (kept in the workspace, not returned)
+ *   joints      : [n,J,3] fp32 device, (y, x, confidence) exactly as SimpleHRNet.py:306-308
+ *   argmax_idx  : [n,J] int32 device flat np.argmax index, or NULL
+ *   boxes       : [n,4] fp32 device (x1,y1,x2,y2), or NULL = [0,0,W,H] (multiperson=False crops)
+ * 0 <= n <= max_batch. Asynchronous on `stream`. */
+int hrnet_forward(HrnetPlan* plan, const float* in_nchw_f32, int n, float* heatmaps, float* joints,
+                  int32_t* argmax_idx, const float* boxes, void* stream);
+
+/* Same call with HOST buffers (pinned for full speed): H2D of the input, forward, D2H of the
+ * joints (and of heat-maps / indices when requested).  Staging buffers live in the workspace.
+ * Synchronises `stream` before returning. */
+int hrnet_forward_host(HrnetPlan* plan, const float* in_nchw_f32_host, int n, float* heatmaps_host,
+                       float* joints_host, int32_t* argmax_idx_host, const float* boxes_host, void* stream);
+
+/* Number of kernels one hrnet_forward(n) launches (for bench.py's gpu_launches). */
+int hrnet_plan_launch_count(const HrnetPlan* plan);
+
+/* ---- single-op entry points (tests, ncu) ------------------------------------------------------ */
+/* kxk conv + BN(scale,bias) (+residual) (+ReLU) on NHWC fp16; weights [cout][k][k][cin] fp16.
+ * use_tc=1 -> tcgen05 implicit GEMM, 0 -> SIMT cross-check kernel.  out_f32 selects fp32 output. */
+int hrnet_conv_bn_act(const void* in_nhwc_f16, const void* w_f16, const float* scale, const float* bias,
+                      const void* residual_f16, void* out, int n, int ih, int iw, int cin, int cout, int ksize,
+                      int stride, int relu, int out_f32, int use_tc, void* stream);
+/* out = act(sum_j nearest_up(src_j, 2^shift_j)); srcs NHWC fp16 (is_f32[j]=0) or fp32. */
+int hrnet_fuse(const void* const* srcs, const int* shifts, const int* is_f32, int nsrc, void* out_f16, int n, int h,
+               int w, int c, int relu, void* stream);
+/* argmax decode of [n,J,Hh,Wh] fp32 heat-maps (SimpleHRNet.py:296-308). */
+int hrnet_argmax(const float* heatmaps, int n, int nof_joints, int hh, int wh, const float* boxes, float* joints,
+                 int32_t* argmax_idx, void* stream);
+/* median device time in microseconds of `iters` launches of one conv (CUDA events on `stream`),
+ * same arguments as hrnet_conv_bn_act; used by bench.py for the per-kernel roofline. */
+int hrnet_conv_bench(const void* in_nhwc_f16, const void* w_f16, const float* scale, const float* bias,
+                     const void* residual_f16, void* out, int n, int ih, int iw, int cin, int cout, int ksize,
+                     int stride, int relu, int iters, float* usec_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRNET_B200_H_ */

@@ -1,0 +1,127 @@
+"""SimpleHRNet: the reference's user-facing class (SimpleHRNet.py:12-496) re-hosted on the B200
+engine for the multiperson=False path (the hot path named by BASELINE.json).  Same constructor
+arguments, same `predict()` input/return formats, same error strings.
+
+Out of scope here: the YOLO person detectors (multiperson=True) and the TensorRT
+loader; both raise NotImplementedError instead of silently doing something else."""
+import numpy as np
+import torch
+
+from .engine import B200Engine
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # SimpleHRNet.py:152
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+class SimpleHRNet:
+    def __init__(self, c, nof_joints, checkpoint_path, model_name='HRNet', resolution=(384, 288),
+                 interpolation=None, multiperson=True, return_heatmaps=False, return_bounding_boxes=False,
+                 max_batch_size=32, yolo_version='v3', yolo_model_def=None, yolo_class_path=None,
+                 yolo_weights_path=None, device=torch.device("cuda"), enable_tensorrt=False, engine_flags=0):
+        self.c = c
+        self.nof_joints = nof_joints
+        self.checkpoint_path = checkpoint_path
+        self.model_name = model_name
+        self.resolution = resolution          # (height, width)
+        self.interpolation = interpolation
+        self.multiperson = multiperson
+        self.return_heatmaps = return_heatmaps
+        self.return_bounding_boxes = return_bounding_boxes
+        self.max_batch_size = max_batch_size
+        self.yolo_version = yolo_version
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        self.enable_tensorrt = enable_tensorrt
+
+        if self.multiperson:
+            if self.yolo_version not in ('v3', 'v5'):
+                raise ValueError('Unsopported YOLO version.')           # SimpleHRNet.py:107 (sic)
+            raise NotImplementedError("multiperson=True needs the YOLO person detector, which is outside the "
+                                      "B200 hot path; crop people yourself and call predict() on the crops")
+        if self.enable_tensorrt:
+            raise NotImplementedError("enable_tensorrt: the B200 engine already occupies the TensorRT seam")
+        if model_name in ('HRNet', 'hrnet'):
+            arch = "hrnet"
+        elif model_name in ('PoseResNet', 'poseresnet', 'ResNet', 'resnet'):
+            arch = "poseresnet"
+        else:
+            raise ValueError('Wrong model name.')                       # SimpleHRNet.py:114
+        dev = str(self.device)
+        if dev == 'cpu':
+            raise ValueError("Wrong device name. The B200 engine is CUDA-only: use torch.device('cuda[:k]')")
+        if not dev.startswith('cuda') or ',' in dev:
+            raise ValueError('Wrong device name.')                      # SimpleHRNet.py:139
+        self.model = B200Engine(arch, c, nof_joints, resolution, max_batch_size, self.device, flags=engine_flags)
+        self.device = self.model.device
+        checkpoint = checkpoint_path if isinstance(checkpoint_path, dict) else \
+            torch.load(checkpoint_path, map_location="cpu")
+        if 'model' in checkpoint:                                        # SimpleHRNet.py:118-121
+            self.model.load_state_dict(checkpoint['model'])
+        else:
+            self.model.load_state_dict(checkpoint)
+        self._mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1, 1)
+        self._std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1, 1)
+
+    # ToTensor + Normalize of SimpleHRNet.py:149-153 on one RGB uint8 HxWx3 image
+    def _transform(self, rgb_u8):
+        t = torch.from_numpy(np.ascontiguousarray(rgb_u8)).permute(2, 0, 1).to(torch.float32).div(255)
+        return (t - self._mean) / self._std
+
+    def _prep(self, image):
+        import cv2
+        interp = cv2.INTER_CUBIC if self.interpolation is None else self.interpolation
+        if self.resolution is not None:
+            image = cv2.resize(image, (self.resolution[1], self.resolution[0]), interpolation=interp)
+        return self._transform(cv2.cvtColor(image, cv2.COLOR_BGR2RGB))
+
+    def predict(self, image):
+        """Same contract as SimpleHRNet.predict (SimpleHRNet.py:174-210): HxWx3 or NxHxWx3 BGR uint8;
+        returns pts [(n,1,)| (1,)] [J,3] as (y, x, confidence) and optionally heat-maps / boxes."""
+        if len(image.shape) == 3:
+            return self._predict_single(image)
+        elif len(image.shape) == 4:
+            return self._predict_batch(image)
+        else:
+            raise ValueError('Wrong image format.')
+
+    def _run(self, images, boxes):
+        n = images.shape[0]
+        J, Hh, Wh = self.nof_joints, self.resolution[0] // 4, self.resolution[1] // 4
+        pts = np.empty((n, J, 3), dtype=np.float32)
+        heatmaps = np.zeros((n, J, Hh, Wh), dtype=np.float32)
+        images = images.to(self.device)
+        for i in range(0, n, self.max_batch_size):                      # SimpleHRNet.py:288-294
+            sl = slice(i, min(n, i + self.max_batch_size))
+            joints, _idx, hm = self.model.forward_decode(images[sl], boxes=boxes[sl],
+                                                         return_heatmaps=self.return_heatmaps)
+            pts[sl] = joints.cpu().numpy()
+            if hm is not None:
+                heatmaps[sl] = hm.cpu().numpy()
+        return heatmaps, pts
+
+    def _pack(self, heatmaps, boxes, pts):
+        res = list()
+        if self.return_heatmaps:
+            res.append(heatmaps)
+        if self.return_bounding_boxes:
+            res.append(boxes)
+        res.append(pts)
+        return res if len(res) > 1 else res[0]
+
+    def _predict_single(self, image):
+        old_res = image.shape
+        images = self._prep(image).unsqueeze(dim=0)
+        boxes = np.asarray([[0, 0, old_res[1], old_res[0]]], dtype=np.float32)   # [x1, y1, x2, y2]
+        heatmaps, pts = self._run(images, boxes)
+        return self._pack(heatmaps, boxes, pts)
+
+    def _predict_batch(self, images):
+        if images.shape[0] == 0:
+            raise ValueError  # the reference reaches `raise ValueError` for an empty non-multiperson batch (:487)
+        old_res = images[0].shape
+        x = torch.empty(images.shape[0], 3, self.resolution[0], self.resolution[1])
+        for i, image in enumerate(images):
+            x[i] = self._prep(image)
+        boxes = np.repeat(np.asarray([[0, 0, old_res[1], old_res[0]]], dtype=np.float32), len(images), axis=0)
+        heatmaps, pts = self._run(x, boxes)
+        pts = np.expand_dims(pts, axis=1)                                # SimpleHRNet.py:475
+        return self._pack(heatmaps, boxes, pts)

@@ -1,0 +1,127 @@
+// Internal types shared by the plan builder, the kernel launchers and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace hrnet {
+
+enum OpKind : int {
+  OP_STEM = 0,     // 3x3 s2 conv on the NCHW fp32 network input -> NHWC fp16 (+BN+ReLU), SIMT
+  OP_CONV = 1,     // kxk conv (k in {1,3}, stride in {1,2}) NHWC fp16 -> NHWC fp16/fp32, BN, +residual, ReLU
+  OP_FUSE = 2,     // out = ReLU(sum_j nearest_up(src_j)) (exchange-unit sum, hrnet.py:60-69)
+  OP_HEAD = 3,     // 1x1 conv + bias, NHWC fp16 -> NCHW fp32 heatmaps
+  OP_ARGMAX = 4,   // per-joint argmax decode -> (y, x, conf) + flat index
+  OP_MAXPOOL = 5,  // 3x3 s2 p1 max pool NHWC fp16 (PoseResNet)
+  OP_STEM7 = 6,    // 7x7 s2 p3 conv on the NCHW fp32 input (PoseResNet)
+};
+
+enum DType : int { DT_F16 = 0, DT_F32 = 1 };
+
+struct TensorInfo {
+  int C = 0, H = 0, W = 0;
+  int dtype = DT_F16;
+  size_t offset = 0;  // byte offset in the activation workspace; (size_t)-1 for external tensors
+  size_t bytes(int n) const { return (size_t)n * C * H * W * (dtype == DT_F16 ? 2 : 4); }
+};
+
+// One weight-carrying layer: what the Python packer must write where.
+struct ParamInfo {
+  std::string conv_key;  // state_dict prefix of the conv ("stage2.0.branches.0.0.conv1"); weight = key + ".weight"
+  std::string bn_key;    // state_dict prefix of the BN ("...bn1"), empty -> scale = 1, bias = conv bias (or 0)
+  int cout = 0, cin = 0, kh = 0, kw = 0;
+  int transposed = 0;    // 1: ConvTranspose2d weight [Cin, Cout, kh, kw]
+  int has_bias = 0;      // conv has its own bias (final_layer)
+  int w_f32 = 0;         // weights stored as fp32 (stem conv1, head) instead of fp16
+  size_t w_offset = 0;   // bytes into the packed weight buffer: [cout][kh][kw][cin]
+  size_t scale_offset = 0, bias_offset = 0;  // fp32 [cout] each
+};
+
+struct ConvTcCfg {
+  int kc = 0;        // channels per k-block (64 / 32 / 16) -> swizzle 128 / 64 / 32 B
+  int bps = 0;       // k-blocks per pipeline stage
+  int n_tile = 0;    // output channels per CTA tile
+  int stages = 0;
+  int smem_bytes = 0;
+  int tmem_cols = 0;
+};
+
+struct Op {
+  int kind = 0;
+  std::string name;
+  int in = -1, out = -1, res = -1;  // tensor ids
+  int param = -1;
+  int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+  int relu = 0;
+  // fuse
+  int nsrc = 0;
+  int src[4] = {-1, -1, -1, -1};
+  int shift[4] = {0, 0, 0, 0};
+  // scheduling
+  int stream = 0;
+  std::vector<int> deps;       // ops that must complete before this one
+  bool needs_event = false;    // some dependant runs on another stream
+  // tcgen05 path
+  bool use_tc = false;
+  ConvTcCfg tc;
+  CUtensorMap tmA, tmB;
+};
+
+// device-side parameter block for the tcgen05 implicit-GEMM conv
+struct ConvTcParams {
+  int M_total, OH, OW, OHW;
+  int ksize, stride, pad_h, pad_w;   // pad_* = leading (top / left) padding
+  int sub, sub_a, sub_b;             // transposed-conv sub-pixel phase: out pixel (2i+a, 2j+b)
+  int Cin, Cout;
+  int kc, cpt, nkb, bps;
+  int n_tile, n_tiles, m_tiles;
+  int stages;
+  int relu, out_f32;
+  int tmem_cols;
+  int a_blk_bytes, b_blk_bytes;
+  const float* scale;
+  const float* bias;
+  const __half* residual;
+  void* out;
+};
+
+// device-side parameter block for the SIMT fallback conv (debug path / odd shapes)
+struct ConvSimtParams {
+  int N, IH, IW, OH, OW, Cin, Cout, ksize, stride, pad, relu, out_f32;
+  const __half* in;
+  const __half* w;  // [Cout][k][k][Cin]
+  const float* scale;
+  const float* bias;
+  const __half* residual;
+  void* out;
+};
+
+struct FuseParams {
+  int N, H, W, C, nsrc, relu;
+  const void* src[4];
+  int shift[4];
+  int f32[4];
+  __half* out;
+};
+
+// launchers (implemented in the .cu files)
+cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int smem_bytes,
+                           int grid, cudaStream_t st);
+cudaError_t launch_conv_simt(const ConvSimtParams& p, cudaStream_t st);
+cudaError_t launch_stem(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
+                        int N, int H, int W, cudaStream_t st);
+cudaError_t launch_fuse(const FuseParams& p, cudaStream_t st);
+cudaError_t launch_head(const __half* in, const float* w, const float* bias, float* out_nchw, int N, int HW, int Cin,
+                        int J, cudaStream_t st);
+cudaError_t launch_argmax(const float* hm, int N, int J, int Hh, int Wh, const float* boxes, float* joints,
+                          int32_t* idx, cudaStream_t st);
+cudaError_t launch_maxpool(const __half* in, __half* out, int N, int IH, int IW, int C, cudaStream_t st);
+cudaError_t launch_stem7(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
+                         int N, int H, int W, cudaStream_t st);
+cudaError_t conv_tc_set_attributes(int max_smem);
+
+}  // namespace hrnet

@@ -1,0 +1,937 @@
+// Plan = the static execution schedule of one network instance (arch, width, resolution, max batch):
+// tensors placed in a caller-owned activation workspace, weight-carrying layers placed in a
+// caller-owned packed weight buffer, an ordered op list with stream assignment and dependencies,
+// TMA descriptors for every tensor-core conv, and a cached CUDA graph per batch size.
+//
+// The graph that is built restates the *structure* of the reference modules
+//   HRNet.forward        models_/hrnet.py:157-189   (stem, layer1, transitions, stages, head)
+//   StageModule.forward  models_/hrnet.py:55-71     (branches, exchange unit)
+//   Bottleneck / BasicBlock  models_/modules.py:20-40 / 56-72
+//   PoseResNet.forward   models_/poseresnet.py:108-122
+// with BN folded to a per-channel fp32 (scale, bias) epilogue, ReLU / residual-add fused into the
+// producing conv, and the four HRNet branches running concurrently on forked streams.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <sstream>
+
+#include "../../include/hrnet_b200.h"
+#include "hrnet_internal.h"
+
+namespace hrnet {
+
+thread_local std::string g_last_error;
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace hrnet
+
+using namespace hrnet;
+
+struct HrnetPlan {
+  HrnetDesc desc{};
+  std::vector<TensorInfo> tensors;
+  std::vector<ParamInfo> params;
+  std::vector<int> param_kind, param_a, param_b;  // deconv sub-pixel phases
+  std::vector<Op> ops;
+  size_t act_bytes = 0, weight_bytes = 0;
+  int t_input = -1, t_heatmaps = -1;
+  int Hh = 0, Wh = 0;
+  // staging for hrnet_forward_host (inside the workspace)
+  size_t off_in_stage = 0, off_joints = 0, off_idx = 0, off_boxes = 0;
+  // bound state
+  bool bound = false;
+  uint8_t* wbase = nullptr;
+  uint8_t* abase = nullptr;
+  int num_sms = 0;
+  cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> events;
+  cudaEvent_t fork_ev = nullptr;
+  std::map<int, cudaGraphExec_t> graphs;
+  int launch_count = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Builder
+// ------------------------------------------------------------------------------------------------
+struct Builder {
+  HrnetPlan& P;
+  int maxb;
+  bool fuse_f16;
+  // arenas: 0 = pre (stem / layer1 / staging), 1 and 2 alternate per stage module
+  size_t arena_off[3] = {0, 0, 0};   // bump pointer (bytes at max batch)
+  size_t arena_max[3] = {0, 0, 0};
+  std::vector<int> tensor_arena;
+  std::vector<int> producer;         // tensor id -> op that writes it (-1 external)
+  std::vector<int> last_on_stream = std::vector<int>(4, -1);
+  size_t wcur = 0;
+
+  explicit Builder(HrnetPlan& p) : P(p), maxb(p.desc.max_batch), fuse_f16((p.desc.flags & HRNET_FLAG_FUSE_F16) != 0) {}
+
+  int new_tensor(int arena, int C, int H, int W, int dtype = DT_F16) {
+    TensorInfo t;
+    t.C = C; t.H = H; t.W = W; t.dtype = dtype;
+    if (arena >= 0) {
+      t.offset = arena_off[arena];
+      arena_off[arena] += align_up(t.bytes(maxb), 1024);
+      arena_max[arena] = std::max(arena_max[arena], arena_off[arena]);
+    } else {
+      t.offset = (size_t)-1;
+    }
+    P.tensors.push_back(t);
+    tensor_arena.push_back(arena);
+    producer.push_back(-1);
+    return (int)P.tensors.size() - 1;
+  }
+  void reset_arena(int a) { arena_off[a] = 0; }
+
+  int new_param(const std::string& conv_key, const std::string& bn_key, int cout, int cin, int kh, int kw,
+                bool has_bias = false, bool w_f32 = false, int kind = 0, int sa = 0, int sb = 0) {
+    ParamInfo pi;
+    pi.conv_key = conv_key; pi.bn_key = bn_key;
+    pi.cout = cout; pi.cin = cin; pi.kh = kh; pi.kw = kw;
+    pi.has_bias = has_bias; pi.w_f32 = w_f32; pi.transposed = kind;
+    wcur = align_up(wcur, 1024);
+    pi.w_offset = wcur;
+    wcur += (size_t)cout * cin * kh * kw * (w_f32 ? 4 : 2);
+    wcur = align_up(wcur, 256);
+    pi.scale_offset = wcur; wcur += (size_t)cout * 4;
+    wcur = align_up(wcur, 256);
+    pi.bias_offset = wcur; wcur += (size_t)cout * 4;
+    P.params.push_back(pi);
+    P.param_kind.push_back(kind); P.param_a.push_back(sa); P.param_b.push_back(sb);
+    return (int)P.params.size() - 1;
+  }
+
+  int push(Op op) {
+    const int id = (int)P.ops.size();
+    auto dep_on = [&](int t) {
+      if (t < 0) return;
+      int pr = producer[t];
+      if (pr >= 0 && std::find(op.deps.begin(), op.deps.end(), pr) == op.deps.end()) op.deps.push_back(pr);
+    };
+    dep_on(op.in); dep_on(op.res);
+    for (int j = 0; j < op.nsrc; ++j) dep_on(op.src[j]);
+    if (P.desc.flags & HRNET_FLAG_SERIAL) op.stream = 0;
+    if (op.out >= 0) producer[op.out] = id;
+    last_on_stream[op.stream] = id;
+    P.ops.push_back(op);
+    return id;
+  }
+
+  // conv + BN (+res) (+relu); returns the output tensor
+  int conv(const std::string& name, const std::string& conv_key, const std::string& bn_key, int in, int cout, int k,
+           int stride, bool relu, int res, int out_tensor, int arena, int stream, int out_dtype = DT_F16) {
+    const TensorInfo& ti = P.tensors[in];
+    const int OH = ti.H / stride, OW = ti.W / stride;
+    int out = out_tensor >= 0 ? out_tensor : new_tensor(arena, cout, OH, OW, out_dtype);
+    Op op;
+    op.kind = OP_CONV; op.name = name; op.in = in; op.out = out; op.res = res;
+    op.cin = ti.C; op.cout = cout; op.k = k; op.stride = stride; op.pad = k / 2; op.relu = relu ? 1 : 0;
+    op.stream = stream;
+    op.param = new_param(conv_key, bn_key, cout, ti.C, k, k);
+    push(op);
+    return out;
+  }
+};
+
+void choose_tc_cfg(Op& op, uint32_t flags) {
+  op.use_tc = false;
+  if (flags & HRNET_FLAG_FORCE_SIMT) return;
+  if (op.kind != OP_CONV) return;
+  if (op.cin % 16 || op.cout % 16) return;
+  if (!(op.k == 1 || op.k == 3 || op.k == 2)) return;
+  ConvTcCfg c;
+  c.kc = op.cin % 64 == 0 ? 64 : (op.cin % 32 == 0 ? 32 : 16);
+  int nt = op.cout;
+  if (nt > 256) {
+    int d = 2;
+    while (op.cout % d || (op.cout / d) > 256 || (op.cout / d) % 16) ++d;
+    nt = op.cout / d;
+  }
+  c.n_tile = nt;
+  c.bps = 64 / c.kc;
+  const int a_blk = (int)align_up((size_t)128 * c.kc * 2, 1024);
+  const int b_blk = (int)align_up((size_t)nt * c.kc * 2, 1024);
+  const int stage = c.bps * (a_blk + b_blk);
+  const int fixed = 1024 + 2 * op.cout * 4 + 256;
+  const int budget = 200 * 1024;
+  const int nkb = op.k * op.k * (op.cin / c.kc);
+  const int kstages = (nkb + c.bps - 1) / c.bps;
+  c.stages = std::max(2, std::min({8, (budget - fixed) / stage, std::max(2, kstages * 2)}));
+  c.smem_bytes = fixed + c.stages * stage;
+  int cols = 32;
+  while (cols < 2 * nt) cols *= 2;
+  c.tmem_cols = cols;
+  op.tc = c;
+  op.use_tc = true;
+}
+
+// ---- HRNet ------------------------------------------------------------------------------------
+int build_hrnet(HrnetPlan& P) {
+  const HrnetDesc& d = P.desc;
+  const int c = d.c, J = d.nof_joints, H = d.height, W = d.width;
+  Builder b(P);
+  const int dt_term = b.fuse_f16 ? DT_F16 : DT_F32;
+
+  P.t_input = b.new_tensor(-1, 3, H, W, DT_F32);
+  // stem (hrnet.py:158-163)
+  int s1 = b.new_tensor(0, 64, H / 2, W / 2);
+  {
+    Op op; op.kind = OP_STEM; op.name = "conv1"; op.in = P.t_input; op.out = s1; op.cin = 3; op.cout = 64; op.k = 3;
+    op.stride = 2; op.pad = 1; op.relu = 1; op.stream = 0;
+    op.param = b.new_param("conv1", "bn1", 64, 3, 3, 3, false, true);
+    b.push(op);
+  }
+  int x = b.conv("conv2", "conv2", "bn2", s1, 64, 3, 2, true, -1, -1, 0, 0);
+  // layer1: 4 x Bottleneck (hrnet.py:86-95, modules.py:20-40)
+  {
+    const int h4 = H / 4, w4 = W / 4;
+    int ta = b.new_tensor(0, 64, h4, w4), tb = b.new_tensor(0, 64, h4, w4);
+    int ty[2] = {b.new_tensor(0, 256, h4, w4), b.new_tensor(0, 256, h4, w4)};
+    int tr = b.new_tensor(0, 256, h4, w4);
+    for (int k = 0; k < 4; ++k) {
+      const std::string p = "layer1." + std::to_string(k);
+      b.conv(p + ".conv1", p + ".conv1", p + ".bn1", x, 64, 1, 1, true, -1, ta, 0, 0);
+      b.conv(p + ".conv2", p + ".conv2", p + ".bn2", ta, 64, 3, 1, true, -1, tb, 0, 0);
+      int res = x;
+      if (k == 0) {
+        b.conv(p + ".downsample", p + ".downsample.0", p + ".downsample.1", x, 256, 1, 1, false, -1, tr, 0, 0);
+        res = tr;
+      }
+      b.conv(p + ".conv3", p + ".conv3", p + ".bn3", tb, 256, 1, 1, true, res, ty[k & 1], 0, 0);
+      x = ty[k & 1];
+    }
+  }
+  // transition1 (hrnet.py:98-109) -> arena 2 (the "previous" arena of module 0, which uses arena 1)
+  std::vector<int> xs;
+  xs.push_back(b.conv("transition1.0", "transition1.0.0", "transition1.0.1", x, c, 3, 1, true, -1, -1, 2, 0));
+  xs.push_back(b.conv("transition1.1", "transition1.1.0.0", "transition1.1.0.1", x, 2 * c, 3, 2, true, -1, -1, 2, 1));
+
+  int module_idx = 0;
+  auto stage_module = [&](const std::string& prefix, int S, int O) {
+    const int arena = 1 + (module_idx & 1);
+    b.reset_arena(arena);
+    ++module_idx;
+    std::vector<int> ys(S);
+    for (int i = 0; i < S; ++i) {
+      const TensorInfo ti = P.tensors[xs[i]];
+      int t = b.new_tensor(arena, ti.C, ti.H, ti.W);
+      int y[2] = {b.new_tensor(arena, ti.C, ti.H, ti.W), b.new_tensor(arena, ti.C, ti.H, ti.W)};
+      int cur = xs[i];
+      for (int k = 0; k < 4; ++k) {
+        const std::string p = prefix + ".branches." + std::to_string(i) + "." + std::to_string(k);
+        b.conv(p + ".conv1", p + ".conv1", p + ".bn1", cur, ti.C, 3, 1, true, -1, t, arena, i);
+        b.conv(p + ".conv2", p + ".conv2", p + ".bn2", t, ti.C, 3, 1, true, cur, y[k & 1], arena, i);
+        cur = y[k & 1];
+      }
+      ys[i] = cur;
+    }
+    std::vector<int> outs(O);
+    for (int i = 0; i < O; ++i) {
+      const TensorInfo ti = P.tensors[ys[i]];
+      Op f; f.kind = OP_FUSE; f.name = prefix + ".fuse." + std::to_string(i); f.relu = 1; f.stream = i; f.nsrc = S;
+      f.cout = ti.C;
+      for (int j = 0; j < S; ++j) {
+        const std::string p = prefix + ".fuse_layers." + std::to_string(i) + "." + std::to_string(j);
+        if (j == i) {
+          f.src[j] = ys[j]; f.shift[j] = 0;
+        } else if (j > i) {
+          // 1x1 conv + BN at the low resolution; the nearest upsample is folded into the fuse read (hrnet.py:30-35)
+          f.src[j] = b.conv(p, p + ".0", p + ".1", ys[j], ti.C, 1, 1, false, -1, -1, arena, i, dt_term);
+          f.shift[j] = j - i;
+        } else {
+          int t = ys[j];
+          const int cj = P.tensors[ys[j]].C;
+          for (int k = 0; k < i - j - 1; ++k)
+            t = b.conv(p + "." + std::to_string(k), p + "." + std::to_string(k) + ".0", p + "." + std::to_string(k) + ".1",
+                       t, cj, 3, 2, true, -1, -1, arena, i);
+          const int k = i - j - 1;
+          f.src[j] = b.conv(p + "." + std::to_string(k), p + "." + std::to_string(k) + ".0",
+                            p + "." + std::to_string(k) + ".1", t, ti.C, 3, 2, false, -1, -1, arena, i, dt_term);
+          f.shift[j] = 0;
+        }
+      }
+      f.out = b.new_tensor(arena, ti.C, ti.H, ti.W);
+      outs[i] = f.out;
+      b.push(f);
+    }
+    xs = outs;
+    return arena;
+  };
+
+  int ar = stage_module("stage2.0", 2, 2);
+  xs.push_back(b.conv("transition2.2", "transition2.2.0.0", "transition2.2.0.1", xs.back(), 4 * c, 3, 2, true, -1, -1,
+                      ar, 2));
+  for (int m = 0; m < 4; ++m) ar = stage_module("stage3." + std::to_string(m), 3, 3);
+  xs.push_back(b.conv("transition3.3", "transition3.3.0.0", "transition3.3.0.1", xs.back(), 8 * c, 3, 2, true, -1, -1,
+                      ar, 3));
+  stage_module("stage4.0", 4, 4);
+  stage_module("stage4.1", 4, 4);
+  stage_module("stage4.2", 4, 1);
+
+  // head (hrnet.py:155,187) + decode (SimpleHRNet.py:296-308)
+  P.Hh = H / 4; P.Wh = W / 4;
+  P.t_heatmaps = b.new_tensor(0, J, P.Hh, P.Wh, DT_F32);
+  {
+    Op op; op.kind = OP_HEAD; op.name = "final_layer"; op.in = xs[0]; op.out = P.t_heatmaps; op.cin = c; op.cout = J;
+    op.k = 1; op.stream = 0;
+    op.param = b.new_param("final_layer", "", J, c, 1, 1, true, true);
+    b.push(op);
+  }
+  {
+    Op op; op.kind = OP_ARGMAX; op.name = "argmax_decode"; op.in = P.t_heatmaps; op.cout = J; op.stream = 0;
+    b.push(op);
+  }
+  // host staging (forward_host): input, joints, idx, boxes
+  const size_t pre = b.arena_max[0];
+  size_t cur = pre;
+  P.off_in_stage = cur; cur += align_up((size_t)b.maxb * 3 * H * W * 4, 1024);
+  P.off_joints = cur;   cur += align_up((size_t)b.maxb * J * 3 * 4, 1024);
+  P.off_idx = cur;      cur += align_up((size_t)b.maxb * J * 4, 1024);
+  P.off_boxes = cur;    cur += align_up((size_t)b.maxb * 4 * 4, 1024);
+  const size_t a0 = cur, a1 = b.arena_max[1], a2 = b.arena_max[2];
+  for (size_t i = 0; i < P.tensors.size(); ++i) {
+    const int a = b.tensor_arena[i];
+    if (a == 1) P.tensors[i].offset += a0;
+    if (a == 2) P.tensors[i].offset += a0 + a1;
+  }
+  P.act_bytes = a0 + a1 + a2;
+  P.weight_bytes = align_up(b.wcur, 1024);
+  return 0;
+}
+
+// ---- PoseResNet (models_/poseresnet.py) -------------------------------------------------------
+int build_poseresnet(HrnetPlan& P) {
+  const HrnetDesc& d = P.desc;
+  const int J = d.nof_joints, H = d.height, W = d.width;
+  int layers[4];
+  if (d.c == 50) { int l[4] = {3, 4, 6, 3}; memcpy(layers, l, sizeof l); }
+  else if (d.c == 101) { int l[4] = {3, 4, 23, 3}; memcpy(layers, l, sizeof l); }
+  else if (d.c == 152) { int l[4] = {3, 8, 36, 3}; memcpy(layers, l, sizeof l); }
+  else return fail(HRNET_E_INVALID, "PoseResNet size must be 50, 101 or 152 (18/34 are broken in the reference, modules.py:51)");
+  Builder b(P);
+  P.t_input = b.new_tensor(-1, 3, H, W, DT_F32);
+  int s1 = b.new_tensor(0, 64, H / 2, W / 2);
+  {
+    Op op; op.kind = OP_STEM7; op.name = "conv1"; op.in = P.t_input; op.out = s1; op.cin = 3; op.cout = 64; op.k = 7;
+    op.stride = 2; op.pad = 3; op.relu = 1;
+    op.param = b.new_param("conv1", "bn1", 64, 3, 7, 7, false, true);
+    b.push(op);
+  }
+  int x = b.new_tensor(0, 64, H / 4, W / 4);
+  {
+    Op op; op.kind = OP_MAXPOOL; op.name = "maxpool"; op.in = s1; op.out = x; op.cin = 64; op.cout = 64; op.k = 3;
+    op.stride = 2; op.pad = 1;
+    b.push(op);
+  }
+  int inplanes = 64;
+  const int planes_l[4] = {64, 128, 256, 512};
+  for (int li = 0; li < 4; ++li) {
+    const int planes = planes_l[li];
+    const int stride = li == 0 ? 1 : 2;
+    for (int k = 0; k < layers[li]; ++k) {
+      const std::string p = "layer" + std::to_string(li + 1) + "." + std::to_string(k);
+      const int s = k == 0 ? stride : 1;
+      const bool down = k == 0 && (stride != 1 || inplanes != planes * 4);
+      int a = b.conv(p + ".conv1", p + ".conv1", p + ".bn1", x, planes, 1, 1, true, -1, -1, 0, 0);
+      int bb = b.conv(p + ".conv2", p + ".conv2", p + ".bn2", a, planes, 3, s, true, -1, -1, 0, 0);
+      int res = x;
+      if (down) res = b.conv(p + ".downsample", p + ".downsample.0", p + ".downsample.1", x, planes * 4, 1, s, false, -1, -1, 0, 0);
+      x = b.conv(p + ".conv3", p + ".conv3", p + ".bn3", bb, planes * 4, 1, 1, true, res, -1, 0, 0);
+      inplanes = planes * 4;
+    }
+  }
+  // 3 x ConvTranspose2d(4, s2, p1) + BN + ReLU as four 2x2 sub-pixel convs each (poseresnet.py:81-106)
+  for (int dl = 0; dl < 3; ++dl) {
+    const TensorInfo ti = P.tensors[x];
+    int out = b.new_tensor(0, 256, ti.H * 2, ti.W * 2);
+    for (int a = 0; a < 2; ++a)
+      for (int bb = 0; bb < 2; ++bb) {
+        Op op; op.kind = OP_CONV; op.name = "deconv" + std::to_string(dl) + "." + std::to_string(a) + std::to_string(bb);
+        op.in = x; op.out = out; op.cin = ti.C; op.cout = 256; op.k = 2; op.stride = 1;
+        op.pad = 100 + a * 2 + bb;  // marks a sub-pixel phase: pad_lo = 1 - a (rows), 1 - b (cols)
+        op.relu = 1; op.stream = 0;
+        op.param = b.new_param("deconv_layers." + std::to_string(3 * dl), "deconv_layers." + std::to_string(3 * dl + 1),
+                               256, ti.C, 2, 2, false, false, 1, a, bb);
+        b.push(op);
+      }
+    x = out;
+  }
+  P.Hh = H / 4; P.Wh = W / 4;
+  P.t_heatmaps = b.new_tensor(0, J, P.Hh, P.Wh, DT_F32);
+  {
+    Op op; op.kind = OP_HEAD; op.name = "final_layer"; op.in = x; op.out = P.t_heatmaps; op.cin = 256; op.cout = J; op.k = 1;
+    op.param = b.new_param("final_layer", "", J, 256, 1, 1, true, true);
+    b.push(op);
+  }
+  {
+    Op op; op.kind = OP_ARGMAX; op.name = "argmax_decode"; op.in = P.t_heatmaps; op.cout = J;
+    b.push(op);
+  }
+  size_t cur = b.arena_max[0];
+  P.off_in_stage = cur; cur += align_up((size_t)b.maxb * 3 * H * W * 4, 1024);
+  P.off_joints = cur;   cur += align_up((size_t)b.maxb * J * 3 * 4, 1024);
+  P.off_idx = cur;      cur += align_up((size_t)b.maxb * J * 4, 1024);
+  P.off_boxes = cur;    cur += align_up((size_t)b.maxb * 4 * 4, 1024);
+  P.act_bytes = cur;
+  P.weight_bytes = align_up(b.wcur, 1024);
+  return 0;
+}
+
+void finalize_schedule(HrnetPlan& P) {
+  for (auto& op : P.ops) choose_tc_cfg(op, P.desc.flags);
+  // every stream's last op must be joined back into stream 0 before the head runs
+  int head = -1;
+  for (size_t i = 0; i < P.ops.size(); ++i) if (P.ops[i].kind == OP_HEAD) head = (int)i;
+  std::vector<int> last(4, -1);
+  for (int i = 0; i < head; ++i) last[P.ops[i].stream] = i;
+  for (int s = 1; s < 4; ++s)
+    if (last[s] >= 0 && std::find(P.ops[head].deps.begin(), P.ops[head].deps.end(), last[s]) == P.ops[head].deps.end())
+      P.ops[head].deps.push_back(last[s]);
+  for (auto& op : P.ops)
+    for (int dpi : op.deps)
+      if (P.ops[dpi].stream != op.stream) P.ops[dpi].needs_event = true;
+  P.launch_count = (int)P.ops.size();
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor encoding (driver entry points resolved at run time: no link-time libcuda dependency,
+// so the library loads on a CPU-only box)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+int g_driver_version = 0;
+
+int load_driver_fns() {
+  if (g_encode_tiled && g_encode_im2col) return 0;
+  cudaDriverEntryPointQueryResult q;
+  void* f = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f)
+    return fail(HRNET_E_CUDA, std::string("cuTensorMapEncodeTiled unavailable: ") + cudaGetErrorString(e));
+  g_encode_tiled = (EncodeTiledFn)f;
+  f = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f)
+    return fail(HRNET_E_CUDA, std::string("cuTensorMapEncodeIm2col unavailable: ") + cudaGetErrorString(e));
+  g_encode_im2col = (EncodeIm2colFn)f;
+  cudaDriverGetVersion(&g_driver_version);
+  return 0;
+}
+
+CUtensorMapSwizzle swizzle_for(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// weights [Cout][K] fp16, box {kc, n_tile}
+int encode_weights(CUtensorMap* tm, const void* w, int cout, int K, int kc, int n_tile) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)n_tile};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HRNET_E_CUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+  return 0;
+}
+
+// activations NHWC fp16 [N, IH, IW, C] as an im2col map: 128 output pixels x kc channels per load.
+// pad_lo / pad_hi per spatial dim allow the asymmetric 2x2 sub-pixel phases of the transposed conv.
+int encode_im2col(CUtensorMap* tm, const void* act, int N, int IH, int IW, int C, int kc, int ksize, int stride,
+                  int pad_lo_h, int pad_hi_h, int pad_lo_w, int pad_hi_w) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)IW, (cuuint64_t)IH, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)IW * C * 2, (cuuint64_t)IH * IW * C * 2};
+  int lower[2] = {-pad_lo_w, -pad_lo_h};
+  int upper[2] = {pad_hi_w - (ksize - 1), pad_hi_h - (ksize - 1)};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(act), dims, strides, lower,
+                               upper, (cuuint32_t)kc, 128, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(HRNET_E_CUDA, "cuTensorMapEncodeIm2col failed: " + std::to_string((int)r));
+  // Known driver issue (<= 13.1) for im2col maps over tensors smaller than 128 KiB: clear bit 21 of
+  // the second descriptor word (same workaround NVIDIA's own CuTe im2col descriptor builder applies).
+  if (g_driver_version <= 13010 && (size_t)N * IH * IW * C * 2 < 131072)
+    reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return 0;
+}
+
+void conv_geometry(const Op& op, int& pad_lo_h, int& pad_hi_h, int& pad_lo_w, int& pad_hi_w, int& sub, int& sa, int& sb) {
+  sub = 0; sa = sb = 0;
+  if (op.pad >= 100) {  // transposed-conv sub-pixel phase
+    sub = 1; sa = (op.pad - 100) / 2; sb = (op.pad - 100) % 2;
+    pad_lo_h = 1 - sa; pad_hi_h = sa; pad_lo_w = 1 - sb; pad_hi_w = sb;
+  } else {
+    pad_lo_h = pad_hi_h = pad_lo_w = pad_hi_w = op.pad;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* hrnet_last_error(void) { return g_last_error.c_str(); }
+
+int hrnet_plan_create(const HrnetDesc* desc, HrnetPlan** out) {
+  if (!desc || !out) return fail(HRNET_E_INVALID, "null argument");
+  if (desc->height <= 0 || desc->width <= 0 || desc->height % 32 || desc->width % 32)
+    return fail(HRNET_E_INVALID, "resolution must be a positive multiple of 32 (exact x8 down/up-sampling)");
+  if (desc->max_batch <= 0) return fail(HRNET_E_INVALID, "max_batch must be positive");
+  if (desc->nof_joints <= 0 || desc->nof_joints > 32) return fail(HRNET_E_INVALID, "nof_joints must be in [1, 32]");
+  HrnetPlan* P = new HrnetPlan();
+  P->desc = *desc;
+  int rc;
+  if (desc->arch == HRNET_ARCH_HRNET) {
+    if (desc->c <= 0 || desc->c % 16) { delete P; return fail(HRNET_E_INVALID, "HRNet width c must be a positive multiple of 16"); }
+    rc = build_hrnet(*P);
+  } else if (desc->arch == HRNET_ARCH_POSERESNET) {
+    rc = build_poseresnet(*P);
+  } else {
+    delete P;
+    return fail(HRNET_E_INVALID, "Wrong model name.");  // SimpleHRNet.py:114
+  }
+  if (rc) { delete P; return rc; }
+  finalize_schedule(*P);
+  *out = P;
+  return HRNET_OK;
+}
+
+void hrnet_plan_destroy(HrnetPlan* P) {
+  if (!P) return;
+  for (auto& kv : P->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto e : P->events) if (e) cudaEventDestroy(e);
+  if (P->fork_ev) cudaEventDestroy(P->fork_ev);
+  for (auto s : P->side) if (s) cudaStreamDestroy(s);
+  delete P;
+}
+
+int hrnet_plan_workspace_bytes(const HrnetPlan* P, size_t* act_bytes, size_t* weight_bytes) {
+  if (!P) return fail(HRNET_E_INVALID, "null plan");
+  if (act_bytes) *act_bytes = P->act_bytes;
+  if (weight_bytes) *weight_bytes = P->weight_bytes;
+  return HRNET_OK;
+}
+
+int hrnet_plan_num_params(const HrnetPlan* P) { return P ? (int)P->params.size() : HRNET_E_INVALID; }
+
+int hrnet_plan_launch_count(const HrnetPlan* P) { return P ? P->launch_count : HRNET_E_INVALID; }
+
+int hrnet_plan_param_info(const HrnetPlan* P, int i, HrnetParamInfo* out) {
+  if (!P || !out || i < 0 || i >= (int)P->params.size()) return fail(HRNET_E_INVALID, "bad param index");
+  const ParamInfo& pi = P->params[i];
+  memset(out, 0, sizeof(*out));
+  snprintf(out->conv_key, sizeof(out->conv_key), "%s", pi.conv_key.c_str());
+  snprintf(out->bn_key, sizeof(out->bn_key), "%s", pi.bn_key.c_str());
+  out->cout = pi.cout; out->cin = pi.cin; out->kh = pi.kh; out->kw = pi.kw;
+  out->kind = P->param_kind[i]; out->sub_a = P->param_a[i]; out->sub_b = P->param_b[i];
+  out->has_bias = pi.has_bias; out->w_f32 = pi.w_f32;
+  out->w_offset = pi.w_offset; out->scale_offset = pi.scale_offset; out->bias_offset = pi.bias_offset;
+  return HRNET_OK;
+}
+
+int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* needed) {
+  if (!P) return fail(HRNET_E_INVALID, "null plan");
+  std::ostringstream o;
+  o << "{\"arch\":" << P->desc.arch << ",\"c\":" << P->desc.c << ",\"nof_joints\":" << P->desc.nof_joints
+    << ",\"height\":" << P->desc.height << ",\"width\":" << P->desc.width << ",\"max_batch\":" << P->desc.max_batch
+    << ",\"act_bytes\":" << P->act_bytes << ",\"weight_bytes\":" << P->weight_bytes << ",\"input\":" << P->t_input
+    << ",\"heatmaps\":" << P->t_heatmaps << ",\"tensors\":[";
+  for (size_t i = 0; i < P->tensors.size(); ++i) {
+    const TensorInfo& t = P->tensors[i];
+    if (i) o << ",";
+    o << "{\"C\":" << t.C << ",\"H\":" << t.H << ",\"W\":" << t.W << ",\"f32\":" << (t.dtype == DT_F32 ? 1 : 0)
+      << ",\"offset\":" << (t.offset == (size_t)-1 ? -1LL : (long long)t.offset) << "}";
+  }
+  o << "],\"ops\":[";
+  for (size_t i = 0; i < P->ops.size(); ++i) {
+    const Op& op = P->ops[i];
+    if (i) o << ",";
+    o << "{\"kind\":" << op.kind << ",\"name\":\"" << op.name << "\",\"in\":" << op.in << ",\"out\":" << op.out
+      << ",\"res\":" << op.res << ",\"param\":" << op.param << ",\"cin\":" << op.cin << ",\"cout\":" << op.cout
+      << ",\"k\":" << op.k << ",\"stride\":" << op.stride << ",\"pad\":" << op.pad << ",\"relu\":" << op.relu
+      << ",\"stream\":" << op.stream << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
+      << op.src[0] << "," << op.src[1] << "," << op.src[2] << "," << op.src[3] << "],\"shift\":[" << op.shift[0] << ","
+      << op.shift[1] << "," << op.shift[2] << "," << op.shift[3] << "],\"deps\":[";
+    for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
+    o << "],\"tc\":{\"kc\":" << op.tc.kc << ",\"bps\":" << op.tc.bps << ",\"n_tile\":" << op.tc.n_tile
+      << ",\"stages\":" << op.tc.stages << ",\"smem\":" << op.tc.smem_bytes << ",\"tmem_cols\":" << op.tc.tmem_cols
+      << "}}";
+  }
+  o << "]}";
+  const std::string s = o.str();
+  if (needed) *needed = s.size() + 1;
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, s.size());
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return HRNET_OK;
+}
+
+int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* workspace_dev, size_t act_bytes) {
+  if (!P || !weights_dev || !workspace_dev) return fail(HRNET_E_INVALID, "null argument");
+  if (weight_bytes < P->weight_bytes || act_bytes < P->act_bytes) return fail(HRNET_E_NOMEM, "buffer too small for this plan");
+  if (((uintptr_t)weights_dev | (uintptr_t)workspace_dev) & 1023) return fail(HRNET_E_INVALID, "buffers must be 1024-byte aligned");
+  int rc = load_driver_fns();
+  if (rc) return rc;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    return fail(HRNET_E_CUDA, "no CUDA device");
+  if (prop.major != 10) return fail(HRNET_E_CUDA, "this library contains sm_100a code only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+  P->num_sms = prop.multiProcessorCount;
+  P->wbase = (uint8_t*)weights_dev;
+  P->abase = (uint8_t*)workspace_dev;
+  for (auto& kv : P->graphs) cudaGraphExecDestroy(kv.second);
+  P->graphs.clear();
+  int max_smem = 0;
+  for (auto& op : P->ops) {
+    if (!op.use_tc) continue;
+    const TensorInfo& ti = P->tensors[op.in];
+    const ParamInfo& pi = P->params[op.param];
+    int plh, phh, plw, phw, sub, sa, sb;
+    conv_geometry(op, plh, phh, plw, phw, sub, sa, sb);
+    rc = encode_im2col(&op.tmA, P->abase + ti.offset, P->desc.max_batch, ti.H, ti.W, ti.C, op.tc.kc, op.k, op.stride,
+                       plh, phh, plw, phw);
+    if (rc) return rc;
+    rc = encode_weights(&op.tmB, P->wbase + pi.w_offset, op.cout, op.k * op.k * op.cin, op.tc.kc, op.tc.n_tile);
+    if (rc) return rc;
+    max_smem = std::max(max_smem, op.tc.smem_bytes);
+  }
+  if (max_smem) {
+    cudaError_t e = conv_tc_set_attributes(std::max(max_smem, 200 * 1024 + 4096));
+    if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  }
+  if (!P->side[0]) {
+    for (int i = 0; i < 3; ++i)
+      if (cudaStreamCreateWithFlags(&P->side[i], cudaStreamNonBlocking) != cudaSuccess) return fail(HRNET_E_CUDA, "stream create failed");
+    P->events.resize(P->ops.size(), nullptr);
+    for (size_t i = 0; i < P->ops.size(); ++i)
+      if (P->ops[i].needs_event && cudaEventCreateWithFlags(&P->events[i], cudaEventDisableTiming) != cudaSuccess)
+        return fail(HRNET_E_CUDA, "event create failed");
+    if (cudaEventCreateWithFlags(&P->fork_ev, cudaEventDisableTiming) != cudaSuccess) return fail(HRNET_E_CUDA, "event create failed");
+  }
+  P->bound = true;
+  return HRNET_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess) return fail(HRNET_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_ext, float* joints, int32_t* idx,
+              const float* boxes, cudaStream_t st) {
+  auto tptr = [&](int t) -> uint8_t* { return P->abase + P->tensors[t].offset; };
+  switch (op.kind) {
+    case OP_STEM:
+    case OP_STEM7: {
+      const ParamInfo& pi = P->params[op.param];
+      auto fn = op.kind == OP_STEM ? launch_stem : launch_stem7;
+      CK(fn(in_ext, (const float*)(P->wbase + pi.w_offset), (const float*)(P->wbase + pi.scale_offset),
+            (const float*)(P->wbase + pi.bias_offset), (__half*)tptr(op.out), n, P->desc.height, P->desc.width, st));
+      return 0;
+    }
+    case OP_MAXPOOL: {
+      const TensorInfo& ti = P->tensors[op.in];
+      CK(launch_maxpool((const __half*)tptr(op.in), (__half*)tptr(op.out), n, ti.H, ti.W, ti.C, st));
+      return 0;
+    }
+    case OP_CONV: {
+      const TensorInfo& ti = P->tensors[op.in];
+      const TensorInfo& to = P->tensors[op.out];
+      const ParamInfo& pi = P->params[op.param];
+      int plh, phh, plw, phw, sub, sa, sb;
+      conv_geometry(op, plh, phh, plw, phw, sub, sa, sb);
+      const int OH = sub ? ti.H : ti.H / op.stride, OW = sub ? ti.W : ti.W / op.stride;
+      if (op.use_tc) {
+        ConvTcParams p{};
+        p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
+        p.ksize = op.k; p.stride = op.stride; p.pad_h = plh; p.pad_w = plw;
+        p.sub = sub; p.sub_a = sa; p.sub_b = sb;
+        p.Cin = op.cin; p.Cout = op.cout;
+        p.kc = op.tc.kc; p.cpt = op.cin / op.tc.kc; p.nkb = op.k * op.k * p.cpt; p.bps = op.tc.bps;
+        p.n_tile = op.tc.n_tile; p.n_tiles = op.cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
+        p.stages = op.tc.stages; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
+        p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
+        p.b_blk_bytes = (int)align_up((size_t)p.n_tile * p.kc * 2, 1024);
+        p.scale = (const float*)(P->wbase + pi.scale_offset);
+        p.bias = (const float*)(P->wbase + pi.bias_offset);
+        p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
+        p.out = tptr(op.out);
+        const int tiles = p.m_tiles * p.n_tiles;
+        if (tiles == 0) return 0;
+        CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, std::min(tiles, P->num_sms), st));
+      } else {
+        if (sub) return fail(HRNET_E_INVALID, "transposed-conv phases are not wired to the SIMT kernel yet");
+        ConvSimtParams p{};
+        p.N = n; p.IH = ti.H; p.IW = ti.W; p.OH = OH; p.OW = OW; p.Cin = op.cin; p.Cout = op.cout; p.ksize = op.k;
+        p.stride = op.stride; p.pad = op.pad; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32;
+        p.in = (const __half*)tptr(op.in); p.w = (const __half*)(P->wbase + pi.w_offset);
+        p.scale = (const float*)(P->wbase + pi.scale_offset); p.bias = (const float*)(P->wbase + pi.bias_offset);
+        p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
+        p.out = tptr(op.out);
+        CK(launch_conv_simt(p, st));
+      }
+      return 0;
+    }
+    case OP_FUSE: {
+      const TensorInfo& to = P->tensors[op.out];
+      FuseParams p{};
+      p.N = n; p.H = to.H; p.W = to.W; p.C = to.C; p.nsrc = op.nsrc; p.relu = op.relu;
+      for (int j = 0; j < op.nsrc; ++j) {
+        p.src[j] = tptr(op.src[j]); p.shift[j] = op.shift[j]; p.f32[j] = P->tensors[op.src[j]].dtype == DT_F32;
+      }
+      p.out = (__half*)tptr(op.out);
+      CK(launch_fuse(p, st));
+      return 0;
+    }
+    case OP_HEAD: {
+      const TensorInfo& ti = P->tensors[op.in];
+      const ParamInfo& pi = P->params[op.param];
+      float* out = hm_ext ? hm_ext : (float*)tptr(op.out);
+      CK(launch_head((const __half*)tptr(op.in), (const float*)(P->wbase + pi.w_offset),
+                     (const float*)(P->wbase + pi.bias_offset), out, n, ti.H * ti.W, op.cin, op.cout, st));
+      return 0;
+    }
+    case OP_ARGMAX: {
+      const float* hm = hm_ext ? hm_ext : (const float*)tptr(op.in);
+      CK(launch_argmax(hm, n, op.cout, P->Hh, P->Wh, boxes, joints, idx, st));
+      return 0;
+    }
+  }
+  return fail(HRNET_E_INVALID, "unknown op kind");
+}
+
+// launches ops [first, last) with stream fork/join according to the dependency lists
+int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, float* hm_ext, float* joints,
+              int32_t* idx, const float* boxes, cudaStream_t s0) {
+  auto stream_of = [&](int s) { return s == 0 ? s0 : P->side[s - 1]; };
+  for (int i = first; i < last; ++i) {
+    const Op& op = P->ops[i];
+    cudaStream_t st = stream_of(op.stream);
+    for (int dpi : op.deps)
+      if (P->ops[dpi].stream != op.stream) CK(cudaStreamWaitEvent(st, P->events[dpi], 0));
+    int rc = launch_op(P, op, n, in_ext, hm_ext, joints, idx, boxes, st);
+    if (rc) return rc;
+    if (op.needs_event) CK(cudaEventRecord(P->events[i], st));
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hrnet_forward(HrnetPlan* P, const float* in, int n, float* heatmaps, float* joints, int32_t* argmax_idx,
+                  const float* boxes, void* stream) {
+  if (!P) return fail(HRNET_E_INVALID, "null plan");
+  if (!P->bound) return fail(HRNET_E_STATE, "hrnet_plan_bind must be called before hrnet_forward");
+  if (n < 0 || n > P->desc.max_batch) return fail(HRNET_E_INVALID, "n out of range [0, max_batch]");
+  if (n == 0) return HRNET_OK;
+  if (!in || !joints) return fail(HRNET_E_INVALID, "null input / joints pointer");
+  cudaStream_t s0 = (cudaStream_t)stream;
+  const int nops = (int)P->ops.size();
+  // ops touching caller pointers stay outside the graph: first (stem) and the last two (head, argmax)
+  const int g_first = 1, g_last = nops - 2;
+  int rc = run_range(P, 0, g_first, n, in, heatmaps, joints, argmax_idx, boxes, s0);
+  if (rc) return rc;
+  if (P->desc.flags & HRNET_FLAG_NO_GRAPH) {
+    rc = run_range(P, g_first, g_last, n, in, heatmaps, joints, argmax_idx, boxes, s0);
+    if (rc) return rc;
+  } else {
+    auto it = P->graphs.find(n);
+    if (it == P->graphs.end()) {
+      // head deps on side streams are recorded inside the capture and joined by the explicit waits below
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+      rc = run_range(P, g_first, g_last, n, in, heatmaps, joints, argmax_idx, boxes, s0);
+      if (!rc) {
+        // join every side stream back into s0 so the capture can end
+        const Op& head = P->ops[g_last];
+        for (int dpi : head.deps)
+          if (P->ops[dpi].stream != 0) {
+            cudaError_t e = cudaStreamWaitEvent(s0, P->events[dpi], 0);
+            if (e != cudaSuccess) { rc = fail(HRNET_E_CUDA, std::string("join: ") + cudaGetErrorString(e)); break; }
+          }
+      }
+      cudaError_t e = cudaStreamEndCapture(s0, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+      cudaGraphExec_t ge = nullptr;
+      e = cudaGraphInstantiate(&ge, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+      it = P->graphs.emplace(n, ge).first;
+    }
+    CK(cudaGraphLaunch(it->second, s0));
+  }
+  // head + argmax on s0 (side streams were joined either by the graph or by the waits in run_range)
+  for (int i = g_last; i < nops; ++i) {
+    const Op& op = P->ops[i];
+    if (P->desc.flags & HRNET_FLAG_NO_GRAPH)
+      for (int dpi : op.deps)
+        if (P->ops[dpi].stream != 0) CK(cudaStreamWaitEvent(s0, P->events[dpi], 0));
+    rc = launch_op(P, op, n, in, heatmaps, joints, argmax_idx, boxes, s0);
+    if (rc) return rc;
+  }
+  return HRNET_OK;
+}
+
+int hrnet_forward_host(HrnetPlan* P, const float* in_h, int n, float* heatmaps_h, float* joints_h, int32_t* idx_h,
+                       const float* boxes_h, void* stream) {
+  if (!P) return fail(HRNET_E_INVALID, "null plan");
+  if (!P->bound) return fail(HRNET_E_STATE, "hrnet_plan_bind must be called before hrnet_forward_host");
+  if (n < 0 || n > P->desc.max_batch) return fail(HRNET_E_INVALID, "n out of range [0, max_batch]");
+  if (n == 0) return HRNET_OK;
+  if (!in_h || !joints_h) return fail(HRNET_E_INVALID, "null input / joints pointer");
+  cudaStream_t s0 = (cudaStream_t)stream;
+  const int J = P->desc.nof_joints;
+  float* in_d = (float*)(P->abase + P->off_in_stage);
+  float* joints_d = (float*)(P->abase + P->off_joints);
+  int32_t* idx_d = (int32_t*)(P->abase + P->off_idx);
+  float* boxes_d = boxes_h ? (float*)(P->abase + P->off_boxes) : nullptr;
+  CK(cudaMemcpyAsync(in_d, in_h, (size_t)n * 3 * P->desc.height * P->desc.width * 4, cudaMemcpyHostToDevice, s0));
+  if (boxes_h) CK(cudaMemcpyAsync(boxes_d, boxes_h, (size_t)n * 16, cudaMemcpyHostToDevice, s0));
+  int rc = hrnet_forward(P, in_d, n, nullptr, joints_d, idx_d, boxes_d, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(joints_h, joints_d, (size_t)n * J * 12, cudaMemcpyDeviceToHost, s0));
+  if (idx_h) CK(cudaMemcpyAsync(idx_h, idx_d, (size_t)n * J * 4, cudaMemcpyDeviceToHost, s0));
+  if (heatmaps_h)
+    CK(cudaMemcpyAsync(heatmaps_h, P->abase + P->tensors[P->t_heatmaps].offset, (size_t)n * J * P->Hh * P->Wh * 4,
+                       cudaMemcpyDeviceToHost, s0));
+  CK(cudaStreamSynchronize(s0));
+  return HRNET_OK;
+}
+
+// ---- single-op entry points ---------------------------------------------------------------------
+static int conv_single(const void* in, const void* w, const float* scale, const float* bias, const void* residual,
+                       void* out, int n, int ih, int iw, int cin, int cout, int ksize, int stride, int relu,
+                       int out_f32, int use_tc, cudaStream_t st) {
+  if (!in || !w || !scale || !bias || !out) return fail(HRNET_E_INVALID, "null argument");
+  if (!(ksize == 1 || ksize == 3) || !(stride == 1 || stride == 2)) return fail(HRNET_E_INVALID, "ksize in {1,3}, stride in {1,2}");
+  if (cin % 8 || cout % 8) return fail(HRNET_E_INVALID, "cin and cout must be multiples of 8");
+  if (ih % stride || iw % stride) return fail(HRNET_E_INVALID, "spatial size must be divisible by the stride");
+  Op op;
+  op.kind = OP_CONV; op.cin = cin; op.cout = cout; op.k = ksize; op.stride = stride; op.pad = ksize / 2; op.relu = relu;
+  const int OH = ih / stride, OW = iw / stride;
+  if (use_tc) {
+    choose_tc_cfg(op, 0);
+    if (!op.use_tc) return fail(HRNET_E_INVALID, "shape not supported by the tcgen05 path (cin, cout must be multiples of 16)");
+    int rc = load_driver_fns();
+    if (rc) return rc;
+    rc = encode_im2col(&op.tmA, in, n, ih, iw, cin, op.tc.kc, ksize, stride, op.pad, op.pad, op.pad, op.pad);
+    if (rc) return rc;
+    rc = encode_weights(&op.tmB, w, cout, ksize * ksize * cin, op.tc.kc, op.tc.n_tile);
+    if (rc) return rc;
+    CK(conv_tc_set_attributes(200 * 1024 + 4096));
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ConvTcParams p{};
+    p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
+    p.ksize = ksize; p.stride = stride; p.pad_h = op.pad; p.pad_w = op.pad; p.Cin = cin; p.Cout = cout;
+    p.kc = op.tc.kc; p.cpt = cin / op.tc.kc; p.nkb = ksize * ksize * p.cpt; p.bps = op.tc.bps;
+    p.n_tile = op.tc.n_tile; p.n_tiles = cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
+    p.stages = op.tc.stages; p.relu = relu; p.out_f32 = out_f32; p.tmem_cols = op.tc.tmem_cols;
+    p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
+    p.b_blk_bytes = (int)align_up((size_t)p.n_tile * p.kc * 2, 1024);
+    p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
+    const int tiles = p.m_tiles * p.n_tiles;
+    if (tiles == 0) return HRNET_OK;
+    CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, std::min(tiles, sms), st));
+  } else {
+    ConvSimtParams p{};
+    p.N = n; p.IH = ih; p.IW = iw; p.OH = OH; p.OW = OW; p.Cin = cin; p.Cout = cout; p.ksize = ksize; p.stride = stride;
+    p.pad = op.pad; p.relu = relu; p.out_f32 = out_f32;
+    p.in = (const __half*)in; p.w = (const __half*)w; p.scale = scale; p.bias = bias;
+    p.residual = (const __half*)residual; p.out = out;
+    CK(launch_conv_simt(p, st));
+  }
+  return HRNET_OK;
+}
+
+int hrnet_conv_bn_act(const void* in, const void* w, const float* scale, const float* bias, const void* residual,
+                      void* out, int n, int ih, int iw, int cin, int cout, int ksize, int stride, int relu, int out_f32,
+                      int use_tc, void* stream) {
+  return conv_single(in, w, scale, bias, residual, out, n, ih, iw, cin, cout, ksize, stride, relu, out_f32, use_tc,
+                     (cudaStream_t)stream);
+}
+
+int hrnet_conv_bench(const void* in, const void* w, const float* scale, const float* bias, const void* residual,
+                     void* out, int n, int ih, int iw, int cin, int cout, int ksize, int stride, int relu, int iters,
+                     float* usec_out, void* stream) {
+  if (!usec_out || iters <= 0) return fail(HRNET_E_INVALID, "bad iters / output");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev(iters + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  for (int i = 0; i < 3; ++i) {
+    int rc = conv_single(in, w, scale, bias, residual, out, n, ih, iw, cin, cout, ksize, stride, relu, 0, 1, st);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(ev[0], st));
+  for (int i = 0; i < iters; ++i) {
+    int rc = conv_single(in, w, scale, bias, residual, out, n, ih, iw, cin, cout, ksize, stride, relu, 0, 1, st);
+    if (rc) return rc;
+    CK(cudaEventRecord(ev[i + 1], st));
+  }
+  CK(cudaStreamSynchronize(st));
+  std::vector<float> t(iters);
+  for (int i = 0; i < iters; ++i) { CK(cudaEventElapsedTime(&t[i], ev[i], ev[i + 1])); t[i] *= 1000.f; }
+  std::sort(t.begin(), t.end());
+  *usec_out = t[iters / 2];
+  for (auto& e : ev) cudaEventDestroy(e);
+  return HRNET_OK;
+}
+
+int hrnet_fuse(const void* const* srcs, const int* shifts, const int* is_f32, int nsrc, void* out, int n, int h, int w,
+               int c, int relu, void* stream) {
+  if (!srcs || !shifts || !is_f32 || !out || nsrc < 1 || nsrc > 4) return fail(HRNET_E_INVALID, "bad argument (1 <= nsrc <= 4)");
+  if (c % 8) return fail(HRNET_E_INVALID, "c must be a multiple of 8");
+  FuseParams p{};
+  p.N = n; p.H = h; p.W = w; p.C = c; p.nsrc = nsrc; p.relu = relu;
+  for (int j = 0; j < nsrc; ++j) {
+    if ((h % (1 << shifts[j])) || (w % (1 << shifts[j]))) return fail(HRNET_E_INVALID, "map size not divisible by the upsample factor");
+    p.src[j] = srcs[j]; p.shift[j] = shifts[j]; p.f32[j] = is_f32[j];
+  }
+  p.out = (__half*)out;
+  CK(launch_fuse(p, (cudaStream_t)stream));
+  return HRNET_OK;
+}
+
+int hrnet_argmax(const float* heatmaps, int n, int J, int hh, int wh, const float* boxes, float* joints,
+                 int32_t* argmax_idx, void* stream) {
+  if (n < 0 || J <= 0 || hh <= 0 || wh <= 0) return fail(HRNET_E_INVALID, "bad shape");
+  if (n == 0) return HRNET_OK;
+  if (!heatmaps || !joints) return fail(HRNET_E_INVALID, "null argument");
+  CK(launch_argmax(heatmaps, n, J, hh, wh, boxes, joints, argmax_idx, (cudaStream_t)stream));
+  return HRNET_OK;
+}
+
+}  // extern "C"

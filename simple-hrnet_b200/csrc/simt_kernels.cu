@@ -1,0 +1,450 @@
+// HBM-bound / odd-shaped kernels of the hot path that do not belong on the tensor cores:
+//   stem_conv3x3s2   : models_/hrnet.py:158-160  (3->64, reads the NCHW fp32 input, writes NHWC fp16)
+//   stem_conv7x7s2   : models_/poseresnet.py:109-111 (3->64, 7x7)
+//   maxpool3x3s2     : models_/poseresnet.py:112
+//   fuse_sum         : models_/hrnet.py:60-69    (sum of identity / nearest-upsampled / down-sampled terms + ReLU)
+//   head_conv1x1     : models_/hrnet.py:187      (c->J 1x1 conv with bias, fp32 NCHW heatmaps)
+//   argmax_decode    : SimpleHRNet.py:296-308    (np.argmax first-occurrence + (y, x, conf) scaling)
+//   conv_simt        : generic direct conv used as the debug cross-check of the tcgen05 path and for shapes
+//                      the implicit GEMM does not cover (Cin or Cout not a multiple of 16)
+#include "hrnet_internal.h"
+
+namespace hrnet {
+
+// ------------------------------------------------------------------------------------------------ stem 3x3 s2
+// block = 256 threads = 64 output pixels x 4 channel groups of 16
+__global__ void __launch_bounds__(256)
+stem_conv3x3s2_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ scale,
+                      const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W) {
+  __shared__ float sw[64 * 27];  // [co][r][s][ci]
+  __shared__ float ss[64], sb[64];
+  for (int i = threadIdx.x; i < 64 * 27; i += 256) sw[i] = w[i];
+  if (threadIdx.x < 64) { ss[threadIdx.x] = scale[threadIdx.x]; sb[threadIdx.x] = bias[threadIdx.x]; }
+  __syncthreads();
+  const int OH = H / 2, OW = W / 2;
+  const long total = (long)N * OH * OW;
+  const long pix = (long)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int cg = threadIdx.x & 3;
+  if (pix >= total) return;
+  const int n = (int)(pix / (OH * OW));
+  const int rem = (int)(pix - (long)n * OH * OW);
+  const int oh = rem / OW, ow = rem - oh * OW;
+  float x[27];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh * 2 - 1 + r;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const int iw = ow * 2 - 1 + s;
+      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        x[(r * 3 + s) * 3 + ci] = ok ? __ldg(in + (((size_t)n * 3 + ci) * H + ih) * W + iw) : 0.f;
+    }
+  }
+  uint4 o[2];
+  __half2* oh2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float y[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int co = cg * 16 + 2 * i + h;
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 27; ++t) acc = fmaf(x[t], sw[co * 27 + t], acc);
+      y[h] = fmaxf(acc * ss[co] + sb[co], 0.f);
+    }
+    oh2[i] = __floats2half2_rn(y[0], y[1]);
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + (size_t)pix * 64 + cg * 16);
+  op[0] = o[0];
+  op[1] = o[1];
+}
+
+cudaError_t launch_stem(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
+                        int N, int H, int W, cudaStream_t st) {
+  const long total = (long)N * (H / 2) * (W / 2);
+  if (total == 0) return cudaSuccess;
+  stem_conv3x3s2_kernel<<<(unsigned)((total + 63) / 64), 256, 0, st>>>(in_nchw, w, scale, bias, out, N, H, W);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ stem 7x7 s2 p3
+// one thread = one output pixel x 16 channels; weights [co][r][s][ci] fp32 in shared memory (64*147 floats)
+__global__ void __launch_bounds__(256)
+stem_conv7x7s2_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ scale,
+                      const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W) {
+  extern __shared__ float sw7[];  // 64*147
+  __shared__ float ss[64], sb[64];
+  for (int i = threadIdx.x; i < 64 * 147; i += 256) sw7[i] = w[i];
+  if (threadIdx.x < 64) { ss[threadIdx.x] = scale[threadIdx.x]; sb[threadIdx.x] = bias[threadIdx.x]; }
+  __syncthreads();
+  const int OH = H / 2, OW = W / 2;
+  const long total = (long)N * OH * OW;
+  const long pix = (long)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int cg = threadIdx.x & 3;
+  if (pix >= total) return;
+  const int n = (int)(pix / (OH * OW));
+  const int rem = (int)(pix - (long)n * OH * OW);
+  const int oh = rem / OW, ow = rem - oh * OW;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int r = 0; r < 7; ++r) {
+    const int ih = oh * 2 - 3 + r;
+    if (ih < 0 || ih >= H) continue;
+    for (int s = 0; s < 7; ++s) {
+      const int iw = ow * 2 - 3 + s;
+      if (iw < 0 || iw >= W) continue;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) {
+        const float x = __ldg(in + (((size_t)n * 3 + ci) * H + ih) * W + iw);
+        const int t = (r * 7 + s) * 3 + ci;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(x, sw7[(cg * 16 + i) * 147 + t], acc[i]);
+      }
+    }
+  }
+  uint4 o[2];
+  __half2* oh2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int co = cg * 16 + 2 * i;
+    oh2[i] = __floats2half2_rn(fmaxf(acc[2 * i] * ss[co] + sb[co], 0.f),
+                               fmaxf(acc[2 * i + 1] * ss[co + 1] + sb[co + 1], 0.f));
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + (size_t)pix * 64 + cg * 16);
+  op[0] = o[0];
+  op[1] = o[1];
+}
+
+cudaError_t launch_stem7(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
+                         int N, int H, int W, cudaStream_t st) {
+  const long total = (long)N * (H / 2) * (W / 2);
+  if (total == 0) return cudaSuccess;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(stem_conv7x7s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 147 * 4);
+    attr = true;
+  }
+  stem_conv7x7s2_kernel<<<(unsigned)((total + 63) / 64), 256, 64 * 147 * 4, st>>>(in_nchw, w, scale, bias, out, N,
+                                                                                  H, W);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ maxpool 3x3 s2 p1
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int N, int IH, int IW, int C) {
+  const int OH = IH / 2, OW = IW / 2, CV = C / 8;
+  const long total = (long)N * OH * OW * CV;
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % CV);
+  const long pix = i / CV;
+  const int n = (int)(pix / (OH * OW));
+  const int rem = (int)(pix - (long)n * OH * OW);
+  const int oh = rem / OW, ow = rem - oh * OW;
+  __half2 m[4];
+  const __half2 ninf = __float2half2_rn(-65504.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) m[k] = ninf;
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh * 2 - 1 + r;
+    if (ih < 0 || ih >= IH) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int iw = ow * 2 - 1 + s;
+      if (iw < 0 || iw >= IW) continue;
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)n * IH + ih) * IW + iw) * C + cv * 8));
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m[k] = __hmax2(m[k], h[k]);
+    }
+  }
+  uint4 o;
+  __half2* oh2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) oh2[k] = m[k];
+  *reinterpret_cast<uint4*>(out + (size_t)pix * C + cv * 8) = o;
+}
+
+cudaError_t launch_maxpool(const __half* in, __half* out, int N, int IH, int IW, int C, cudaStream_t st) {
+  const long total = (long)N * (IH / 2) * (IW / 2) * (C / 8);
+  if (total == 0) return cudaSuccess;
+  maxpool3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, N, IH, IW, C);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ fuse sum
+// out[n,h,w,c] = act( sum_j src_j[n, h >> shift_j, w >> shift_j, c] ), fp32 sum in ascending j like hrnet.py:61-66.
+// one thread = 8 channels (16 B fp16 / 32 B fp32 per source)
+__global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseParams p) {
+  const int CV = p.C / 8;
+  const long total = (long)p.N * p.H * p.W * CV;
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % CV);
+  const long pix = i / CV;
+  const int n = (int)(pix / (p.H * p.W));
+  const int rem = (int)(pix - (long)n * p.H * p.W);
+  const int h = rem / p.W, w = rem - h * p.W;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (j >= p.nsrc) break;
+    const int sh = p.shift[j];
+    const int sH = p.H >> sh, sW = p.W >> sh;
+    const size_t off = ((((size_t)n * sH + (h >> sh)) * sW + (w >> sh)) * p.C) + (size_t)cv * 8;
+    float v[8];
+    if (p.f32[j]) {
+      const float4* sp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.src[j]) + off);
+      float4 a = __ldg(sp), b = __ldg(sp + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+      uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(p.src[j]) + off));
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { float2 f = __half22float2(hh[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+    }
+    if (j == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = v[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float a = acc[2 * k], b = acc[2 * k + 1];
+    if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    oh[k] = __floats2half2_rn(a, b);
+  }
+  *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.C + (size_t)cv * 8) = o;
+}
+
+cudaError_t launch_fuse(const FuseParams& p, cudaStream_t st) {
+  const long total = (long)p.N * p.H * p.W * (p.C / 8);
+  if (total == 0) return cudaSuccess;
+  fuse_sum_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ head 1x1 + bias
+// in NHWC fp16 [N*HW, Cin], w fp32 [J][Cin], out NCHW fp32 [N, J, HW]; one thread = one pixel, all joints
+constexpr int kHeadMaxJ = 32;
+__global__ void __launch_bounds__(128)
+head_conv1x1_kernel(const __half* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ out, int N, int HW, int Cin, int J) {
+  extern __shared__ float shw[];  // [J][Cin] + [J]
+  float* sbias = shw + J * Cin;
+  for (int i = threadIdx.x; i < J * Cin; i += 128) shw[i] = w[i];
+  for (int i = threadIdx.x; i < J; i += 128) sbias[i] = bias[i];
+  __syncthreads();
+  const long pix = (long)blockIdx.x * 128 + threadIdx.x;
+  if (pix >= (long)N * HW) return;
+  const int n = (int)(pix / HW);
+  const int hw = (int)(pix - (long)n * HW);
+  float acc[kHeadMaxJ];
+#pragma unroll
+  for (int j = 0; j < kHeadMaxJ; ++j) acc[j] = 0.f;
+  const __half* ip = in + (size_t)pix * Cin;
+  for (int c = 0; c < Cin; c += 8) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(ip + c));
+    const __half2* hh = reinterpret_cast<const __half2*>(&u);
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { float2 f = __half22float2(hh[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
+#pragma unroll
+    for (int j = 0; j < kHeadMaxJ; ++j) {
+      if (j < J) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j] = fmaf(x[k], shw[j * Cin + c + k], acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kHeadMaxJ; ++j)
+    if (j < J) out[((size_t)n * J + j) * HW + hw] = acc[j] + sbias[j];
+}
+
+cudaError_t launch_head(const __half* in, const float* w, const float* bias, float* out_nchw, int N, int HW, int Cin,
+                        int J, cudaStream_t st) {
+  const long total = (long)N * HW;
+  if (total == 0) return cudaSuccess;
+  if (J > kHeadMaxJ) return cudaErrorInvalidValue;
+  const int smem = (J * Cin + J) * 4;
+  static int attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaFuncSetAttribute(head_conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = smem;
+  }
+  head_conv1x1_kernel<<<(unsigned)((total + 127) / 128), 128, smem, st>>>(in, w, bias, out_nchw, N, HW, Cin, J);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ argmax decode
+// One 256-thread block per (person, joint) heatmap.  np.argmax semantics: flat row-major index of the first
+// maximum; a NaN counts as the maximum (first NaN wins).  Warp-shuffle reduction, then one warp reduces the
+// 8 per-warp candidates.  (y, x) follow SimpleHRNet.py:306-307 evaluated in float64 and rounded to float32.
+__device__ __forceinline__ bool better(float a, int ia, float b, int ib) {
+  const bool an = a != a, bn = b != b;
+  if (an != bn) return an;        // NaN beats non-NaN
+  if (an) return ia < ib;         // both NaN: first
+  if (a != b) return a > b;
+  return ia < ib;                 // tie: first occurrence
+}
+
+__global__ void __launch_bounds__(256)
+argmax_decode_kernel(const float* __restrict__ hm, int J, int Hh, int Wh, const float* __restrict__ boxes,
+                     float* __restrict__ joints, int32_t* __restrict__ idx_out) {
+  const int pj = blockIdx.x;  // person * J + joint
+  const int HW = Hh * Wh;
+  const float* p = hm + (size_t)pj * HW;
+  float best = 0.f;
+  int bi = 0x7fffffff;
+  // vectorised scan when the map is 16B-aligned (HW % 4 == 0 holds for every supported resolution)
+  if ((HW & 3) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    for (int i = threadIdx.x; i < HW / 4; i += 256) {
+      float4 v = __ldg(p4 + i);
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (bi == 0x7fffffff || better(e[k], 4 * i + k, best, bi)) { best = e[k]; bi = 4 * i + k; }
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += 256) {
+      const float v = __ldg(p + i);
+      if (bi == 0x7fffffff || better(v, i, best, bi)) { best = v; bi = i; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ob, oi, best, bi))) { best = ob; bi = oi; }
+  }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < 8 ? sv[lane] : 0.f;
+    bi = lane < 8 ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ob, oi, best, bi))) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      const int person = pj / J;
+      const int r = bi / Wh, c = bi - r * Wh;
+      float x1 = 0.f, y1 = 0.f, x2 = (float)(Wh * 4), y2 = (float)(Hh * 4);
+      if (boxes != nullptr) {
+        x1 = boxes[person * 4 + 0]; y1 = boxes[person * 4 + 1];
+        x2 = boxes[person * 4 + 2]; y2 = boxes[person * 4 + 3];
+      }
+      const float dy = y2 - y1, dx = x2 - x1;  // float32 subtraction like the numpy f32 box array
+      const double y = (double)r * 1.0 / (double)Hh * (double)dy + (double)y1;
+      const double x = (double)c * 1.0 / (double)Wh * (double)dx + (double)x1;
+      joints[(size_t)pj * 3 + 0] = (float)y;
+      joints[(size_t)pj * 3 + 1] = (float)x;
+      joints[(size_t)pj * 3 + 2] = best;
+      if (idx_out != nullptr) idx_out[pj] = bi;
+    }
+  }
+}
+
+cudaError_t launch_argmax(const float* hm, int N, int J, int Hh, int Wh, const float* boxes, float* joints,
+                          int32_t* idx, cudaStream_t st) {
+  if (N * J == 0) return cudaSuccess;
+  argmax_decode_kernel<<<N * J, 256, 0, st>>>(hm, J, Hh, Wh, boxes, joints, idx);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ generic SIMT conv
+// one thread = one output pixel x 8 output channels; fp32 accumulate.  Debug cross-check, not the hot path.
+__global__ void __launch_bounds__(128) conv_simt_kernel(const ConvSimtParams p) {
+  const int CO8 = p.Cout / 8;
+  const long total = (long)p.N * p.OH * p.OW * CO8;
+  const long i = (long)blockIdx.x * 128 + threadIdx.x;
+  if (i >= total) return;
+  const int cg = (int)(i % CO8);
+  const long pix = i / CO8;
+  const int n = (int)(pix / (p.OH * p.OW));
+  const int rem = (int)(pix - (long)n * p.OH * p.OW);
+  const int oh = rem / p.OW, ow = rem - oh * p.OW;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const int K = p.ksize * p.ksize * p.Cin;
+  for (int r = 0; r < p.ksize; ++r) {
+    const int ih = oh * p.stride - p.pad + r;
+    if (ih < 0 || ih >= p.IH) continue;
+    for (int s = 0; s < p.ksize; ++s) {
+      const int iw = ow * p.stride - p.pad + s;
+      if (iw < 0 || iw >= p.IW) continue;
+      const __half* ip = p.in + (((size_t)n * p.IH + ih) * p.IW + iw) * p.Cin;
+      const __half* wp = p.w + (size_t)(cg * 8) * K + (size_t)(r * p.ksize + s) * p.Cin;
+      for (int c = 0; c < p.Cin; c += 8) {
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(ip + c));
+        const __half2* xh = reinterpret_cast<const __half2*>(&u);
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float2 f = __half22float2(xh[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          uint4 wu = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)o * K + c));
+          const __half2* wh = reinterpret_cast<const __half2*>(&wu);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float2 f = __half22float2(wh[k]);
+            acc[o] = fmaf(x[2 * k], f.x, acc[o]);
+            acc[o] = fmaf(x[2 * k + 1], f.y, acc[o]);
+          }
+        }
+      }
+    }
+  }
+  const size_t off = (size_t)pix * p.Cout + (size_t)cg * 8;
+  float y[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) y[o] = acc[o] * p.scale[cg * 8 + o] + p.bias[cg * 8 + o];
+  if (p.residual != nullptr) {
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(p.residual + off));
+    const __half2* rh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { float2 f = __half22float2(rh[k]); y[2 * k] += f.x; y[2 * k + 1] += f.y; }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) y[o] = fmaxf(y[o], 0.f);
+  }
+  if (p.out_f32) {
+    float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+    op[0] = make_float4(y[0], y[1], y[2], y[3]);
+    op[1] = make_float4(y[4], y[5], y[6], y[7]);
+  } else {
+    uint4 o4;
+    __half2* oh2 = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) oh2[k] = __floats2half2_rn(y[2 * k], y[2 * k + 1]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + off) = o4;
+  }
+}
+
+cudaError_t launch_conv_simt(const ConvSimtParams& p, cudaStream_t st) {
+  const long total = (long)p.N * p.OH * p.OW * (p.Cout / 8);
+  if (total == 0) return cudaSuccess;
+  conv_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace hrnet
