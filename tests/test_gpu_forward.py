@@ -1,0 +1,147 @@
+"""`-m gpu` end-to-end parity: CUDA engine (through the C ABI) vs the oracle and the committed
+reference fixtures.  Tolerances:
+  P2  heat-maps: max-abs <= 1e-3 on the north-star configs (random-init weights = default BN init);
+      the randomised-BN sets have heat-maps up to +-1.3, bar scaled to 2.5e-3 * max|hm|.
+  P4  end-to-end argmax: exact wherever the reference's top1-top2 gap > 2 x measured heat-map error."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hrnet_oracle as O
+from simple_hrnet_b200 import B200Engine, SimpleHRNet, _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(arch, c, res, maxb, sd, flags=0):
+    e = B200Engine(arch, c, 17, res, maxb, torch.device("cuda:0"), flags=flags)
+    e.load_state_dict(sd)
+    return e
+
+
+def _check_argmax(hm_ref, idx_gpu, err):
+    flat = torch.from_numpy(hm_ref).reshape(hm_ref.shape[0], hm_ref.shape[1], -1)
+    top = flat.topk(2, dim=2).values
+    gap = (top[..., 0] - top[..., 1]).numpy()
+    ref_idx = flat.argmax(dim=2).numpy()
+    robust = gap > 2 * err
+    assert np.array_equal(idx_gpu[robust], ref_idx[robust])
+    return int((idx_gpu != ref_idx).sum()), int((~robust).sum())
+
+
+@pytest.mark.parametrize("name,tol_scale", [("w32_64x64_n2_rand", 2.5e-3), ("w32_256x192_n2_default", 1e-3),
+                                            ("w32_256x192_n2_rand", 2.5e-3), ("w48_384x288_n1_default", 1e-3)])
+def test_forward_matches_reference_fixture(golden_dir, name, tol_scale):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    c, n, h, w = int(g["c"]), int(g["n"]), int(g["h"]), int(g["w"])
+    sd = O.make_state_dict(O.hrnet_param_spec(c, 17), seed=int(g["wseed"]), bn=str(g["bn"]))
+    x = torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(int(g["xseed"])))
+    e = _engine("hrnet", c, (h, w), n, sd)
+    joints, idx, hm = e.forward_decode(x.cuda(), return_heatmaps=True)
+    torch.cuda.synchronize()
+    ref = g["heatmaps"]
+    err = float(np.abs(hm.cpu().numpy() - ref).max())
+    tol = tol_scale if str(g["bn"]) == "default" else tol_scale * max(1.0, float(np.abs(ref).max()))
+    print(f"{name}: heat-map max-abs err {err:.3e} (tol {tol:.1e})")
+    assert err <= tol
+    flips, fragile = _check_argmax(ref, idx.cpu().numpy(), err)
+    print(f"{name}: argmax flips {flips} (fragile joints {fragile} of {idx.numel()})")
+    # the decode itself is exact on the engine's own heat-maps
+    pts, oidx = O.decode_joints(hm.cpu().numpy(), np.repeat(np.asarray([[0, 0, w, h]], np.float32), n, 0))
+    assert np.array_equal(idx.cpu().numpy(), oidx.astype(np.int32))
+    assert np.array_equal(joints.cpu().numpy().view(np.uint32), pts.view(np.uint32))
+
+
+def test_forward_variants_agree():
+    """graph vs direct launch vs serial streams are bit-identical; the SIMT cross-check path agrees to
+    accumulation-order noise; fp16 exchange terms stay inside the bar."""
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=4, bn="default")
+    x = torch.randn(3, 3, 128, 96, generator=torch.Generator().manual_seed(1)).cuda()
+    ref = O.hrnet_forward(sd, x.cpu()).numpy()
+    base = _engine("hrnet", 32, (128, 96), 4, sd)(x).cpu().numpy()
+    again = _engine("hrnet", 32, (128, 96), 4, sd)(x).cpu().numpy()
+    assert np.array_equal(base, again)
+    for flags in (_lib.FLAG_NO_GRAPH, _lib.FLAG_SERIAL, _lib.FLAG_NO_GRAPH | _lib.FLAG_SERIAL):
+        assert np.array_equal(_engine("hrnet", 32, (128, 96), 4, sd, flags)(x).cpu().numpy(), base), flags
+    simt = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_FORCE_SIMT | _lib.FLAG_NO_GRAPH)(x).cpu().numpy()
+    assert np.abs(simt - base).max() < 5e-4
+    f16 = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_FUSE_F16)(x).cpu().numpy()
+    assert np.abs(f16 - ref).max() < 1e-3 and np.abs(base - ref).max() < 1e-3
+
+
+def test_batch_invariance_and_chunking_full_size():
+    """BASELINE-size property (W48 384x288, N=64): each person's result is independent of its batch
+    neighbours (eval-mode BN) -> forward(batch)[i] == forward(batch[i:i+1]) bit-exactly,
+    and a graph replay gives the same bits."""
+    sd = O.make_state_dict(O.hrnet_param_spec(48, 17), seed=0, bn="default")
+    e = _engine("hrnet", 48, (384, 288), 64, sd)
+    x = torch.randn(64, 3, 384, 288, generator=torch.Generator().manual_seed(3)).cuda()
+    j64, i64, h64 = e.forward_decode(x, return_heatmaps=True)
+    j64b, i64b, _ = e.forward_decode(x, return_heatmaps=False)
+    assert torch.equal(j64, j64b) and torch.equal(i64, i64b)
+    for i in (0, 17, 63):
+        j1, i1, h1 = e.forward_decode(x[i:i + 1], return_heatmaps=True)
+        assert torch.equal(h1[0], h64[i]) and torch.equal(j1[0], j64[i])
+    j5, _, _ = e.forward_decode(x[:5])
+    assert torch.equal(j5, j64[:5])
+    # against the oracle on a 2-person slice (CPU fp32 takes ~1 s)
+    ref = O.hrnet_forward(sd, x[:2].cpu()).numpy()
+    assert np.abs(h64[:2].cpu().numpy() - ref).max() <= 1e-3
+
+
+def test_forward_host_equals_device_path():
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=2, bn="default")
+    e = _engine("hrnet", 32, (256, 192), 8, sd)
+    x = torch.randn(8, 3, 256, 192, generator=torch.Generator().manual_seed(2))
+    boxes = np.asarray([[3, 5, 100 + i, 200 + 2 * i] for i in range(8)], dtype=np.float32)
+    jd, idd, _ = e.forward_decode(x.cuda(), boxes=boxes)
+    xh = x.pin_memory().numpy()
+    jh, ih, hmh = e.forward_host(xh, boxes, want_heatmaps=True)
+    assert np.array_equal(jd.cpu().numpy(), jh) and np.array_equal(idd.cpu().numpy(), ih)
+    assert np.array_equal(e(x.cuda()).cpu().numpy(), hmh)
+    # n = 0 and n > max_batch
+    assert e.forward_decode(x[:0].cuda())[0].shape == (0, 17, 3)
+    with pytest.raises(ValueError):
+        e.forward_decode(torch.zeros(9, 3, 256, 192).cuda())
+
+
+def test_simplehrnet_predict_api(golden_dir):
+    """BASELINE config 1 through the public API: same call, same return structure as the reference."""
+    g = np.load(os.path.join(golden_dir, "w32_256x192_predict.npz"))
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=int(g["wseed"]), bn=str(g["bn"]))
+    img = np.random.default_rng(int(g["iseed"])).integers(0, 256, tuple(g["img_shape"]), dtype=np.uint8)
+    m = SimpleHRNet(32, 17, sd, resolution=(256, 192), multiperson=False, return_heatmaps=True,
+                    return_bounding_boxes=True, max_batch_size=4, device=torch.device("cuda:0"))
+    hm, boxes, pts = m.predict(img)
+    assert hm.shape == g["heatmaps"].shape and pts.shape == (1, 17, 3) and pts.dtype == np.float32
+    assert np.array_equal(boxes, g["boxes"])
+    err = float(np.abs(hm - g["heatmaps"]).max())
+    assert err <= 1e-3
+    robust = g["gaps"] > 2 * err
+    assert np.array_equal(pts[..., :2][robust], g["pts"][..., :2][robust])
+    assert np.abs(pts[..., 2] - g["pts"][..., 2]).max() <= 1e-3
+    # batch form: [n,H,W,3] -> pts [n,1,J,3] (SimpleHRNet.py:475), chunked by max_batch_size=4
+    batch = np.stack([img] * 6)
+    m2 = SimpleHRNet(32, 17, sd, resolution=(256, 192), multiperson=False, max_batch_size=4, device=torch.device("cuda:0"))
+    pts_b = m2.predict(batch)
+    assert pts_b.shape == (6, 1, 17, 3)
+    assert all(np.array_equal(pts_b[i, 0], pts[0]) for i in range(6))
+    with pytest.raises(ValueError, match="Wrong image format"):
+        m2.predict(np.zeros((4, 4), np.uint8))
+    with pytest.raises(ValueError, match="Wrong model name"):
+        SimpleHRNet(32, 17, sd, model_name="vgg", multiperson=False)
+    with pytest.raises(ValueError, match="Wrong device name"):
+        SimpleHRNet(32, 17, sd, multiperson=False, device=torch.device("cpu"))
+
+
+def test_poseresnet_forward_matches_reference_fixture(golden_dir):
+    g = np.load(os.path.join(golden_dir, "poseresnet50_256x192_n1_default.npz"))
+    sd = O.make_state_dict(O.poseresnet_param_spec(50, 17), seed=int(g["wseed"]), bn=str(g["bn"]))
+    x = torch.randn(1, 3, 256, 192, generator=torch.Generator().manual_seed(int(g["xseed"])))
+    e = _engine("poseresnet", 50, (256, 192), 1, sd)
+    hm = e(x.cuda()).cpu().numpy()
+    err = float(np.abs(hm - g["heatmaps"]).max())
+    print(f"poseresnet50: heat-map max-abs err {err:.3e}")
+    assert err <= 1e-3

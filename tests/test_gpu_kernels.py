@@ -1,0 +1,146 @@
+"""`-m gpu` parity tests of the individual CUDA kernels, called through the C ABI."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hrnet_oracle as O
+from simple_hrnet_b200 import _lib
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+# (n, ih, iw, cin, cout, k, stride): covers kc = 64 / 32 / 16 (swizzle 128/64/32), both strides, 1x1 and 3x3,
+# N-split (cout 384, 512), M not a multiple of 128, tiles straddling rows and images, tiny maps (12x9, 8x6).
+CONV_SHAPES = [
+    (2, 16, 16, 64, 64, 1, 1),      # plain GEMM, one k-block
+    (2, 16, 16, 64, 64, 3, 1),      # 3x3 im2col, SW128
+    (3, 24, 18, 192, 192, 3, 1),    # W48 branch 2
+    (5, 12, 9, 384, 384, 3, 1),     # W48 branch 3: odd map, N split 2x192, M = 540 (ragged last tile)
+    (2, 48, 36, 96, 96, 3, 1),      # W48 branch 1: kc = 32 (SW64)
+    (1, 96, 72, 48, 48, 3, 1),      # W48 branch 0: kc = 16 (SW32)
+    (2, 64, 48, 32, 32, 3, 1),      # W32 branch 0: kc = 32
+    (3, 8, 6, 256, 256, 3, 1),      # W32 branch 3: 8x6 map
+    (2, 96, 72, 48, 96, 3, 2),      # stride-2 fuse/transition conv
+    (2, 24, 18, 192, 384, 3, 2),    # stride-2 into the 12x9 map
+    (2, 32, 32, 64, 64, 3, 2),      # stem conv2 shape class
+    (2, 24, 18, 192, 48, 1, 1),     # 1x1 up-path conv
+    (2, 24, 24, 256, 64, 1, 1),     # bottleneck 1x1 reduce
+    (2, 24, 24, 64, 256, 1, 1),     # bottleneck 1x1 expand
+    (1, 16, 12, 256, 512, 1, 2),    # PoseResNet 1x1 stride-2 downsample, N split
+    (1, 8, 8, 16, 16, 3, 1),        # smallest legal channels; M = 64 < one tile
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_matches_cpu(shape):
+    case = G.conv_case(*shape, relu=True, residual=(shape[6] == 1 and shape[3] == shape[4]), out_f32=False, seed=1)
+    out = G.run_conv(case, use_tc=True)
+    err = (out - case["ref"]).abs().max().item()
+    assert err <= G.conv_tolerance(case), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 18, 192, 48, 1, 1), (2, 48, 36, 96, 192, 3, 2)], ids=str)
+def test_conv_tc_f32_output_no_relu(shape):
+    case = G.conv_case(*shape, relu=False, residual=False, out_f32=True, seed=2)
+    out = G.run_conv(case, use_tc=True)
+    assert (out - case["ref"]).abs().max().item() <= 1e-3 * max(1.0, case["ref"].abs().max().item())
+    assert (out < 0).any()
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64, 3, 1), (2, 24, 18, 48, 96, 3, 2), (1, 12, 9, 64, 24, 1, 1)], ids=str)
+def test_conv_simt_matches_cpu(shape):
+    case = G.conv_case(*shape, relu=True, residual=False, out_f32=False, seed=3)
+    out = G.run_conv(case, use_tc=False)
+    assert (out - case["ref"]).abs().max().item() <= G.conv_tolerance(case)
+
+
+def test_conv_tc_full_size_linearity():
+    """BASELINE-size property test (W48 branch 2 at N=64, no oracle needed): conv is linear, so with
+    scale=1, bias=0, no ReLU, fp32 output: conv(2x) == 2*conv(x) exactly (power-of-two scaling)."""
+    d = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    n, h, w, c = 64, 24, 18, 192
+    x = (torch.randn(n, h, w, c, generator=g) * 0.25).to(torch.float16).to(d)
+    wt = (torch.randn(c, 3, 3, c, generator=g) / (9 * c) ** 0.5).to(torch.float16).to(d)
+    one, zero = torch.ones(c, device=d), torch.zeros(c, device=d)
+    outs = []
+    for xin in (x, x * 2):
+        o = torch.empty(n, h, w, c, dtype=torch.float32, device=d)
+        _lib.check(G.lib().hrnet_conv_bn_act(G.ptr(xin), G.ptr(wt), G.ptr(one), G.ptr(zero), None, G.ptr(o), n, h, w,
+                                             c, c, 3, 1, 0, 1, 1, G.stream()))
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[1], outs[0] * 2)
+    assert outs[0].abs().max() > 0.1
+
+
+def test_fuse_kernel():
+    d = torch.device("cuda")
+    g = torch.Generator().manual_seed(0)
+    n, h, w, c = 2, 16, 8, 48
+    s0 = torch.randn(n, h, w, c, generator=g).to(torch.float16)
+    s1 = torch.randn(n, h // 2, w // 2, c, generator=g)
+    s2 = torch.randn(n, h // 4, w // 4, c, generator=g).to(torch.float16)
+    s3 = torch.randn(n, h // 8, w // 8, c, generator=g)
+    srcs = [s0, s1, s2, s3]
+    dev = [t.to(d) for t in srcs]
+    up = lambda t, k: t.float().repeat_interleave(2 ** k, dim=1).repeat_interleave(2 ** k, dim=2)
+    ref = up(s0, 0)
+    for k in (1, 2, 3):
+        ref = ref + up(srcs[k], k)
+    ref = torch.relu(ref).to(torch.float16)
+    out = torch.empty(n, h, w, c, dtype=torch.float16, device=d)
+    arr = (ctypes.c_void_p * 4)(*[t.data_ptr() for t in dev])
+    shifts = (ctypes.c_int * 4)(0, 1, 2, 3)
+    f32 = (ctypes.c_int * 4)(0, 1, 0, 1)
+    _lib.check(G.lib().hrnet_fuse(arr, shifts, f32, 4, G.ptr(out), n, h, w, c, 1, G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)
+
+
+def _argmax_gpu(hm, boxes):
+    d = torch.device("cuda")
+    n, J, Hh, Wh = hm.shape
+    hmd = torch.from_numpy(hm).to(d)
+    bx = torch.from_numpy(boxes).to(d) if boxes is not None else None
+    joints = torch.empty(n, J, 3, dtype=torch.float32, device=d)
+    idx = torch.empty(n, J, dtype=torch.int32, device=d)
+    _lib.check(G.lib().hrnet_argmax(G.ptr(hmd), n, J, Hh, Wh, G.ptr(bx), G.ptr(joints), G.ptr(idx), G.stream()))
+    torch.cuda.synchronize()
+    return joints.cpu().numpy(), idx.cpu().numpy()
+
+
+def test_argmax_edge_fixture_bit_exact(golden_dir):
+    """Fed the reference's own fp32 heat-maps: indices, confidences and (y, x) are bit-identical,
+    incl. exact ties (first occurrence), all-equal maps, negative maps and non-integer box scaling."""
+    g = np.load(os.path.join(golden_dir, "decode_edge.npz"))
+    joints, idx = _argmax_gpu(g["heatmaps"], g["boxes"])
+    assert np.array_equal(idx, g["argmax"].astype(np.int32))
+    assert np.array_equal(joints.view(np.uint32), g["pts"].view(np.uint32))
+
+
+def test_argmax_reference_heatmaps_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "w48_384x288_n1_default.npz"))
+    joints, idx = _argmax_gpu(g["heatmaps"], None)
+    assert np.array_equal(idx, g["argmax"].astype(np.int32))
+    assert np.array_equal(joints.view(np.uint32), g["pts"].view(np.uint32))
+
+
+def test_argmax_random_ties_nan_and_full_size():
+    rng = np.random.default_rng(3)
+    hm = rng.integers(0, 4, (64, 17, 96, 72)).astype(np.float32)      # BASELINE size; heavy ties
+    hm[5, 2, 40, 10] = np.nan
+    hm[5, 2, 50, 10] = np.nan
+    boxes = np.concatenate([rng.uniform(0, 50, (64, 2)), rng.uniform(60, 400, (64, 2))], axis=1).astype(np.float32)
+    joints, idx = _argmax_gpu(hm, boxes)
+    pts, oidx = O.decode_joints(hm, boxes)
+    assert np.array_equal(idx, oidx.astype(np.int32))
+    assert np.array_equal(joints.view(np.uint32), pts.view(np.uint32))
+    assert idx[5, 2] == 40 * 72 + 10   # np.argmax: first NaN wins
+
+
+def test_argmax_empty_batch_is_noop():
+    _lib.check(G.lib().hrnet_argmax(None, 0, 17, 64, 48, None, None, None, G.stream()))
