@@ -51,6 +51,7 @@ struct HrnetPlan {
   uint8_t* abase = nullptr;
   int num_sms = 0;
   cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t cap = nullptr;  // capture origin: the caller's stream may be the legacy default stream, which cannot capture
   std::vector<cudaEvent_t> events;
   cudaEvent_t fork_ev = nullptr;
   std::map<int, cudaGraphExec_t> graphs;
@@ -522,6 +523,7 @@ void hrnet_plan_destroy(HrnetPlan* P) {
   for (auto e : P->events) if (e) cudaEventDestroy(e);
   if (P->fork_ev) cudaEventDestroy(P->fork_ev);
   for (auto s : P->side) if (s) cudaStreamDestroy(s);
+  if (P->cap) cudaStreamDestroy(P->cap);
   delete P;
 }
 
@@ -625,6 +627,7 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
   if (!P->side[0]) {
     for (int i = 0; i < 3; ++i)
       if (cudaStreamCreateWithFlags(&P->side[i], cudaStreamNonBlocking) != cudaSuccess) return fail(HRNET_E_CUDA, "stream create failed");
+    if (cudaStreamCreateWithFlags(&P->cap, cudaStreamNonBlocking) != cudaSuccess) return fail(HRNET_E_CUDA, "stream create failed");
     P->events.resize(P->ops.size(), nullptr);
     for (size_t i = 0; i < P->ops.size(); ++i)
       if (P->ops[i].needs_event && cudaEventCreateWithFlags(&P->events[i], cudaEventDisableTiming) != cudaSuccess)
@@ -769,18 +772,19 @@ int hrnet_forward(HrnetPlan* P, const float* in, int n, float* heatmaps, float* 
     if (it == P->graphs.end()) {
       // head deps on side streams are recorded inside the capture and joined by the explicit waits below
       cudaGraph_t g = nullptr;
-      CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
-      rc = run_range(P, g_first, g_last, n, in, heatmaps, joints, argmax_idx, boxes, s0);
+      cudaStream_t cs = P->cap;
+      CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      rc = run_range(P, g_first, g_last, n, in, heatmaps, joints, argmax_idx, boxes, cs);
       if (!rc) {
         // join every side stream back into s0 so the capture can end
         const Op& head = P->ops[g_last];
         for (int dpi : head.deps)
           if (P->ops[dpi].stream != 0) {
-            cudaError_t e = cudaStreamWaitEvent(s0, P->events[dpi], 0);
+            cudaError_t e = cudaStreamWaitEvent(cs, P->events[dpi], 0);
             if (e != cudaSuccess) { rc = fail(HRNET_E_CUDA, std::string("join: ") + cudaGetErrorString(e)); break; }
           }
       }
-      cudaError_t e = cudaStreamEndCapture(s0, &g);
+      cudaError_t e = cudaStreamEndCapture(cs, &g);
       if (rc) { if (g) cudaGraphDestroy(g); return rc; }
       if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
       cudaGraphExec_t ge = nullptr;

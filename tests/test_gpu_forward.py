@@ -14,6 +14,17 @@ from simple_hrnet_b200 import B200Engine, SimpleHRNet, _lib
 
 pytestmark = pytest.mark.gpu
 
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _report(line):
+    """Measured parity numbers are appended to gpurun_out/parity.log (copied into profiles/ per round)."""
+    print(line)
+    d = os.path.join(_ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity.log"), "a") as f:
+            f.write(line + "\n")
+
 
 def _engine(arch, c, res, maxb, sd, flags=0):
     e = B200Engine(arch, c, 17, res, maxb, torch.device("cuda:0"), flags=flags)
@@ -44,10 +55,10 @@ def test_forward_matches_reference_fixture(golden_dir, name, tol_scale):
     ref = g["heatmaps"]
     err = float(np.abs(hm.cpu().numpy() - ref).max())
     tol = tol_scale if str(g["bn"]) == "default" else tol_scale * max(1.0, float(np.abs(ref).max()))
-    print(f"{name}: heat-map max-abs err {err:.3e} (tol {tol:.1e})")
+    _report(f"{name}: heat-map max-abs err {err:.3e} (tol {tol:.1e}, max|hm| {float(np.abs(ref).max()):.3f})")
     assert err <= tol
     flips, fragile = _check_argmax(ref, idx.cpu().numpy(), err)
-    print(f"{name}: argmax flips {flips} (fragile joints {fragile} of {idx.numel()})")
+    _report(f"{name}: end-to-end argmax flips {flips} of {idx.numel()} (joints with gap <= 2*err: {fragile})")
     # the decode itself is exact on the engine's own heat-maps
     pts, oidx = O.decode_joints(hm.cpu().numpy(), np.repeat(np.asarray([[0, 0, w, h]], np.float32), n, 0))
     assert np.array_equal(idx.cpu().numpy(), oidx.astype(np.int32))
@@ -66,7 +77,9 @@ def test_forward_variants_agree():
     for flags in (_lib.FLAG_NO_GRAPH, _lib.FLAG_SERIAL, _lib.FLAG_NO_GRAPH | _lib.FLAG_SERIAL):
         assert np.array_equal(_engine("hrnet", 32, (128, 96), 4, sd, flags)(x).cpu().numpy(), base), flags
     simt = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_FORCE_SIMT | _lib.FLAG_NO_GRAPH)(x).cpu().numpy()
-    assert np.abs(simt - base).max() < 5e-4
+    # different accumulation order flips fp16 roundings; through ~60 layers the two fp16 pipelines drift apart by
+    # about as much as either drifts from the fp32 reference (measured 6.5e-4 on B200)
+    assert np.abs(simt - base).max() < 1.5e-3 and np.abs(simt - ref).max() < 1e-3
     f16 = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_FUSE_F16)(x).cpu().numpy()
     assert np.abs(f16 - ref).max() < 1e-3 and np.abs(base - ref).max() < 1e-3
 
@@ -88,7 +101,9 @@ def test_batch_invariance_and_chunking_full_size():
     assert torch.equal(j5, j64[:5])
     # against the oracle on a 2-person slice (CPU fp32 takes ~1 s)
     ref = O.hrnet_forward(sd, x[:2].cpu()).numpy()
-    assert np.abs(h64[:2].cpu().numpy() - ref).max() <= 1e-3
+    err = float(np.abs(h64[:2].cpu().numpy() - ref).max())
+    _report(f"w48_384x288 N=64 (persons 0-1 vs oracle): heat-map max-abs err {err:.3e}")
+    assert err <= 1e-3
 
 
 def test_forward_host_equals_device_path():
@@ -143,5 +158,5 @@ def test_poseresnet_forward_matches_reference_fixture(golden_dir):
     e = _engine("poseresnet", 50, (256, 192), 1, sd)
     hm = e(x.cuda()).cpu().numpy()
     err = float(np.abs(hm - g["heatmaps"]).max())
-    print(f"poseresnet50: heat-map max-abs err {err:.3e}")
+    _report(f"poseresnet50_256x192_n1_default: heat-map max-abs err {err:.3e}")
     assert err <= 1e-3
