@@ -246,6 +246,7 @@ def main():
         tot_flop, tot_us = 0.0, 0.0
         for (c, h, w) in STAGE4_BRANCH:
             n = PER_GPU_BATCH
+            kern = 2 if c <= 96 else 1   # halo-patch kernel where the plan uses it (branches 0-1), im2col kernel otherwise
             x = (torch.randn(n, h, w, c, device=dev) * 0.5).to(torch.float16)
             wt = (torch.randn(c, 3, 3, c, device=dev) / (9 * c) ** 0.5).to(torch.float16)
             sc, bi = torch.ones(c, device=dev), torch.zeros(c, device=dev)
@@ -253,15 +254,15 @@ def main():
             out = torch.empty(n, h, w, c, dtype=torch.float16, device=dev)
             us = ctypes.c_float()
             _lib.check(lib.hrnet_conv_bench(G.ptr(x), G.ptr(wt), G.ptr(sc), G.ptr(bi), G.ptr(res), G.ptr(out), n, h, w,
-                                            c, c, 3, 1, 1, 30, ctypes.byref(us), G.stream()))
+                                            c, c, 3, 1, 1, kern, 30, ctypes.byref(us), G.stream()))
             flop = 2.0 * n * h * w * 9 * c * c
-            per_branch.append({"C": c, "map": f"{h}x{w}", "us": round(us.value, 2),
+            per_branch.append({"C": c, "map": f"{h}x{w}", "kernel": "patch" if kern == 2 else "im2col", "us": round(us.value, 2),
                                "tflops": round(flop / us.value / 1e6, 1),
                                "frac": round(flop / us.value / 1e6 / peaks["tflops"], 4)})
             tot_flop += flop; tot_us += us.value
         ach = tot_flop / tot_us / 1e6
-        roofline = {"kernel": "conv_igemm_tc_kernel (stage-4 3x3 s1 branch convs, N=64, one launch per branch, "
-                              "FLOP-weighted aggregate)",
+        roofline = {"kernel": "stage-4 3x3 s1 branch convs (conv3x3_patch_tc_kernel for C=48/96, conv_igemm_tc_kernel for "
+                              "C=192/384), N=64, one launch per branch, FLOP-weighted aggregate",
                     "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": round(ach / peaks["tflops"], 4), "traffic": None, "peak_source": peaks["source"] + ", burst",
                     "per_branch": per_branch}

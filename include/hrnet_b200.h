@@ -43,6 +43,7 @@ extern "C" {
 #define HRNET_FLAG_NO_GRAPH 2u     /* debug: launch kernels directly instead of replaying a graph   */
 #define HRNET_FLAG_FUSE_F16 4u     /* store exchange-unit partial terms in fp16 instead of fp32     */
 #define HRNET_FLAG_SERIAL 8u       /* debug: run all branches on the caller's stream                */
+#define HRNET_FLAG_NO_PATCH 16u    /* debug: disable the halo-patch 3x3 kernel (im2col kernel everywhere) */
 
 typedef struct HrnetPlan HrnetPlan;
 
@@ -111,7 +112,8 @@ int hrnet_plan_launch_count(const HrnetPlan* plan);
 
 /* ---- single-op entry points (tests, ncu) ------------------------------------------------------ */
 /* kxk conv + BN(scale,bias) (+residual) (+ReLU) on NHWC fp16; weights [cout][k][k][cin] fp16.
- * use_tc=1 -> tcgen05 implicit GEMM, 0 -> SIMT cross-check kernel.  out_f32 selects fp32 output. */
+ * use_tc: 0 = SIMT cross-check kernel, 1 = tcgen05 implicit GEMM (TMA im2col), 2 = tcgen05 halo-patch
+ * kernel (3x3 stride 1 with shared-memory-resident weights).  out_f32 selects fp32 output. */
 int hrnet_conv_bn_act(const void* in_nhwc_f16, const void* w_f16, const float* scale, const float* bias,
                       const void* residual_f16, void* out, int n, int ih, int iw, int cin, int cout, int ksize,
                       int stride, int relu, int out_f32, int use_tc, void* stream);
@@ -125,7 +127,7 @@ int hrnet_argmax(const float* heatmaps, int n, int nof_joints, int hh, int wh, c
  * same arguments as hrnet_conv_bn_act; used by bench.py for the per-kernel roofline. */
 int hrnet_conv_bench(const void* in_nhwc_f16, const void* w_f16, const float* scale, const float* bias,
                      const void* residual_f16, void* out, int n, int ih, int iw, int cin, int cout, int ksize,
-                     int stride, int relu, int iters, float* usec_out, void* stream);
+                     int stride, int relu, int use_tc, int iters, float* usec_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ class HrnetParamInfo(ctypes.Structure):
 
 
 ARCH_HRNET, ARCH_POSERESNET = 0, 1
-FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F16, FLAG_SERIAL = 1, 2, 4, 8
+FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F16, FLAG_SERIAL, FLAG_NO_PATCH = 1, 2, 4, 8, 16
 
 # every symbol include/hrnet_b200.h declares: (name, restype, argtypes)
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
@@ -46,7 +46,7 @@ SYMBOLS = {
     "hrnet_conv_bn_act": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "hrnet_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "hrnet_argmax": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "hrnet_conv_bench": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+    "hrnet_conv_bench": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                               ctypes.POINTER(ctypes.c_float), _vp]),
 }
 

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhrnet_b200.so")
-SOURCES = ["plan.cu", "conv_igemm_tc.cu", "simt_kernels.cu"]
+SOURCES = ["plan.cu", "conv_igemm_tc.cu", "conv3x3_patch_tc.cu", "simt_kernels.cu"]
 HEADERS = ["hrnet_internal.h", "ptx.cuh", os.path.join("..", "..", "include", "hrnet_b200.h")]
 
 
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
     tmp = LIB + ".tmp"
-    subprocess.check_call([_nvcc(), "-shared", "-o", tmp] + objs + ["-cudart", "static"])
+    subprocess.check_call([_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", tmp] + objs + ["-cudart", "static"])
     os.replace(tmp, LIB)
     return LIB
 

@@ -1,0 +1,235 @@
+// 3x3 stride-1 convolution with halo-patch operand reuse on tcgen05 (sm_100a).
+//
+// The im2col kernel (conv_igemm_tc.cu) re-fetches every input pixel nine times (once per filter tap) and
+// streams the weights once per 128-pixel tile; measured on B200 it is bound by the L2->SM path
+// (~28 B/clk/SM, ~4 clk per TMA row) at 5-26 % of tensor peak.  This kernel removes that traffic:
+//
+//   * output tile = 8 (w) x 16 (h) pixels of one image = 128 GEMM rows; its 10 x 18 input patch
+//     (1-pixel halo, zero-filled out of bounds by TMA) is loaded ONCE per channel chunk by a tiled 4-D
+//     TMA into swizzled shared memory, [18][10] pixels x (kc * 2) bytes.
+//   * each of the 9 filter taps is then just a *row-shifted view* of that patch: the UMMA shared-memory
+//     descriptor starts at patch + (r * 10 + s) pixel rows and steps 10 rows between 8-row core groups
+//     (SBO = 10 * row bytes).  tcgen05 applies the swizzle to absolute shared-memory address bits, so a
+//     descriptor that starts on a 128 B (not 1024 B) boundary reads exactly what TMA wrote
+//     (profiles/r01_exp_shifted_umma_descriptor.log).
+//   * the weights of all 9 taps stay resident in shared memory for the whole persistent CTA.
+//
+// L2->SM traffic per tile drops from 9 x (128 x Cin) + 9 x Cin x Cout to 180 x Cin elements.
+// Epilogue / TMEM double buffering / warp roles as in conv_igemm_tc.cu.
+#include "hrnet_internal.h"
+#include "ptx.cuh"
+
+namespace hrnet {
+
+constexpr int kPThreads = 192;
+constexpr int kPMaxSlots = 8;
+
+struct __align__(8) PatchBars {
+  uint64_t b_full;
+  uint64_t a_full[kPMaxSlots];
+  uint64_t a_empty[kPMaxSlots];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+struct PatchMaps {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
+};
+
+__global__ void __launch_bounds__(kPThreads, 1)
+conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t b_base = smem_base;                              // resident weights
+  const uint32_t a_base = smem_base + (uint32_t)p.b_bytes;        // patch slots
+  float* s_scale = reinterpret_cast<float*>(smem_aligned + (size_t)p.b_bytes + (size_t)p.nslots * p.slot_bytes);
+  float* s_bias = s_scale + p.Cout;
+  PatchBars* bars = reinterpret_cast<PatchBars*>(s_bias + p.Cout);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 3; ++i) { ptx::prefetch_tmap(&maps.a[i]); ptx::prefetch_tmap(&maps.b[i]); }
+    ptx::mbar_init(ptx::smem_u32(&bars->b_full), 1);
+    for (int i = 0; i < p.nslots; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < p.Cout; i += 128) {
+      s_scale[i] = p.scale[i];
+      s_bias[i] = p.bias[i];
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      // resident weights: 9 taps x nchunks blocks of [Cout rows x kc channels]
+      uint32_t btx = 0;
+      for (int j = 0; j < p.nchunks; ++j) btx += 9u * (uint32_t)(p.Cout * p.kc[j] * 2);
+      const uint32_t bfull = ptx::smem_u32(&bars->b_full);
+      ptx::mbar_expect_tx(bfull, btx);
+      for (int j = 0; j < p.nchunks; ++j)
+        for (int t = 0; t < 9; ++t)
+          ptx::tma_load_2d(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), &maps.b[p.mapi[j]], bfull,
+                           t * p.Cin + p.c0[j], 0);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_per_img;
+        const int rem = tile - img * tiles_per_img;
+        const int th = rem / p.tiles_w;
+        const int tw = rem - th * p.tiles_w;
+        for (int j = 0; j < p.nchunks; ++j) {
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[slot]), phase ^ 1u);
+          const uint32_t full = ptx::smem_u32(&bars->a_full[slot]);
+          ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * p.kc[j] * 2));
+          ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a[p.mapi[j]], full, p.c0[j],
+                           tw * kPatchTW - 1, th * kPatchTH - 1, img);
+          if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(128, p.Cout);
+      ptx::mbar_wait(ptx::smem_u32(&bars->b_full), 0);
+      int slot = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+        uint32_t accumulate = 0;
+        for (int j = 0; j < p.nchunks; ++j) {
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_full[slot]), phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t rowb = (uint32_t)p.kc[j] * 2u;
+          const uint32_t a_slot = a_base + (uint32_t)(slot * p.slot_bytes);
+          const int nk = p.kc[j] / 16;
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            const int r = t / 3, s = t - 3 * r;
+            // tap (r, s) = the same patch viewed from pixel row r * 10 + s; 8-row groups are one patch row apart
+            const uint64_t adesc = ptx::umma_desc_kmajor(a_slot + (uint32_t)(r * kPatchPW + s) * rowb, rowb,
+                                                         (uint32_t)kPatchPW * rowb);
+            const uint64_t bdesc = ptx::umma_desc_kmajor(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), rowb, 8u * rowb);
+            for (int k = 0; k < nk; ++k) {
+              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          ptx::mma_commit(ptx::smem_u32(&bars->a_empty[slot]));
+          if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        }
+        ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dh = row >> 3, dw = row & 7;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int th = rem / p.tiles_w;
+      const int tw = rem - th * p.tiles_w;
+      const int oh = th * kPatchTH + dh, ow = tw * kPatchTW + dw;
+      const bool valid = oh < p.H && ow < p.W;
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
+      ptx::tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout);
+      const size_t row_off = (((size_t)img * p.H + oh) * p.W + ow) * p.Cout;
+      for (int c = 0; c < p.Cout; c += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld16(t_row + (uint32_t)c, v);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]) * s_scale[c + i] + s_bias[c + i];
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c);
+            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
+              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
+              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_off + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+          } else {
+            uint4 o[2];
+            __half2* oh2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) oh2[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row_off + c);
+            op[0] = o[0];
+            op[1] = o[1];
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+cudaError_t conv_patch_set_attributes(int max_smem) {
+  return cudaFuncSetAttribute(conv3x3_patch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
+
+cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, const ConvPatchParams& p, int smem_bytes,
+                              int grid, cudaStream_t st) {
+  PatchMaps m;
+  for (int i = 0; i < 3; ++i) { m.a[i] = tmA3[i]; m.b[i] = tmB3[i]; }
+  conv3x3_patch_tc_kernel<<<grid, kPThreads, smem_bytes, st>>>(m, p);
+  return cudaGetLastError();
+}
+
+}  // namespace hrnet

@@ -50,26 +50,6 @@ struct ConvTcCfg {
   int tmem_cols = 0;
 };
 
-struct Op {
-  int kind = 0;
-  std::string name;
-  int in = -1, out = -1, res = -1;  // tensor ids
-  int param = -1;
-  int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
-  int relu = 0;
-  // fuse
-  int nsrc = 0;
-  int src[4] = {-1, -1, -1, -1};
-  int shift[4] = {0, 0, 0, 0};
-  // scheduling
-  int stream = 0;
-  std::vector<int> deps;       // ops that must complete before this one
-  bool needs_event = false;    // some dependant runs on another stream
-  // tcgen05 path
-  bool use_tc = false;
-  ConvTcCfg tc;
-  CUtensorMap tmA, tmB;
-};
 
 // device-side parameter block for the tcgen05 implicit-GEMM conv
 struct ConvTcParams {
@@ -83,6 +63,25 @@ struct ConvTcParams {
   int relu, out_f32;
   int tmem_cols;
   int a_blk_bytes, b_blk_bytes;
+  const float* scale;
+  const float* bias;
+  const __half* residual;
+  void* out;
+};
+
+// device-side parameter block for the halo-patch 3x3 stride-1 conv (conv3x3_patch_tc.cu)
+constexpr int kPatchTW = 8, kPatchTH = 16;                 // output tile: 8 wide x 16 high = 128 GEMM rows
+constexpr int kPatchPW = kPatchTW + 2, kPatchPH = kPatchTH + 2;  // input patch with the 1-pixel halo
+constexpr int kPatchRows = kPatchPW * kPatchPH;            // 180 pixels
+struct ConvPatchParams {
+  int N, H, W, Cin, Cout;
+  int tiles_w, tiles_h, total_tiles;
+  int nchunks;                 // channel chunks of the K dimension (each 64 / 32 / 16 channels)
+  int c0[4], kc[4], mapi[4];   // first channel, width, tensor-map index (0: 64, 1: 32, 2: 16)
+  int boff[4], bblk[4];        // resident-weight block offset / per-tap block size in shared memory
+  int b_bytes;                 // shared memory reserved for the resident weights
+  int slot_bytes, nslots;      // ring of patch slots (one channel chunk of one tile each)
+  int relu, out_f32, tmem_cols;
   const float* scale;
   const float* bias;
   const __half* residual;
@@ -108,6 +107,32 @@ struct FuseParams {
   __half* out;
 };
 
+struct Op {
+  int kind = 0;
+  std::string name;
+  int in = -1, out = -1, res = -1;  // tensor ids
+  int param = -1;
+  int cin = 0, cout = 0, k = 1, stride = 1, pad = 0;
+  int relu = 0;
+  // fuse
+  int nsrc = 0;
+  int src[4] = {-1, -1, -1, -1};
+  int shift[4] = {0, 0, 0, 0};
+  // scheduling
+  int stream = 0;
+  std::vector<int> deps;       // ops that must complete before this one
+  bool needs_event = false;    // some dependant runs on another stream
+  // tcgen05 path
+  bool use_tc = false;
+  ConvTcCfg tc;
+  CUtensorMap tmA, tmB;
+  // halo-patch path (3x3 stride 1 with shared-memory-resident weights)
+  bool use_patch = false;
+  ConvPatchParams pp{};
+  int patch_smem = 0;
+  CUtensorMap tmPA[3], tmPB[3];
+};
+
 // launchers (implemented in the .cu files)
 cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int smem_bytes,
                            int grid, cudaStream_t st);
@@ -123,5 +148,8 @@ cudaError_t launch_maxpool(const __half* in, __half* out, int N, int IH, int IW,
 cudaError_t launch_stem7(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
                          int N, int H, int W, cudaStream_t st);
 cudaError_t conv_tc_set_attributes(int max_smem);
+cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, const ConvPatchParams& p, int smem_bytes,
+                              int grid, cudaStream_t st);
+cudaError_t conv_patch_set_attributes(int max_smem);
 
 }  // namespace hrnet

@@ -176,6 +176,48 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   op.use_tc = true;
 }
 
+// Halo-patch path: 3x3 stride-1 convs whose 9-tap weights fit in shared memory next to >= 2 patch slots and
+// whose map tiles into 8x16 output tiles with little waste.
+constexpr int kMaxDynSmem = 226 * 1024;
+bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
+  op.use_patch = false;
+  if (flags & (HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_NO_PATCH)) return false;
+  if (op.kind != OP_CONV || op.k != 3 || op.stride != 1 || op.pad != 1) return false;
+  if (op.cin % 16 || op.cout % 16 || op.cout > 256 || op.cin > 256) return false;
+  const int tw = (W + kPatchTW - 1) / kPatchTW, th = (H + kPatchTH - 1) / kPatchTH;
+  if ((double)(H * W) / (double)(tw * kPatchTW * th * kPatchTH) < 0.85) return false;
+  ConvPatchParams p{};
+  p.H = H; p.W = W; p.Cin = op.cin; p.Cout = op.cout; p.tiles_w = tw; p.tiles_h = th;
+  int c = 0, n = 0, maxkc = 0;
+  size_t boff = 0;
+  while (c < op.cin) {
+    const int rem = op.cin - c;
+    const int kc = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+    if (n == 4) return false;
+    p.c0[n] = c; p.kc[n] = kc; p.mapi[n] = kc == 64 ? 0 : (kc == 32 ? 1 : 2);
+    p.bblk[n] = (int)align_up((size_t)op.cout * kc * 2, 1024);
+    p.boff[n] = (int)boff;
+    boff += (size_t)9 * p.bblk[n];
+    maxkc = std::max(maxkc, kc);
+    c += kc; ++n;
+  }
+  p.nchunks = n;
+  p.b_bytes = (int)boff;
+  p.slot_bytes = (int)align_up((size_t)kPatchRows * maxkc * 2, 1024);
+  const int fixed = 1024 + 2 * op.cout * 4 + 512;
+  const int avail = kMaxDynSmem - fixed - p.b_bytes;
+  if (avail < 2 * p.slot_bytes) return false;
+  p.nslots = std::min(8, avail / p.slot_bytes);
+  int cols = 32;
+  while (cols < 2 * op.cout) cols *= 2;
+  p.tmem_cols = cols;
+  p.relu = op.relu;
+  op.pp = p;
+  op.patch_smem = fixed + p.b_bytes + p.nslots * p.slot_bytes;
+  op.use_patch = true;
+  return true;
+}
+
 // ---- HRNet ------------------------------------------------------------------------------------
 int build_hrnet(HrnetPlan& P) {
   const HrnetDesc& d = P.desc;
@@ -389,7 +431,10 @@ int build_poseresnet(HrnetPlan& P) {
 }
 
 void finalize_schedule(HrnetPlan& P) {
-  for (auto& op : P.ops) choose_tc_cfg(op, P.desc.flags);
+  for (auto& op : P.ops) {
+    choose_tc_cfg(op, P.desc.flags);
+    if (op.use_tc && op.in >= 0) choose_patch_cfg(op, P.tensors[op.in].H, P.tensors[op.in].W, P.desc.flags);
+  }
   // every stream's last op must be joined back into stream 0 before the head runs
   int head = -1;
   for (size_t i = 0; i < P.ops.size(); ++i) if (P.ops[i].kind == OP_HEAD) head = (int)i;
@@ -471,6 +516,39 @@ int encode_im2col(CUtensorMap* tm, const void* act, int N, int IH, int IW, int C
   // the second descriptor word (same workaround NVIDIA's own CuTe im2col descriptor builder applies).
   if (g_driver_version <= 13010 && (size_t)N * IH * IW * C * 2 < 131072)
     reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+  return 0;
+}
+
+// activations NHWC fp16 as a tiled 4-D map whose box is one 10 x 18 halo patch of kc channels
+int encode_patch(CUtensorMap* tm, const void* act, int N, int H, int W, int C, int kc) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)kPatchPW, (cuuint32_t)kPatchPH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(act), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HRNET_E_CUDA, "cuTensorMapEncodeTiled(patch) failed: " + std::to_string((int)r));
+  return 0;
+}
+
+// all tensor maps of a patch op: one activation map and one weight map per chunk width in use
+int encode_patch_maps(Op& op, const void* act, const void* w, int N) {
+  const ConvPatchParams& p = op.pp;
+  bool have[3] = {false, false, false};
+  for (int j = 0; j < p.nchunks; ++j) have[p.mapi[j]] = true;
+  const int kcs[3] = {64, 32, 16};
+  int first = -1;
+  for (int i = 0; i < 3; ++i) {
+    if (!have[i]) continue;
+    int rc = encode_patch(&op.tmPA[i], act, N, p.H, p.W, p.Cin, kcs[i]);
+    if (rc) return rc;
+    rc = encode_weights(&op.tmPB[i], w, p.Cout, 9 * p.Cin, kcs[i], p.Cout);
+    if (rc) return rc;
+    if (first < 0) first = i;
+  }
+  for (int i = 0; i < 3; ++i)
+    if (!have[i]) { op.tmPA[i] = op.tmPA[first]; op.tmPB[i] = op.tmPB[first]; }
   return 0;
 }
 
@@ -571,7 +649,7 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     o << "{\"kind\":" << op.kind << ",\"name\":\"" << op.name << "\",\"in\":" << op.in << ",\"out\":" << op.out
       << ",\"res\":" << op.res << ",\"param\":" << op.param << ",\"cin\":" << op.cin << ",\"cout\":" << op.cout
       << ",\"k\":" << op.k << ",\"stride\":" << op.stride << ",\"pad\":" << op.pad << ",\"relu\":" << op.relu
-      << ",\"stream\":" << op.stream << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
+      << ",\"stream\":" << op.stream << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
       << op.src[0] << "," << op.src[1] << "," << op.src[2] << "," << op.src[3] << "],\"shift\":[" << op.shift[0] << ","
       << op.shift[1] << "," << op.shift[2] << "," << op.shift[3] << "],\"deps\":[";
     for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
@@ -606,7 +684,7 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
   P->abase = (uint8_t*)workspace_dev;
   for (auto& kv : P->graphs) cudaGraphExecDestroy(kv.second);
   P->graphs.clear();
-  int max_smem = 0;
+  int max_smem = 0, max_patch_smem = 0;
   for (auto& op : P->ops) {
     if (!op.use_tc) continue;
     const TensorInfo& ti = P->tensors[op.in];
@@ -619,6 +697,15 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
     rc = encode_weights(&op.tmB, P->wbase + pi.w_offset, op.cout, op.k * op.k * op.cin, op.tc.kc, op.tc.n_tile);
     if (rc) return rc;
     max_smem = std::max(max_smem, op.tc.smem_bytes);
+    if (op.use_patch) {
+      rc = encode_patch_maps(op, P->abase + ti.offset, P->wbase + pi.w_offset, P->desc.max_batch);
+      if (rc) return rc;
+      max_patch_smem = std::max(max_patch_smem, op.patch_smem);
+    }
+  }
+  if (max_patch_smem) {
+    cudaError_t e = conv_patch_set_attributes(kMaxDynSmem);
+    if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute(patch): ") + cudaGetErrorString(e));
   }
   if (max_smem) {
     cudaError_t e = conv_tc_set_attributes(std::max(max_smem, 200 * 1024 + 4096));
@@ -672,7 +759,17 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
       int plh, phh, plw, phw, sub, sa, sb;
       conv_geometry(op, plh, phh, plw, phw, sub, sa, sb);
       const int OH = sub ? ti.H : ti.H / op.stride, OW = sub ? ti.W : ti.W / op.stride;
-      if (op.use_tc) {
+      if (op.use_patch) {
+        ConvPatchParams p = op.pp;
+        p.N = n; p.total_tiles = n * p.tiles_w * p.tiles_h;
+        p.out_f32 = to.dtype == DT_F32;
+        p.scale = (const float*)(P->wbase + pi.scale_offset);
+        p.bias = (const float*)(P->wbase + pi.bias_offset);
+        p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
+        p.out = tptr(op.out);
+        if (p.total_tiles == 0) return 0;
+        CK(launch_conv_patch(op.tmPA, op.tmPB, p, op.patch_smem, std::min(p.total_tiles, P->num_sms), st));
+      } else if (op.use_tc) {
         ConvTcParams p{};
         p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
         p.ksize = op.k; p.stride = op.stride; p.pad_h = plh; p.pad_w = plw;
@@ -844,6 +941,25 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
   Op op;
   op.kind = OP_CONV; op.cin = cin; op.cout = cout; op.k = ksize; op.stride = stride; op.pad = ksize / 2; op.relu = relu;
   const int OH = ih / stride, OW = iw / stride;
+  if (use_tc == 2) {
+    op.use_tc = true;
+    if (!choose_patch_cfg(op, ih, iw, 0))
+      return fail(HRNET_E_INVALID, "shape not eligible for the halo-patch path (3x3 s1, cin/cout % 16, weights must fit in smem, map must tile 8x16)");
+    int rc = load_driver_fns();
+    if (rc) return rc;
+    rc = encode_patch_maps(op, in, w, n);
+    if (rc) return rc;
+    CK(conv_patch_set_attributes(kMaxDynSmem));
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ConvPatchParams p = op.pp;
+    p.N = n; p.total_tiles = n * p.tiles_w * p.tiles_h; p.relu = relu; p.out_f32 = out_f32;
+    p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
+    if (p.total_tiles == 0) return HRNET_OK;
+    CK(launch_conv_patch(op.tmPA, op.tmPB, p, op.patch_smem, std::min(p.total_tiles, sms), st));
+    return HRNET_OK;
+  }
   if (use_tc) {
     choose_tc_cfg(op, 0);
     if (!op.use_tc) return fail(HRNET_E_INVALID, "shape not supported by the tcgen05 path (cin, cout must be multiples of 16)");
@@ -888,20 +1004,20 @@ int hrnet_conv_bn_act(const void* in, const void* w, const float* scale, const f
 }
 
 int hrnet_conv_bench(const void* in, const void* w, const float* scale, const float* bias, const void* residual,
-                     void* out, int n, int ih, int iw, int cin, int cout, int ksize, int stride, int relu, int iters,
-                     float* usec_out, void* stream) {
+                     void* out, int n, int ih, int iw, int cin, int cout, int ksize, int stride, int relu, int use_tc,
+                     int iters, float* usec_out, void* stream) {
   if (!usec_out || iters <= 0) return fail(HRNET_E_INVALID, "bad iters / output");
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<cudaEvent_t> ev(iters + 1);
   for (auto& e : ev) CK(cudaEventCreate(&e));
   for (int i = 0; i < 3; ++i) {
-    int rc = conv_single(in, w, scale, bias, residual, out, n, ih, iw, cin, cout, ksize, stride, relu, 0, 1, st);
+    int rc = conv_single(in, w, scale, bias, residual, out, n, ih, iw, cin, cout, ksize, stride, relu, 0, use_tc, st);
     if (rc) return rc;
   }
   CK(cudaStreamSynchronize(st));
   CK(cudaEventRecord(ev[0], st));
   for (int i = 0; i < iters; ++i) {
-    int rc = conv_single(in, w, scale, bias, residual, out, n, ih, iw, cin, cout, ksize, stride, relu, 0, 1, st);
+    int rc = conv_single(in, w, scale, bias, residual, out, n, ih, iw, cin, cout, ksize, stride, relu, 0, use_tc, st);
     if (rc) return rc;
     CK(cudaEventRecord(ev[i + 1], st));
   }

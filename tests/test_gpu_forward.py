@@ -74,6 +74,8 @@ def test_forward_variants_agree():
     base = _engine("hrnet", 32, (128, 96), 4, sd)(x).cpu().numpy()
     again = _engine("hrnet", 32, (128, 96), 4, sd)(x).cpu().numpy()
     assert np.array_equal(base, again)
+    nopatch = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_NO_PATCH)(x).cpu().numpy()
+    assert np.abs(nopatch - base).max() < 1.5e-3 and np.abs(nopatch - ref).max() < 1e-3
     for flags in (_lib.FLAG_NO_GRAPH, _lib.FLAG_SERIAL, _lib.FLAG_NO_GRAPH | _lib.FLAG_SERIAL):
         assert np.array_equal(_engine("hrnet", 32, (128, 96), 4, sd, flags)(x).cpu().numpy(), base), flags
     simt = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_FORCE_SIMT | _lib.FLAG_NO_GRAPH)(x).cpu().numpy()

@@ -42,6 +42,40 @@ def test_conv_tc_matches_cpu(shape):
     assert err <= G.conv_tolerance(case), f"max abs err {err}"
 
 
+# halo-patch kernel (use_tc=2): 3x3 s1 with resident weights; chunk mixes 64 / 32+16 / 64+32 / 4x64, ragged tile
+# columns (W=36 -> 5 tiles of 8), ragged rows (H=40 -> 3 tiles of 16), single-tile and multi-image cases.
+PATCH_SHAPES = [
+    (1, 96, 72, 48, 48, 3, 1),      # W48 branch 0 (chunks 32 + 16)
+    (2, 48, 36, 96, 96, 3, 1),      # W48 branch 1 (chunks 64 + 32), ragged tile columns
+    (2, 96, 72, 64, 64, 3, 1),      # layer1 3x3
+    (2, 64, 48, 32, 32, 3, 1),      # W32 branch 0
+    (3, 32, 24, 64, 64, 3, 1),      # W32 branch 1
+    (2, 64, 48, 256, 32, 3, 1),     # W32 transition1.0 (4 chunks of 64)
+    (1, 16, 8, 16, 16, 3, 1),       # exactly one tile
+    (5, 40, 24, 48, 96, 3, 1),      # ragged tile rows, Cin != Cout
+]
+
+
+@pytest.mark.parametrize("shape", PATCH_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_conv_patch_matches_cpu(shape):
+    case = G.conv_case(*shape, relu=True, residual=(shape[3] == shape[4]), out_f32=False, seed=4)
+    out = G.run_conv(case, use_tc=2)
+    err = (out - case["ref"]).abs().max().item()
+    assert err <= G.conv_tolerance(case), f"max abs err {err}"
+    assert not torch.isnan(out).any()
+
+
+def test_conv_patch_equals_im2col_kernel_bitwise_f32():
+    """Same K order is not guaranteed, but with fp32 output and no epilogue both tcgen05 kernels must agree to
+    accumulation-order noise, and the patch kernel must reject shapes it does not cover."""
+    case = G.conv_case(2, 48, 36, 96, 96, 3, 1, relu=False, residual=False, out_f32=True, seed=6)
+    a, b = G.run_conv(case, use_tc=1), G.run_conv(case, use_tc=2)
+    assert (a - b).abs().max().item() < 1e-4
+    bad = G.conv_case(1, 24, 18, 192, 192, 3, 1, relu=False, residual=False, out_f32=True, seed=6)
+    with pytest.raises(_lib.HrnetError, match="not eligible"):
+        G.run_conv(bad, use_tc=2)
+
+
 @pytest.mark.parametrize("shape", [(2, 24, 18, 192, 48, 1, 1), (2, 48, 36, 96, 192, 3, 2)], ids=str)
 def test_conv_tc_f32_output_no_relu(shape):
     case = G.conv_case(*shape, relu=False, residual=False, out_f32=True, seed=2)
