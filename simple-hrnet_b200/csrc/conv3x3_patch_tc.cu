@@ -17,7 +17,7 @@
 // L2->SM traffic per tile drops from 9 x (128 x Cin) + 9 x Cin x Cout to 180 x Cin elements.
 // Epilogue / TMEM double buffering / warp roles as in conv_igemm_tc.cu.
 #include "hrnet_internal.h"
-#include "ptx.cuh"
+#include "epilogue.cuh"
 
 namespace hrnet {
 
@@ -162,49 +162,15 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
       const int tw = rem - th * p.tiles_w;
       const int oh = th * kPatchTH + dh, ow = tw * kPatchTW + dw;
       const bool valid = oh < p.H && ow < p.W;
+      EpiRow e;
+      e.s_scale = s_scale; e.s_bias = s_bias; e.residual = p.residual; e.out = p.out;
+      e.row_off = (((size_t)img * p.H + oh) * p.W + ow) * p.Cout;
+      e.ch0 = 0; e.ncols = p.Cout; e.relu = p.relu; e.out_f32 = p.out_f32; e.valid = valid;
+      uint4 rres[16];
+      epi_load_residual(rres, e, 0);            // in flight while the MMAs of this tile finish
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
       ptx::tc_fence_after_sync();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout);
-      const size_t row_off = (((size_t)img * p.H + oh) * p.W + ow) * p.Cout;
-      for (int c = 0; c < p.Cout; c += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(t_row + (uint32_t)c, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          float y[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]) * s_scale[c + i] + s_bias[c + i];
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c);
-            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-            const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
-              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
-              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_off + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-          } else {
-            uint4 o[2];
-            __half2* oh2 = reinterpret_cast<__half2*>(o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) oh2[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row_off + c);
-            op[0] = o[0];
-            op[1] = o[1];
-          }
-        }
-      }
+      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout));
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
       acc ^= 1;

@@ -20,8 +20,10 @@
 // Replaces, for the hot path, every nn.Conv2d + nn.BatchNorm2d (+ReLU, + `out += residual`) pair of
 // reference models_/modules.py:56-72 (BasicBlock), :20-40 (Bottleneck) and models_/hrnet.py:23-51,
 // 98-145 (fuse / transition convs).
+#include <algorithm>
+
 #include "hrnet_internal.h"
-#include "ptx.cuh"
+#include "epilogue.cuh"
 
 namespace hrnet {
 
@@ -57,7 +59,15 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   float* s_bias = s_scale + p.Cout;
   PipeBars* bars = reinterpret_cast<PipeBars*>(s_bias + p.Cout);
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // Cluster of `cs` CTAs = cs consecutive M-tiles of the same N-tile: every CTA loads 1/cs of each weight
+  // k-block and multicasts it to the whole cluster (weights cross the L2->SM path once per cluster).
+  const int cs = p.cs;
+  const uint32_t crank = cs > 1 ? ptx::cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / cs;
+  const int num_clusters = gridDim.x / cs;
+  const int m_super = (p.m_tiles + cs - 1) / cs;
+  const int total_super = m_super * p.n_tiles;
+  const uint16_t mc_mask = (uint16_t)((1u << cs) - 1u);
   const int nstages_k = (p.nkb + p.bps - 1) / p.bps;  // pipeline stages consumed per tile
 
   if (warp == 0 && lane == 0) {
@@ -65,7 +75,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     ptx::prefetch_tmap(&tmB);
     for (int i = 0; i < p.stages; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), (uint32_t)cs);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
@@ -84,6 +94,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (cs > 1) ptx::cluster_sync_all();   // peers' barriers must be initialised before any remote arrive / multicast
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -92,9 +103,11 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles;
-        const int nt = tile - mt * p.n_tiles;
+      const int b_slice_rows = p.n_tile / cs;
+      const uint32_t b_slice_off = crank * (uint32_t)(b_slice_rows * p.kc * 2);
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
+        const int nt = st / m_super;
+        const int mt = min((st - nt * m_super) * cs + (int)crank, p.m_tiles - 1);  // ghost CTAs redo the last tile
         const int m0 = mt * kTileM;
         const int img = m0 / p.OHW;
         const int rem = m0 - img * p.OHW;
@@ -119,7 +132,11 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const int s = tap - r * p.ksize;
             ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, full, c0, bw, bh, img,
                                     (uint16_t)s, (uint16_t)r);
-            ptx::tma_load_2d(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, full, tap * p.Cin + c0, n0);
+            if (cs == 1)
+              ptx::tma_load_2d(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, full, tap * p.Cin + c0, n0);
+            else
+              ptx::tma_load_2d_mc(b_dst + (uint32_t)(j * p.b_blk_bytes) + b_slice_off, &tmB, full, tap * p.Cin + c0,
+                                  n0 + (int)crank * b_slice_rows, mc_mask);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -136,7 +153,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
@@ -156,7 +173,9 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               accumulate = 1;
             }
           }
-          ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));  // frees the smem slot when the MMAs retire
+          // frees the smem slot (in every CTA of the cluster: peers multicast into it) when the MMAs retire
+          if (cs == 1) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
+          else ptx::mma_commit_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));  // accumulator ready for the epilogue
@@ -170,15 +189,13 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int row = q * 32 + lane;        // accumulator row == output pixel within the tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile / p.n_tiles;
-      const int nt = tile - mt * p.n_tiles;
+    for (int st = cluster_id; st < total_super; st += num_clusters) {
+      const int nt = st / m_super;
+      const int mt_raw = (st - nt * m_super) * cs + (int)crank;
+      const int mt = min(mt_raw, p.m_tiles - 1);
       const int m = mt * kTileM + row;
       const int n0 = nt * p.n_tile;
-      const bool valid = m < p.M_total;
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
-      ptx::tc_fence_after_sync();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      const bool valid = m < p.M_total && mt_raw < p.m_tiles;
       size_t opix = (size_t)m;
       if (p.sub) {  // sub-pixel phase of a stride-2 transposed conv: (n, i, j) -> (n, 2i+a, 2j+b)
         const int img = m / p.OHW;
@@ -187,46 +204,15 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int j = rem - i * p.OW;
         opix = ((size_t)img * (2 * p.OH) + (size_t)(2 * i + p.sub_a)) * (size_t)(2 * p.OW) + (size_t)(2 * j + p.sub_b);
       }
-      const size_t row_off = opix * p.Cout + n0;
-      for (int c = 0; c < p.n_tile; c += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(t_row + (uint32_t)c, v);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          float y[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = __uint_as_float(v[i]) * s_scale[n0 + c + i] + s_bias[n0 + c + i];
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + c);
-            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-            const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
-              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
-              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_off + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) op[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-          } else {
-            uint4 o[2];
-            __half2* oh = reinterpret_cast<__half2*>(o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) oh[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
-            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + row_off + c);
-            op[0] = o[0];
-            op[1] = o[1];
-          }
-        }
-      }
+      EpiRow e;
+      e.s_scale = s_scale; e.s_bias = s_bias; e.residual = p.residual; e.out = p.out;
+      e.row_off = opix * p.Cout + n0;
+      e.ch0 = n0; e.ncols = p.n_tile; e.relu = p.relu; e.out_f32 = p.out_f32; e.valid = valid;
+      uint4 rres[16];
+      epi_load_residual(rres, e, 0);            // in flight while the MMAs of this tile finish
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
+      ptx::tc_fence_after_sync();
+      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile));
       // all TMEM reads of this thread are complete (wait::ld above): release the accumulator
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
@@ -237,6 +223,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (cs > 1) ptx::cluster_sync_all();   // no CTA may exit while peers can still multicast / arrive into it
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -247,10 +234,49 @@ cudaError_t conv_tc_set_attributes(int max_smem) {
   return cudaFuncSetAttribute(conv_igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
 }
 
+// grid size for a persistent launch: as many clusters as can be co-resident (cudaOccupancyMaxActiveClusters), capped
+// by the work available
+int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms) {
+  const int cs = p.cs;
+  const int m_super = (p.m_tiles + cs - 1) / cs;
+  const int need = m_super * p.n_tiles;
+  int max_clusters = num_sms / cs;
+  if (cs > 1) {
+    static int cached[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (cached[cs] == 0) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(num_sms / cs * cs));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = 200 * 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, conv_igemm_tc_kernel, &cfg) == cudaSuccess && nc > 0) cached[cs] = nc;
+      else { cudaGetLastError(); cached[cs] = num_sms / cs; }
+    }
+    max_clusters = cached[cs];
+  }
+  return std::min(need, max_clusters) * cs;
+}
+
 cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int smem_bytes,
                            int grid, cudaStream_t st) {
-  conv_igemm_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, p);
-  return cudaGetLastError();
+  if (p.cs <= 1) {
+    conv_igemm_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)p.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel, tmA, tmB, p);
 }
 
 }  // namespace hrnet

@@ -48,6 +48,7 @@ struct ConvTcCfg {
   int stages = 0;
   int smem_bytes = 0;
   int tmem_cols = 0;
+  int cs = 1;        // cluster size (weight multicast)
 };
 
 
@@ -59,6 +60,7 @@ struct ConvTcParams {
   int Cin, Cout;
   int kc, cpt, nkb, bps;
   int n_tile, n_tiles, m_tiles;
+  int cs;            // cluster size along M (weights multicast): 1, 2 or 4
   int stages;
   int relu, out_f32;
   int tmem_cols;
@@ -148,6 +150,7 @@ cudaError_t launch_maxpool(const __half* in, __half* out, int N, int IH, int IW,
 cudaError_t launch_stem7(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
                          int N, int H, int W, cudaStream_t st);
 cudaError_t conv_tc_set_attributes(int max_smem);
+int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms);
 cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, const ConvPatchParams& p, int smem_bytes,
                               int grid, cudaStream_t st);
 cudaError_t conv_patch_set_attributes(int max_smem);

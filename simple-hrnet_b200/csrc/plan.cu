@@ -172,6 +172,14 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   int cols = 32;
   while (cols < 2 * nt) cols *= 2;
   c.tmem_cols = cols;
+  // weight multicast across a cluster of CTAs working on neighbouring M-tiles: worth it when the weight tile is a
+  // large share of the per-tile L2->SM traffic.  HRNET_B200_CS=1|2|4 overrides (experiments).
+  c.cs = nt >= 96 ? 2 : 1;
+  if (const char* e = getenv("HRNET_B200_CS")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) c.cs = v;
+  }
+  while (c.cs > 1 && (nt % c.cs || (nt / c.cs) % 8)) c.cs /= 2;
   op.tc = c;
   op.use_tc = true;
 }
@@ -654,7 +662,7 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
       << op.shift[1] << "," << op.shift[2] << "," << op.shift[3] << "],\"deps\":[";
     for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
     o << "],\"tc\":{\"kc\":" << op.tc.kc << ",\"bps\":" << op.tc.bps << ",\"n_tile\":" << op.tc.n_tile
-      << ",\"stages\":" << op.tc.stages << ",\"smem\":" << op.tc.smem_bytes << ",\"tmem_cols\":" << op.tc.tmem_cols
+      << ",\"cs\":" << op.tc.cs << ",\"stages\":" << op.tc.stages << ",\"smem\":" << op.tc.smem_bytes << ",\"tmem_cols\":" << op.tc.tmem_cols
       << "}}";
   }
   o << "]}";
@@ -694,7 +702,7 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
     rc = encode_im2col(&op.tmA, P->abase + ti.offset, P->desc.max_batch, ti.H, ti.W, ti.C, op.tc.kc, op.k, op.stride,
                        plh, phh, plw, phw);
     if (rc) return rc;
-    rc = encode_weights(&op.tmB, P->wbase + pi.w_offset, op.cout, op.k * op.k * op.cin, op.tc.kc, op.tc.n_tile);
+    rc = encode_weights(&op.tmB, P->wbase + pi.w_offset, op.cout, op.k * op.k * op.cin, op.tc.kc, op.tc.n_tile / op.tc.cs);
     if (rc) return rc;
     max_smem = std::max(max_smem, op.tc.smem_bytes);
     if (op.use_patch) {
@@ -777,6 +785,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.Cin = op.cin; p.Cout = op.cout;
         p.kc = op.tc.kc; p.cpt = op.cin / op.tc.kc; p.nkb = op.k * op.k * p.cpt; p.bps = op.tc.bps;
         p.n_tile = op.tc.n_tile; p.n_tiles = op.cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
+        p.cs = op.tc.cs;
         p.stages = op.tc.stages; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
         p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
         p.b_blk_bytes = (int)align_up((size_t)p.n_tile * p.kc * 2, 1024);
@@ -786,7 +795,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.out = tptr(op.out);
         const int tiles = p.m_tiles * p.n_tiles;
         if (tiles == 0) return 0;
-        CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, std::min(tiles, P->num_sms), st));
+        CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, conv_tc_grid(p, op.tc.smem_bytes, P->num_sms), st));
       } else {
         if (sub) return fail(HRNET_E_INVALID, "transposed-conv phases are not wired to the SIMT kernel yet");
         ConvSimtParams p{};
@@ -967,7 +976,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     if (rc) return rc;
     rc = encode_im2col(&op.tmA, in, n, ih, iw, cin, op.tc.kc, ksize, stride, op.pad, op.pad, op.pad, op.pad);
     if (rc) return rc;
-    rc = encode_weights(&op.tmB, w, cout, ksize * ksize * cin, op.tc.kc, op.tc.n_tile);
+    rc = encode_weights(&op.tmB, w, cout, ksize * ksize * cin, op.tc.kc, op.tc.n_tile / op.tc.cs);
     if (rc) return rc;
     CK(conv_tc_set_attributes(200 * 1024 + 4096));
     int dev = 0, sms = 0;
@@ -978,13 +987,14 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.ksize = ksize; p.stride = stride; p.pad_h = op.pad; p.pad_w = op.pad; p.Cin = cin; p.Cout = cout;
     p.kc = op.tc.kc; p.cpt = cin / op.tc.kc; p.nkb = ksize * ksize * p.cpt; p.bps = op.tc.bps;
     p.n_tile = op.tc.n_tile; p.n_tiles = cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
+    p.cs = op.tc.cs;
     p.stages = op.tc.stages; p.relu = relu; p.out_f32 = out_f32; p.tmem_cols = op.tc.tmem_cols;
     p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
     p.b_blk_bytes = (int)align_up((size_t)p.n_tile * p.kc * 2, 1024);
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
     const int tiles = p.m_tiles * p.n_tiles;
     if (tiles == 0) return HRNET_OK;
-    CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, std::min(tiles, sms), st));
+    CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, conv_tc_grid(p, op.tc.smem_bytes, sms), st));
   } else {
     ConvSimtParams p{};
     p.N = n; p.IH = ih; p.IW = iw; p.OH = OH; p.OW = OW; p.Cin = cin; p.Cout = cout; p.ksize = ksize; p.stride = stride;

@@ -12,13 +12,18 @@
 namespace hrnet {
 
 // ------------------------------------------------------------------------------------------------ stem 3x3 s2
-// block = 256 threads = 64 output pixels x 4 channel groups of 16
+// block = 256 threads = 64 output pixels x 4 channel groups of 16.  Weights sit in shared memory transposed to
+// [tap][cout] so a thread fetches its 16 output channels of one tap with four 128-bit loads (the first version
+// read them one float at a time and was shared-memory-issue bound: 842 us at N=64, profiles/r01_launches_v1.csv).
 __global__ void __launch_bounds__(256)
 stem_conv3x3s2_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ scale,
                       const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W) {
-  __shared__ float sw[64 * 27];  // [co][r][s][ci]
-  __shared__ float ss[64], sb[64];
-  for (int i = threadIdx.x; i < 64 * 27; i += 256) sw[i] = w[i];
+  __shared__ __align__(16) float sw[27 * 64];  // [t = (r*3+s)*3+ci][co]
+  __shared__ __align__(16) float ss[64], sb[64];
+  for (int i = threadIdx.x; i < 64 * 27; i += 256) {
+    const int co = i / 27, t = i - co * 27;   // global layout [co][r][s][ci]
+    sw[t * 64 + co] = w[i];
+  }
   if (threadIdx.x < 64) { ss[threadIdx.x] = scale[threadIdx.x]; sb[threadIdx.x] = bias[threadIdx.x]; }
   __syncthreads();
   const int OH = H / 2, OW = W / 2;
@@ -29,7 +34,9 @@ stem_conv3x3s2_kernel(const float* __restrict__ in, const float* __restrict__ w,
   const int n = (int)(pix / (OH * OW));
   const int rem = (int)(pix - (long)n * OH * OW);
   const int oh = rem / OW, ow = rem - oh * OW;
-  float x[27];
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     const int ih = oh * 2 - 1 + r;
@@ -38,24 +45,27 @@ stem_conv3x3s2_kernel(const float* __restrict__ in, const float* __restrict__ w,
       const int iw = ow * 2 - 1 + s;
       const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci)
-        x[(r * 3 + s) * 3 + ci] = ok ? __ldg(in + (((size_t)n * 3 + ci) * H + ih) * W + iw) : 0.f;
+      for (int ci = 0; ci < 3; ++ci) {
+        const float x = ok ? __ldg(in + (((size_t)n * 3 + ci) * H + ih) * W + iw) : 0.f;
+        const float4* wp = reinterpret_cast<const float4*>(sw + ((r * 3 + s) * 3 + ci) * 64 + cg * 16);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const float4 wv = wp[v];
+          acc[4 * v + 0] = fmaf(x, wv.x, acc[4 * v + 0]);
+          acc[4 * v + 1] = fmaf(x, wv.y, acc[4 * v + 1]);
+          acc[4 * v + 2] = fmaf(x, wv.z, acc[4 * v + 2]);
+          acc[4 * v + 3] = fmaf(x, wv.w, acc[4 * v + 3]);
+        }
+      }
     }
   }
   uint4 o[2];
   __half2* oh2 = reinterpret_cast<__half2*>(o);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float y[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int co = cg * 16 + 2 * i + h;
-      float acc = 0.f;
-#pragma unroll
-      for (int t = 0; t < 27; ++t) acc = fmaf(x[t], sw[co * 27 + t], acc);
-      y[h] = fmaxf(acc * ss[co] + sb[co], 0.f);
-    }
-    oh2[i] = __floats2half2_rn(y[0], y[1]);
+    const int co = cg * 16 + 2 * i;
+    oh2[i] = __floats2half2_rn(fmaxf(acc[2 * i] * ss[co] + sb[co], 0.f),
+                               fmaxf(acc[2 * i + 1] * ss[co + 1] + sb[co + 1], 0.f));
   }
   uint4* op = reinterpret_cast<uint4*>(out + (size_t)pix * 64 + cg * 16);
   op[0] = o[0];

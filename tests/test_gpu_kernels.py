@@ -52,7 +52,7 @@ PATCH_SHAPES = [
     (3, 32, 24, 64, 64, 3, 1),      # W32 branch 1
     (2, 64, 48, 256, 32, 3, 1),     # W32 transition1.0 (4 chunks of 64)
     (1, 16, 8, 16, 16, 3, 1),       # exactly one tile
-    (5, 40, 24, 48, 96, 3, 1),      # ragged tile rows, Cin != Cout
+    (5, 48, 24, 48, 96, 3, 1),      # Cin != Cout, 3x3 tiles per image
 ]
 
 
