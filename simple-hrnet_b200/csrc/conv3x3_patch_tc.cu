@@ -44,7 +44,7 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::warp_idx_uniform();   // warp-uniform by construction (see ptx::elect_one)
   const int lane = threadIdx.x & 31;
 
   const uint32_t b_base = smem_base;                              // resident weights
@@ -80,73 +80,95 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (warp-uniform loop,
+    // one elected lane issues)
+    {
       // resident weights: 9 taps x nchunks blocks of [Cout rows x kc channels]
       uint32_t btx = 0;
       for (int j = 0; j < p.nchunks; ++j) btx += 9u * (uint32_t)(p.Cout * p.kc[j] * 2);
       const uint32_t bfull = ptx::smem_u32(&bars->b_full);
-      ptx::mbar_expect_tx(bfull, btx);
-      for (int j = 0; j < p.nchunks; ++j)
-        for (int t = 0; t < 9; ++t)
-          ptx::tma_load_2d(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), &maps.b[p.mapi[j]], bfull,
-                           t * p.Cin + p.c0[j], 0);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(bfull, btx);
+        for (int j = 0; j < p.nchunks; ++j)
+          for (int t = 0; t < 9; ++t)
+            ptx::tma_load_2d(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), &maps.b[p.mapi[j]], bfull,
+                             t * p.Cin + p.c0[j], 0);
+      }
+      __syncwarp();
       int slot = 0;
       uint32_t phase = 0;
+      long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img;
         const int rem = tile - img * tiles_per_img;
         const int th = rem / p.tiles_w;
         const int tw = rem - th * p.tiles_w;
         for (int j = 0; j < p.nchunks; ++j) {
+          long long tq0 = 0; if (p.dbg) tq0 = clock64();
           ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[slot]), phase ^ 1u);
+          if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
           const uint32_t full = ptx::smem_u32(&bars->a_full[slot]);
-          ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * p.kc[j] * 2));
-          ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a[p.mapi[j]], full, p.c0[j],
-                           tw * kPatchTW - 1, th * kPatchTH - 1, img);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * p.kc[j] * 2));
+            ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a[p.mapi[j]], full, p.c0[j],
+                             tw * kPatchTW - 1, th * kPatchTH - 1, img);
+          }
+          __syncwarp();
+          if (p.dbg) dbg_issue += clock64() - tq0;
           if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
         }
       }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = dbg_wait; p.dbg[blockIdx.x * 16 + 1] = dbg_issue; p.dbg[blockIdx.x * 16 + 2] = clock64() - dbg_t0; }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (warp-uniform loop,
+    // one elected lane issues)
+    {
       const uint32_t idesc = ptx::umma_idesc_f16(128, p.Cout);
       ptx::mbar_wait(ptx::smem_u32(&bars->b_full), 0);
       int slot = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        long long tq0 = 0; if (p.dbg) tq0 = clock64();
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        if (p.dbg) dbg_wtm += clock64() - tq0;
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
-        uint32_t accumulate = 0;
         for (int j = 0; j < p.nchunks; ++j) {
+          if (p.dbg) tq0 = clock64();
           ptx::mbar_wait(ptx::smem_u32(&bars->a_full[slot]), phase);
+          if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; }
           ptx::tc_fence_after_sync();
           const uint32_t rowb = (uint32_t)p.kc[j] * 2u;
           const uint32_t a_slot = a_base + (uint32_t)(slot * p.slot_bytes);
           const int nk = p.kc[j] / 16;
+          if (ptx::elect_one()) {
 #pragma unroll 1
-          for (int t = 0; t < 9; ++t) {
-            const int r = t / 3, s = t - 3 * r;
-            // tap (r, s) = the same patch viewed from pixel row r * 10 + s; 8-row groups are one patch row apart
-            const uint64_t adesc = ptx::umma_desc_kmajor(a_slot + (uint32_t)(r * kPatchPW + s) * rowb, rowb,
-                                                         (uint32_t)kPatchPW * rowb);
-            const uint64_t bdesc = ptx::umma_desc_kmajor(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), rowb, 8u * rowb);
-            for (int k = 0; k < nk; ++k) {
-              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
-              accumulate = 1;
+            for (int t = 0; t < 9; ++t) {
+              const int r = t / 3, s = t - 3 * r;
+              // tap (r, s) = the same patch viewed from pixel row r * 10 + s; 8-row groups are one patch row apart
+              const uint64_t adesc = ptx::umma_desc_kmajor(a_slot + (uint32_t)(r * kPatchPW + s) * rowb, rowb,
+                                                           (uint32_t)kPatchPW * rowb);
+              const uint64_t bdesc = ptx::umma_desc_kmajor(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), rowb, 8u * rowb);
+              for (int k = 0; k < nk; ++k)
+                ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                (uint32_t)((j | t | k) != 0));
             }
+            ptx::mma_commit(ptx::smem_u32(&bars->a_empty[slot]));
           }
-          ptx::mma_commit(ptx::smem_u32(&bars->a_empty[slot]));
+          __syncwarp();
+          if (p.dbg) dbg_mma += clock64() - tq0;
           if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
         }
-        ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+        if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 4] = dbg_wfull; p.dbg[blockIdx.x * 16 + 5] = dbg_wtm; p.dbg[blockIdx.x * 16 + 6] = dbg_mma; p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0; }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -155,6 +177,7 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
     const int dh = row >> 3, dw = row & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img;
       const int rem = tile - img * tiles_per_img;
@@ -168,14 +191,18 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
       e.ch0 = 0; e.ncols = p.Cout; e.relu = p.relu; e.out_f32 = p.out_f32; e.valid = valid;
       uint4 rres[16];
       epi_load_residual(rres, e, 0);            // in flight while the MMAs of this tile finish
+      long long tq0 = 0; if (p.dbg) tq0 = clock64();
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
+      if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
       ptx::tc_fence_after_sync();
       epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout));
+      if (p.dbg) dbg_work += clock64() - tq0;
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (p.dbg && threadIdx.x == 64) { p.dbg[blockIdx.x * 16 + 8] = dbg_wacc; p.dbg[blockIdx.x * 16 + 9] = dbg_work; p.dbg[blockIdx.x * 16 + 10] = clock64() - dbg_t0; }
   }
 
   ptx::tc_fence_before_sync();

@@ -48,7 +48,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::warp_idx_uniform();   // warp-uniform by construction (see ptx::elect_one)
   const int lane = threadIdx.x & 31;
 
   const int a_stage_bytes = p.bps * p.a_blk_bytes;
@@ -99,8 +99,10 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (warp-uniform loop,
+    // one elected lane issues)
+    {
+      long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
       int stage = 0;
       uint32_t phase = 0;
       const int b_slice_rows = p.n_tile / cs;
@@ -119,11 +121,14 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int ks = 0; ks < nstages_k; ++ks) {
           const int kb0 = ks * p.bps;
           const int nblk = min(p.bps, p.nkb - kb0);
+          long long tq0 = 0; if (p.dbg) tq0 = clock64();
           ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
+          if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
           const uint32_t full = ptx::smem_u32(&bars->full[stage]);
-          ptx::mbar_expect_tx(full, (uint32_t)(nblk * (kTileM * p.kc * 2 + p.n_tile * p.kc * 2)));
           const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
           const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
+          if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(full, (uint32_t)(nblk * (kTileM * p.kc * 2 + p.n_tile * p.kc * 2)));
           for (int j = 0; j < nblk; ++j) {
             const int kb = kb0 + j;
             const int tap = kb / p.cpt;
@@ -138,13 +143,18 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               ptx::tma_load_2d_mc(b_dst + (uint32_t)(j * p.b_blk_bytes) + b_slice_off, &tmB, full, tap * p.Cin + c0,
                                   n0 + (int)crank * b_slice_rows, mc_mask);
           }
+          }
+          __syncwarp();
+          if (p.dbg) dbg_issue += clock64() - tq0;
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = dbg_wait; p.dbg[blockIdx.x * 16 + 1] = dbg_issue; p.dbg[blockIdx.x * 16 + 2] = clock64() - dbg_t0; }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (warp-uniform loop,
+    // one elected lane issues)
+    {
       const uint32_t idesc = ptx::umma_idesc_f16(kTileM, p.n_tile);
       const uint32_t sw_bytes = (uint32_t)p.kc * 2u;
       const uint32_t sbo = 8u * sw_bytes;
@@ -153,35 +163,45 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
       for (int st = cluster_id; st < total_super; st += num_clusters) {
+        long long tq0 = 0; if (p.dbg) tq0 = clock64();
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        if (p.dbg) dbg_wtm += clock64() - tq0;
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-        uint32_t accumulate = 0;
         for (int ks = 0; ks < nstages_k; ++ks) {
           const int nblk = min(p.bps, p.nkb - ks * p.bps);
+          if (p.dbg) tq0 = clock64();
           ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+          if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; }
           ptx::tc_fence_after_sync();
           const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
           const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
-          for (int j = 0; j < nblk; ++j) {
-            const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)(j * p.a_blk_bytes), sw_bytes, sbo);
-            const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), sw_bytes, sbo);
-            for (int k = 0; k < k16_per_blk; ++k) {
-              // advancing K by 16 fp16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate);
-              accumulate = 1;
+          if (ptx::elect_one()) {
+            for (int j = 0; j < nblk; ++j) {
+              const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)(j * p.a_blk_bytes), sw_bytes, sbo);
+              const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), sw_bytes, sbo);
+              for (int k = 0; k < k16_per_blk; ++k) {
+                // advancing K by 16 fp16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+                ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                (uint32_t)((ks | j | k) != 0));
+              }
             }
+            // frees the smem slot (in every CTA of the cluster: peers multicast into it) when the MMAs retire
+            if (cs == 1) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
+            else ptx::mma_commit_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
           }
-          // frees the smem slot (in every CTA of the cluster: peers multicast into it) when the MMAs retire
-          if (cs == 1) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
-          else ptx::mma_commit_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
+          __syncwarp();
+          if (p.dbg) dbg_mma += clock64() - tq0;
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));  // accumulator ready for the epilogue
+        if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));  // accumulator ready
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
+      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 4] = dbg_wfull; p.dbg[blockIdx.x * 16 + 5] = dbg_wtm; p.dbg[blockIdx.x * 16 + 6] = dbg_mma; p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0; }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -189,6 +209,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int row = q * 32 + lane;        // accumulator row == output pixel within the tile
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
     for (int st = cluster_id; st < total_super; st += num_clusters) {
       const int nt = st / m_super;
       const int mt_raw = (st - nt * m_super) * cs + (int)crank;
@@ -210,15 +231,19 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       e.ch0 = n0; e.ncols = p.n_tile; e.relu = p.relu; e.out_f32 = p.out_f32; e.valid = valid;
       uint4 rres[16];
       epi_load_residual(rres, e, 0);            // in flight while the MMAs of this tile finish
+      long long tq0 = 0; if (p.dbg) tq0 = clock64();
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
+      if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
       ptx::tc_fence_after_sync();
       epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile));
+      if (p.dbg) dbg_work += clock64() - tq0;
       // all TMEM reads of this thread are complete (wait::ld above): release the accumulator
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (p.dbg && threadIdx.x == 64) { p.dbg[blockIdx.x * 16 + 8] = dbg_wacc; p.dbg[blockIdx.x * 16 + 9] = dbg_work; p.dbg[blockIdx.x * 16 + 10] = clock64() - dbg_t0; }
   }
 
   ptx::tc_fence_before_sync();

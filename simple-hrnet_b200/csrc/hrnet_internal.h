@@ -69,6 +69,7 @@ struct ConvTcParams {
   const float* bias;
   const __half* residual;
   void* out;
+  long long* dbg;    // optional per-CTA role timers (16 x int64 per CTA), nullptr in production
 };
 
 // device-side parameter block for the halo-patch 3x3 stride-1 conv (conv3x3_patch_tc.cu)
@@ -88,6 +89,7 @@ struct ConvPatchParams {
   const float* bias;
   const __half* residual;
   void* out;
+  long long* dbg;    // optional per-CTA role timers (16 x int64 per CTA), nullptr in production
 };
 
 // device-side parameter block for the SIMT fallback conv (debug path / odd shapes)

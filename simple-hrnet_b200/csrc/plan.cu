@@ -939,6 +939,32 @@ int hrnet_forward_host(HrnetPlan* P, const float* in_h, int n, float* heatmaps_h
   return HRNET_OK;
 }
 
+
+// Debug only (HRNET_B200_DBG=1, single-op entry points): per-CTA role timers of the tcgen05 kernels.
+struct DbgTimers {
+  long long* dev = nullptr;
+  int grid = 0;
+  bool on() const { return dev != nullptr; }
+  void begin(int g) {
+    if (!getenv("HRNET_B200_DBG")) return;
+    grid = g;
+    if (cudaMalloc(&dev, (size_t)g * 16 * sizeof(long long)) != cudaSuccess) { dev = nullptr; return; }
+    cudaMemset(dev, 0, (size_t)g * 16 * sizeof(long long));
+  }
+  void end(cudaStream_t st, const char* what, int tiles) {
+    if (!dev) return;
+    cudaStreamSynchronize(st);
+    std::vector<long long> h((size_t)grid * 16);
+    cudaMemcpy(h.data(), dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    double a[16] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
+    fprintf(stderr, "[dbg] %s grid=%d tiles=%d (%.2f/CTA) cycles/CTA: producer wait_empty=%.0f issue=%.0f total=%.0f | "
+            "mma wait_full=%.0f wait_tmem=%.0f issue=%.0f total=%.0f | epilogue wait_acc=%.0f work=%.0f total=%.0f\n",
+            what, grid, tiles, (double)tiles / grid, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+  }
+};
+
 // ---- single-op entry points ---------------------------------------------------------------------
 static int conv_single(const void* in, const void* w, const float* scale, const float* bias, const void* residual,
                        void* out, int n, int ih, int iw, int cin, int cout, int ksize, int stride, int relu,
@@ -966,7 +992,9 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.N = n; p.total_tiles = n * p.tiles_w * p.tiles_h; p.relu = relu; p.out_f32 = out_f32;
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
     if (p.total_tiles == 0) return HRNET_OK;
+    DbgTimers dt; dt.begin(std::min(p.total_tiles, sms)); p.dbg = dt.dev;
     CK(launch_conv_patch(op.tmPA, op.tmPB, p, op.patch_smem, std::min(p.total_tiles, sms), st));
+    dt.end(st, "patch", p.total_tiles);
     return HRNET_OK;
   }
   if (use_tc) {
@@ -994,7 +1022,9 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
     const int tiles = p.m_tiles * p.n_tiles;
     if (tiles == 0) return HRNET_OK;
+    DbgTimers dt; dt.begin(conv_tc_grid(p, op.tc.smem_bytes, sms)); p.dbg = dt.dev;
     CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, conv_tc_grid(p, op.tc.smem_bytes, sms), st));
+    dt.end(st, "im2col", tiles);
   } else {
     ConvSimtParams p{};
     p.N = n; p.IH = ih; p.IW = iw; p.OH = OH; p.OW = OW; p.Cin = cin; p.Cout = cout; p.ksize = ksize; p.stride = stride;

@@ -71,6 +71,19 @@ __device__ __forceinline__ void tc_fence_before_sync() {
 __device__ __forceinline__ void tc_fence_after_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// One lane of a fully converged warp (warp-uniform control flow around it keeps TMA / UMMA operands in uniform
+// registers; issuing from inside a divergent `if (lane == 0)` region makes ptxas wrap every UTMALDG / UTCHMMA in an
+// elect + R2UR.BROADCAST waterfall loop: measured ~200 clk per instruction, profiles/r01_dbg_role_timers_v1.log).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -19,8 +19,8 @@ class ShardedPredictor:
 
     `local_fn(images_local, joints_out)` runs the engine on this rank's shard and writes
     [n_local,J,3] into `joints_out` (a view into the gather buffer).  With equal shards the
-    collective is a single in-place all_gather_into_tensor; ragged shards fall back to all_gather
-    over per-rank views (still one collective)."""
+    collective is a single in-place all_gather_into_tensor; ragged shards gather max-size padded slots
+    (still one collective) and compact."""
 
     def __init__(self, local_fn, nof_joints, device, group=None):
         self.local_fn = local_fn
@@ -42,6 +42,13 @@ class ShardedPredictor:
         if B % self.world == 0:
             dist.all_gather_into_tensor(buf, buf[lo:hi], group=self.group)
         else:
-            views = [buf[slice(*shard_range(B, self.world, r))] for r in range(self.world)]
-            dist.all_gather(views, buf[lo:hi].clone(), group=self.group)
+            # ragged shards: one all-gather of max-size padded slots, then compact
+            mx = -(-B // self.world)
+            slots = torch.zeros(self.world * mx, self.J, 3, dtype=torch.float32, device=self.device)
+            mine = torch.zeros(mx, self.J, 3, dtype=torch.float32, device=self.device)
+            mine[: hi - lo] = buf[lo:hi]
+            dist.all_gather_into_tensor(slots, mine, group=self.group)
+            for r in range(self.world):
+                a, b = shard_range(B, self.world, r)
+                buf[a:b] = slots[r * mx: r * mx + (b - a)]
         return buf
