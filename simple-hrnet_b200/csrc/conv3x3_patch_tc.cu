@@ -15,13 +15,19 @@
 //   * the weights of all 9 taps stay resident in shared memory for the whole persistent CTA.
 //
 // L2->SM traffic per tile drops from 9 x (128 x Cin) + 9 x Cin x Cout to 180 x Cin elements.
-// Epilogue / TMEM double buffering / warp roles as in conv_igemm_tc.cu.
+//
+// Channel chunks: the patch of every chunk is a 64-channel (128 B per pixel, SWIZZLE_128B) slot; when Cin is not a
+// multiple of 64 the last chunk overhangs the channel dimension, TMA zero-fills the tail and only the K16 steps
+// holding real channels are issued (64 B / 32 B swizzled A operands measured ~3x slower per MMA).  The resident
+// weight block of a chunk is as wide as its real channels need (64 / 32 / 16 -> 128 / 64 / 32 B swizzle).
+// Warp roles (2 producers, 1 MMA issuer, 2 epilogue warpgroups), TMEM double buffering and the epilogue as in
+// conv_igemm_tc.cu.
 #include "hrnet_internal.h"
 #include "epilogue.cuh"
 
 namespace hrnet {
 
-constexpr int kPThreads = 192;
+constexpr int kPThreads = 384;
 constexpr int kPMaxSlots = 8;
 
 struct __align__(8) PatchBars {
@@ -35,8 +41,8 @@ struct __align__(8) PatchBars {
 };
 
 struct PatchMaps {
-  CUtensorMap a[3];
-  CUtensorMap b[3];
+  CUtensorMap a;      // activations, box {64, 10, 18, 1}, SWIZZLE_128B
+  CUtensorMap b[3];   // weights, box {64 | 32 | 16, Cout}
 };
 
 __global__ void __launch_bounds__(kPThreads, 1)
@@ -54,7 +60,8 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
   PatchBars* bars = reinterpret_cast<PatchBars*>(s_bias + p.Cout);
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 3; ++i) { ptx::prefetch_tmap(&maps.a[i]); ptx::prefetch_tmap(&maps.b[i]); }
+    ptx::prefetch_tmap(&maps.a);
+    for (int i = 0; i < 3; ++i) ptx::prefetch_tmap(&maps.b[i]);
     ptx::mbar_init(ptx::smem_u32(&bars->b_full), 1);
     for (int i = 0; i < p.nslots; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 1);
@@ -66,9 +73,9 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < p.Cout; i += 128) {
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+  if (warp >= 4) {
+    for (int i = threadIdx.x - 128; i < p.Cout; i += 256) {
       s_scale[i] = p.scale[i];
       s_bias[i] = p.bias[i];
     }
@@ -79,13 +86,13 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
   const uint32_t tmem_base = bars->tmem_base;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer (warp-uniform loop,
-    // one elected lane issues)
-    {
-      // resident weights: 9 taps x nchunks blocks of [Cout rows x kc channels]
+  if (warp < 2) {
+    // ===================================================================== TMA producers (slot parity = warp)
+    long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
+    if (warp == 0) {
+      // resident weights: 9 taps x nchunks blocks of [Cout rows x bkc channels]
       uint32_t btx = 0;
-      for (int j = 0; j < p.nchunks; ++j) btx += 9u * (uint32_t)(p.Cout * p.kc[j] * 2);
+      for (int j = 0; j < p.nchunks; ++j) btx += 9u * (uint32_t)(p.Cout * p.bkc[j] * 2);
       const uint32_t bfull = ptx::smem_u32(&bars->b_full);
       if (ptx::elect_one()) {
         ptx::mbar_expect_tx(bfull, btx);
@@ -95,90 +102,95 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
                              t * p.Cin + p.c0[j], 0);
       }
       __syncwarp();
-      int slot = 0;
-      uint32_t phase = 0;
-      long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int img = tile / tiles_per_img;
-        const int rem = tile - img * tiles_per_img;
-        const int th = rem / p.tiles_w;
-        const int tw = rem - th * p.tiles_w;
-        for (int j = 0; j < p.nchunks; ++j) {
-          long long tq0 = 0; if (p.dbg) tq0 = clock64();
-          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[slot]), phase ^ 1u);
-          if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
-          const uint32_t full = ptx::smem_u32(&bars->a_full[slot]);
-          if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * p.kc[j] * 2));
-            ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a[p.mapi[j]], full, p.c0[j],
-                             tw * kPatchTW - 1, th * kPatchTH - 1, img);
-          }
-          __syncwarp();
-          if (p.dbg) dbg_issue += clock64() - tq0;
-          if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
-        }
-      }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = dbg_wait; p.dbg[blockIdx.x * 16 + 1] = dbg_issue; p.dbg[blockIdx.x * 16 + 2] = clock64() - dbg_t0; }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (warp-uniform loop,
-    // one elected lane issues)
-    {
-      const uint32_t idesc = ptx::umma_idesc_f16(128, p.Cout);
-      ptx::mbar_wait(ptx::smem_u32(&bars->b_full), 0);
-      int slot = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int L = 0;                            // running slot-load index over all (tile, chunk) of this CTA
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int th = rem / p.tiles_w;
+      const int tw = rem - th * p.tiles_w;
+      for (int j = 0; j < p.nchunks; ++j, ++L) {
+        if ((L & 1) != warp) continue;
+        const int slot = L % p.nslots;
+        const uint32_t phase = (uint32_t)((L / p.nslots) & 1);
         long long tq0 = 0; if (p.dbg) tq0 = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
-        if (p.dbg) dbg_wtm += clock64() - tq0;
-        ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
-        for (int j = 0; j < p.nchunks; ++j) {
-          if (p.dbg) tq0 = clock64();
-          ptx::mbar_wait(ptx::smem_u32(&bars->a_full[slot]), phase);
-          if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; }
-          ptx::tc_fence_after_sync();
-          const uint32_t rowb = (uint32_t)p.kc[j] * 2u;
-          const uint32_t a_slot = a_base + (uint32_t)(slot * p.slot_bytes);
-          const int nk = p.kc[j] / 16;
-          if (ptx::elect_one()) {
-#pragma unroll 1
-            for (int t = 0; t < 9; ++t) {
-              const int r = t / 3, s = t - 3 * r;
-              // tap (r, s) = the same patch viewed from pixel row r * 10 + s; 8-row groups are one patch row apart
-              const uint64_t adesc = ptx::umma_desc_kmajor(a_slot + (uint32_t)(r * kPatchPW + s) * rowb, rowb,
-                                                           (uint32_t)kPatchPW * rowb);
-              const uint64_t bdesc = ptx::umma_desc_kmajor(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), rowb, 8u * rowb);
-              for (int k = 0; k < nk; ++k)
-                ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                (uint32_t)((j | t | k) != 0));
-            }
-            ptx::mma_commit(ptx::smem_u32(&bars->a_empty[slot]));
-          }
-          __syncwarp();
-          if (p.dbg) dbg_mma += clock64() - tq0;
-          if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[slot]), phase ^ 1u);
+        if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
+        const uint32_t full = ptx::smem_u32(&bars->a_full[slot]);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 128));
+          ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a, full, p.c0[j], tw * kPatchTW - 1,
+                           th * kPatchTH - 1, img);
         }
-        if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
         __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (p.dbg) dbg_issue += clock64() - tq0;
       }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 4] = dbg_wfull; p.dbg[blockIdx.x * 16 + 5] = dbg_wtm; p.dbg[blockIdx.x * 16 + 6] = dbg_mma; p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0; }
     }
-  } else {
-    // ===================================================================== epilogue (warps 2..5)
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 0 + 11 * warp] = dbg_wait;
+      p.dbg[blockIdx.x * 16 + 1 + 11 * warp] = dbg_issue;
+      p.dbg[blockIdx.x * 16 + 2 + 11 * warp] = clock64() - dbg_t0;
+    }
+  } else if (warp == 2) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = ptx::umma_idesc_f16(128, p.Cout);
+    ptx::mbar_wait(ptx::smem_u32(&bars->b_full), 0);
+    int L = 0;
+    int it = 0;
+    long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      long long tq0 = 0; if (p.dbg) tq0 = clock64();
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+      if (p.dbg) dbg_wtm += clock64() - tq0;
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+      for (int j = 0; j < p.nchunks; ++j, ++L) {
+        const int slot = L % p.nslots;
+        const uint32_t phase = (uint32_t)((L / p.nslots) & 1);
+        if (p.dbg) tq0 = clock64();
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_full[slot]), phase);
+        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; }
+        ptx::tc_fence_after_sync();
+        const uint32_t a_slot = a_base + (uint32_t)(slot * p.slot_bytes);
+        const uint32_t brow = (uint32_t)p.bkc[j] * 2u;          // weight block row bytes == its swizzle span
+        const int nk = p.kreal[j] / 16;
+        if (ptx::elect_one()) {
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            const int r = t / 3, s = t - 3 * r;
+            // tap (r, s) = the same patch viewed from pixel row r * 10 + s; 8-row groups are one patch row apart
+            const uint64_t adesc = ptx::umma_desc_kmajor(a_slot + (uint32_t)(r * kPatchPW + s) * 128u, 128u,
+                                                         (uint32_t)kPatchPW * 128u);
+            const uint64_t bdesc = ptx::umma_desc_kmajor(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), brow, 8u * brow);
+            for (int k = 0; k < nk; ++k)
+              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                              (uint32_t)((j | t | k) != 0));
+          }
+          ptx::mma_commit(ptx::smem_u32(&bars->a_empty[slot]));
+        }
+        __syncwarp();
+        if (p.dbg) dbg_mma += clock64() - tq0;
+      }
+      if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+      __syncwarp();
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 4] = dbg_wfull; p.dbg[blockIdx.x * 16 + 5] = dbg_wtm;
+      p.dbg[blockIdx.x * 16 + 6] = dbg_mma; p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0;
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (two warpgroups, alternating tiles)
+    const int g = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int dh = row >> 3, dw = row & 7;
-    int acc = 0;
-    uint32_t acc_phase = 0;
     long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != g) continue;
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int img = tile / tiles_per_img;
       const int rem = tile - img * tiles_per_img;
       const int th = rem / p.tiles_w;
@@ -189,25 +201,26 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
       e.s_scale = s_scale; e.s_bias = s_bias; e.residual = p.residual; e.out = p.out;
       e.row_off = (((size_t)img * p.H + oh) * p.W + ow) * p.Cout;
       e.ch0 = 0; e.ncols = p.Cout; e.relu = p.relu; e.out_f32 = p.out_f32; e.valid = valid;
-      uint4 rres[16];
+      uint4 rres[8];
       epi_load_residual(rres, e, 0);            // in flight while the MMAs of this tile finish
       long long tq0 = 0; if (p.dbg) tq0 = clock64();
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
       if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
       ptx::tc_fence_after_sync();
-      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout));
+      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cout));
       if (p.dbg) dbg_work += clock64() - tq0;
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
     }
-    if (p.dbg && threadIdx.x == 64) { p.dbg[blockIdx.x * 16 + 8] = dbg_wacc; p.dbg[blockIdx.x * 16 + 9] = dbg_work; p.dbg[blockIdx.x * 16 + 10] = clock64() - dbg_t0; }
+    if (p.dbg && threadIdx.x == 128) {
+      p.dbg[blockIdx.x * 16 + 8] = dbg_wacc; p.dbg[blockIdx.x * 16 + 9] = dbg_work;
+      p.dbg[blockIdx.x * 16 + 10] = clock64() - dbg_t0;
+    }
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -220,7 +233,8 @@ cudaError_t conv_patch_set_attributes(int max_smem) {
 cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, const ConvPatchParams& p, int smem_bytes,
                               int grid, cudaStream_t st) {
   PatchMaps m;
-  for (int i = 0; i < 3; ++i) { m.a[i] = tmA3[i]; m.b[i] = tmB3[i]; }
+  m.a = tmA3[0];
+  for (int i = 0; i < 3; ++i) m.b[i] = tmB3[i];
   conv3x3_patch_tc_kernel<<<grid, kPThreads, smem_bytes, st>>>(m, p);
   return cudaGetLastError();
 }

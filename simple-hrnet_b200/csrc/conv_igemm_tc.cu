@@ -3,19 +3,25 @@
 //   out[p, co] = act( scale[co] * sum_{r,s,ci} in[pix(p) + (r,s), ci] * w[co, r, s, ci] + bias[co] (+ residual[p, co]) )
 //
 // GEMM view: M = output pixels (n, oh, ow) flattened (NHWC), N = Cout, K = k*k*Cin (tap-major).
-//   A (activations): never materialised.  Each k-block (one filter tap x `kc` input channels) of a
-//     128-pixel M-tile is fetched by ONE TMA im2col load (cp.async.bulk.tensor.4d...im2col): the
-//     hardware walks 128 consecutive output pixels across row / image boundaries, applies the tap
-//     offset and the conv stride, and zero-fills the padding halo.  It lands in shared memory in
-//     the 128B/64B/32B-swizzled K-major layout tcgen05.mma consumes.
-//   B (weights [Cout][k*k*Cin] fp16): plain 2D tiled TMA, same swizzle.
-//   D: fp32 accumulators in TMEM, double buffered (2 x n_tile columns) so the epilogue of tile i
-//     overlaps the MMAs of tile i+1.
+//   A (activations): never materialised.  Each k-block (one filter tap x 64 input channels) of a 128-pixel M-tile
+//     is fetched by ONE TMA im2col load (cp.async.bulk.tensor.4d...im2col): the hardware walks 128 consecutive
+//     output pixels across row / image boundaries, applies the tap offset and the conv stride, and zero-fills the
+//     padding halo.  It lands in shared memory in the 128B-swizzled K-major layout tcgen05.mma consumes.  When Cin
+//     is not a multiple of 64 the last block of a tap overhangs the channel dimension: TMA zero-fills the tail and
+//     the MMA loop only runs the K16 steps that hold real channels (64 B / 32 B swizzled operands measured ~3x
+//     slower per MMA than 128 B ones, profiles/r01_dbg_role_timers_v2_uniform_issue.log).
+//   B (weights [Cout][k*k*Cin] fp16): plain 2D tiled TMA, same swizzle; optionally multicast across a CTA cluster.
+//   D: fp32 accumulators in TMEM, double buffered (2 x n_tile columns) so the epilogue of tile i overlaps the MMAs of
+//     tile i+1.
 //
-// Persistent, warp-specialised CTA (192 threads, 1 CTA/SM):
-//   warp 0   : TMA producer (one lane)         -- smem ring: full[]/empty[] mbarriers
-//   warp 1   : TMEM alloc + MMA issuer (one lane) -- tcgen05.mma / tcgen05.commit
-//   warps 2-5: epilogue: tcgen05.ld -> BN scale/bias (fp32) -> +residual -> ReLU -> fp16/fp32 NHWC store
+// Persistent, warp-specialised CTA (384 threads, 1 CTA/SM):
+//   warps 0-1 : TMA producers, alternating pipeline stages (one producer's wait -> expect_tx -> issue chain costs
+//               ~480 + 80/TMA clk per stage, profiles/r01_exp_tma_issue.log; two chains run concurrently)
+//   warp  2   : TMEM alloc + MMA issuer (tcgen05.mma / tcgen05.commit)
+//   warp  3   : idle
+//   warps 4-7 / 8-11 : two epilogue warpgroups, alternating tiles: tcgen05.ld -> BN scale/bias (fp32) -> +residual
+//               -> ReLU -> fp16/fp32 NHWC store
+// All role loops are warp-uniform with one elected lane issuing (ptx::elect_one).
 //
 // Replaces, for the hot path, every nn.Conv2d + nn.BatchNorm2d (+ReLU, + `out += residual`) pair of
 // reference models_/modules.py:56-72 (BasicBlock), :20-40 (Bottleneck) and models_/hrnet.py:23-51,
@@ -28,8 +34,9 @@
 namespace hrnet {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 384;
 constexpr int kMaxStages = 8;
+constexpr int kKC = 64;                 // channels per k-block: 128-byte swizzled rows
 
 struct __align__(8) PipeBars {
   uint64_t full[kMaxStages];
@@ -83,11 +90,9 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
-  }
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < p.Cout; i += 128) {
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+  if (warp >= 4) {
+    for (int i = threadIdx.x - 128; i < p.Cout; i += 256) {
       s_scale[i] = p.scale[i];
       s_bias[i] = p.bias[i];
     }
@@ -98,41 +103,41 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer (warp-uniform loop,
-    // one elected lane issues)
-    {
-      long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
-      int stage = 0;
-      uint32_t phase = 0;
-      const int b_slice_rows = p.n_tile / cs;
-      const uint32_t b_slice_off = crank * (uint32_t)(b_slice_rows * p.kc * 2);
-      for (int st = cluster_id; st < total_super; st += num_clusters) {
-        const int nt = st / m_super;
-        const int mt = min((st - nt * m_super) * cs + (int)crank, p.m_tiles - 1);  // ghost CTAs redo the last tile
-        const int m0 = mt * kTileM;
-        const int img = m0 / p.OHW;
-        const int rem = m0 - img * p.OHW;
-        const int oh0 = rem / p.OW;
-        const int ow0 = rem - oh0 * p.OW;
-        const int bw = ow0 * p.stride - p.pad_w;
-        const int bh = oh0 * p.stride - p.pad_h;
-        const int n0 = nt * p.n_tile;
-        for (int ks = 0; ks < nstages_k; ++ks) {
-          const int kb0 = ks * p.bps;
-          const int nblk = min(p.bps, p.nkb - kb0);
-          long long tq0 = 0; if (p.dbg) tq0 = clock64();
-          ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
-          if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
-          const uint32_t full = ptx::smem_u32(&bars->full[stage]);
-          const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
-          const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
-          if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(full, (uint32_t)(nblk * (kTileM * p.kc * 2 + p.n_tile * p.kc * 2)));
+  if (warp < 2) {
+    // ===================================================================== TMA producers (stage parity = warp)
+    long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
+    const int b_slice_rows = p.n_tile / cs;
+    const uint32_t b_slice_off = crank * (uint32_t)(b_slice_rows * kKC * 2);
+    int L = 0;                            // running stage-load index over all tiles of this CTA
+    for (int st = cluster_id; st < total_super; st += num_clusters) {
+      const int nt = st / m_super;
+      const int mt = min((st - nt * m_super) * cs + (int)crank, p.m_tiles - 1);  // ghost CTAs redo the last tile
+      const int m0 = mt * kTileM;
+      const int img = m0 / p.OHW;
+      const int rem = m0 - img * p.OHW;
+      const int oh0 = rem / p.OW;
+      const int ow0 = rem - oh0 * p.OW;
+      const int bw = ow0 * p.stride - p.pad_w;
+      const int bh = oh0 * p.stride - p.pad_h;
+      const int n0 = nt * p.n_tile;
+      for (int ks = 0; ks < nstages_k; ++ks, ++L) {
+        if ((L & 1) != warp) continue;
+        const int stage = L % p.stages;
+        const uint32_t phase = (uint32_t)((L / p.stages) & 1);
+        const int kb0 = ks * p.bps;
+        const int nblk = min(p.bps, p.nkb - kb0);
+        long long tq0 = 0; if (p.dbg) tq0 = clock64();
+        ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
+        if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
+        const uint32_t full = ptx::smem_u32(&bars->full[stage]);
+        const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
+        const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(full, (uint32_t)(nblk * (kTileM * kKC * 2 + p.n_tile * kKC * 2)));
           for (int j = 0; j < nblk; ++j) {
             const int kb = kb0 + j;
             const int tap = kb / p.cpt;
-            const int c0 = (kb - tap * p.cpt) * p.kc;
+            const int c0 = (kb - tap * p.cpt) * kKC;
             const int r = tap / p.ksize;
             const int s = tap - r * p.ksize;
             ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, full, c0, bw, bh, img,
@@ -143,74 +148,79 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               ptx::tma_load_2d_mc(b_dst + (uint32_t)(j * p.b_blk_bytes) + b_slice_off, &tmB, full, tap * p.Cin + c0,
                                   n0 + (int)crank * b_slice_rows, mc_mask);
           }
-          }
-          __syncwarp();
-          if (p.dbg) dbg_issue += clock64() - tq0;
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-      }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 0] = dbg_wait; p.dbg[blockIdx.x * 16 + 1] = dbg_issue; p.dbg[blockIdx.x * 16 + 2] = clock64() - dbg_t0; }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (warp-uniform loop,
-    // one elected lane issues)
-    {
-      const uint32_t idesc = ptx::umma_idesc_f16(kTileM, p.n_tile);
-      const uint32_t sw_bytes = (uint32_t)p.kc * 2u;
-      const uint32_t sbo = 8u * sw_bytes;
-      const int k16_per_blk = p.kc / 16;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
-      for (int st = cluster_id; st < total_super; st += num_clusters) {
-        long long tq0 = 0; if (p.dbg) tq0 = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
-        if (p.dbg) dbg_wtm += clock64() - tq0;
-        ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-        for (int ks = 0; ks < nstages_k; ++ks) {
-          const int nblk = min(p.bps, p.nkb - ks * p.bps);
-          if (p.dbg) tq0 = clock64();
-          ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
-          if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; }
-          ptx::tc_fence_after_sync();
-          const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
-          const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
-          if (ptx::elect_one()) {
-            for (int j = 0; j < nblk; ++j) {
-              const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)(j * p.a_blk_bytes), sw_bytes, sbo);
-              const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), sw_bytes, sbo);
-              for (int k = 0; k < k16_per_blk; ++k) {
-                // advancing K by 16 fp16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-                ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                (uint32_t)((ks | j | k) != 0));
-              }
-            }
-            // frees the smem slot (in every CTA of the cluster: peers multicast into it) when the MMAs retire
-            if (cs == 1) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
-            else ptx::mma_commit_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
-          }
-          __syncwarp();
-          if (p.dbg) dbg_mma += clock64() - tq0;
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-        }
-        if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));  // accumulator ready
         __syncwarp();
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (p.dbg) dbg_issue += clock64() - tq0;
       }
-      if (p.dbg && lane == 0) { p.dbg[blockIdx.x * 16 + 4] = dbg_wfull; p.dbg[blockIdx.x * 16 + 5] = dbg_wtm; p.dbg[blockIdx.x * 16 + 6] = dbg_mma; p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0; }
     }
-  } else {
-    // ===================================================================== epilogue (warps 2..5)
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 0 + 11 * warp] = dbg_wait;
+      p.dbg[blockIdx.x * 16 + 1 + 11 * warp] = dbg_issue;
+      p.dbg[blockIdx.x * 16 + 2 + 11 * warp] = clock64() - dbg_t0;
+    }
+  } else if (warp == 2) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = ptx::umma_idesc_f16(kTileM, p.n_tile);
+    const int ctail = p.Cin - (p.cpt - 1) * kKC;          // real channels in the last k-block of a tap
+    int L = 0;
+    int it = 0;
+    long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
+    for (int st = cluster_id; st < total_super; st += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      long long tq0 = 0; if (p.dbg) tq0 = clock64();
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+      if (p.dbg) dbg_wtm += clock64() - tq0;
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+      for (int ks = 0; ks < nstages_k; ++ks, ++L) {
+        const int stage = L % p.stages;
+        const uint32_t phase = (uint32_t)((L / p.stages) & 1);
+        const int kb0 = ks * p.bps;
+        const int nblk = min(p.bps, p.nkb - kb0);
+        if (p.dbg) tq0 = clock64();
+        ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; }
+        ptx::tc_fence_after_sync();
+        const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
+        const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
+        if (ptx::elect_one()) {
+          for (int j = 0; j < nblk; ++j) {
+            const int kb = kb0 + j;
+            const int cblk = kb % p.cpt;
+            const int nk = (cblk == p.cpt - 1 ? ctail : kKC) / 16;
+            const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)(j * p.a_blk_bytes), 128u, 1024u);
+            const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), 128u, 1024u);
+            for (int k = 0; k < nk; ++k) {
+              // advancing K by 16 fp16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                              (uint32_t)((ks | j | k) != 0));
+            }
+          }
+          // frees the smem slot (in every CTA of the cluster: peers multicast into it) when the MMAs retire
+          if (cs == 1) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
+          else ptx::mma_commit_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
+        }
+        __syncwarp();
+        if (p.dbg) dbg_mma += clock64() - tq0;
+      }
+      if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));  // accumulator ready
+      __syncwarp();
+    }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 4] = dbg_wfull; p.dbg[blockIdx.x * 16 + 5] = dbg_wtm;
+      p.dbg[blockIdx.x * 16 + 6] = dbg_mma; p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0;
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (two warpgroups, alternating tiles)
+    const int g = (warp - 4) >> 2;        // warpgroup == accumulator buffer it drains
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;        // accumulator row == output pixel within the tile
-    int acc = 0;
-    uint32_t acc_phase = 0;
     long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    for (int st = cluster_id; st < total_super; st += num_clusters) {
+    int it = 0;
+    for (int st = cluster_id; st < total_super; st += num_clusters, ++it) {
+      if ((it & 1) != g) continue;
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int nt = st / m_super;
       const int mt_raw = (st - nt * m_super) * cs + (int)crank;
       const int mt = min(mt_raw, p.m_tiles - 1);
@@ -229,27 +239,28 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       e.s_scale = s_scale; e.s_bias = s_bias; e.residual = p.residual; e.out = p.out;
       e.row_off = opix * p.Cout + n0;
       e.ch0 = n0; e.ncols = p.n_tile; e.relu = p.relu; e.out_f32 = p.out_f32; e.valid = valid;
-      uint4 rres[16];
+      uint4 rres[8];
       epi_load_residual(rres, e, 0);            // in flight while the MMAs of this tile finish
       long long tq0 = 0; if (p.dbg) tq0 = clock64();
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
       if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
       ptx::tc_fence_after_sync();
-      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.n_tile));
+      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile));
       if (p.dbg) dbg_work += clock64() - tq0;
-      // all TMEM reads of this thread are complete (wait::ld above): release the accumulator
+      // all TMEM reads of this thread are complete (wait::ld inside): release the accumulator
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
     }
-    if (p.dbg && threadIdx.x == 64) { p.dbg[blockIdx.x * 16 + 8] = dbg_wacc; p.dbg[blockIdx.x * 16 + 9] = dbg_work; p.dbg[blockIdx.x * 16 + 10] = clock64() - dbg_t0; }
+    if (p.dbg && threadIdx.x == 128) {
+      p.dbg[blockIdx.x * 16 + 8] = dbg_wacc; p.dbg[blockIdx.x * 16 + 9] = dbg_work;
+      p.dbg[blockIdx.x * 16 + 10] = clock64() - dbg_t0;
+    }
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (cs > 1) ptx::cluster_sync_all();   // no CTA may exit while peers can still multicast / arrive into it
-  if (warp == 1) {
+  if (warp == 2) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }

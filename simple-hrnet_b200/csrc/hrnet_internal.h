@@ -79,8 +79,9 @@ constexpr int kPatchRows = kPatchPW * kPatchPH;            // 180 pixels
 struct ConvPatchParams {
   int N, H, W, Cin, Cout;
   int tiles_w, tiles_h, total_tiles;
-  int nchunks;                 // channel chunks of the K dimension (each 64 / 32 / 16 channels)
-  int c0[4], kc[4], mapi[4];   // first channel, width, tensor-map index (0: 64, 1: 32, 2: 16)
+  int nchunks;                 // channel chunks of the K dimension: 64-channel patch slots (zero-filled tail)
+  int c0[4], kreal[4];         // first channel, real channels in the chunk (multiple of 16)
+  int bkc[4], mapi[4];         // weight block width (64 / 32 / 16) and its tensor-map index (0 / 1 / 2)
   int boff[4], bblk[4];        // resident-weight block offset / per-tap block size in shared memory
   int b_bytes;                 // shared memory reserved for the resident weights
   int slot_bytes, nslots;      // ring of patch slots (one channel chunk of one tile each)

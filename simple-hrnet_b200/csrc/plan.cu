@@ -151,7 +151,7 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   if (op.cin % 16 || op.cout % 16) return;
   if (!(op.k == 1 || op.k == 3 || op.k == 2)) return;
   ConvTcCfg c;
-  c.kc = op.cin % 64 == 0 ? 64 : (op.cin % 32 == 0 ? 32 : 16);
+  c.kc = 64;   // 128-byte swizzled k-blocks; a channel tail is zero-filled by TMA and skipped by the MMA loop
   int nt = op.cout;
   if (nt > 256) {
     int d = 2;
@@ -159,15 +159,16 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
     nt = op.cout / d;
   }
   c.n_tile = nt;
-  c.bps = 64 / c.kc;
+  c.bps = 1;
   const int a_blk = (int)align_up((size_t)128 * c.kc * 2, 1024);
   const int b_blk = (int)align_up((size_t)nt * c.kc * 2, 1024);
   const int stage = c.bps * (a_blk + b_blk);
   const int fixed = 1024 + 2 * op.cout * 4 + 256;
   const int budget = 200 * 1024;
-  const int nkb = op.k * op.k * (op.cin / c.kc);
+  const int nkb = op.k * op.k * ((op.cin + c.kc - 1) / c.kc);
   const int kstages = (nkb + c.bps - 1) / c.bps;
   c.stages = std::max(2, std::min({8, (budget - fixed) / stage, std::max(2, kstages * 2)}));
+  c.stages &= ~1;   // two producer warps alternate stages
   c.smem_bytes = fixed + c.stages * stage;
   int cols = 32;
   while (cols < 2 * nt) cols *= 2;
@@ -196,26 +197,25 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
   if ((double)(H * W) / (double)(tw * kPatchTW * th * kPatchTH) < 0.85) return false;
   ConvPatchParams p{};
   p.H = H; p.W = W; p.Cin = op.cin; p.Cout = op.cout; p.tiles_w = tw; p.tiles_h = th;
-  int c = 0, n = 0, maxkc = 0;
+  int c = 0, n = 0;
   size_t boff = 0;
   while (c < op.cin) {
-    const int rem = op.cin - c;
-    const int kc = rem >= 64 ? 64 : (rem >= 32 ? 32 : 16);
+    const int real = std::min(64, op.cin - c);
     if (n == 4) return false;
-    p.c0[n] = c; p.kc[n] = kc; p.mapi[n] = kc == 64 ? 0 : (kc == 32 ? 1 : 2);
-    p.bblk[n] = (int)align_up((size_t)op.cout * kc * 2, 1024);
+    const int bkc = real > 32 ? 64 : (real > 16 ? 32 : 16);
+    p.c0[n] = c; p.kreal[n] = real; p.bkc[n] = bkc; p.mapi[n] = bkc == 64 ? 0 : (bkc == 32 ? 1 : 2);
+    p.bblk[n] = (int)align_up((size_t)op.cout * bkc * 2, 1024);
     p.boff[n] = (int)boff;
     boff += (size_t)9 * p.bblk[n];
-    maxkc = std::max(maxkc, kc);
-    c += kc; ++n;
+    c += 64; ++n;
   }
   p.nchunks = n;
   p.b_bytes = (int)boff;
-  p.slot_bytes = (int)align_up((size_t)kPatchRows * maxkc * 2, 1024);
+  p.slot_bytes = (int)align_up((size_t)kPatchRows * 128, 1024);
   const int fixed = 1024 + 2 * op.cout * 4 + 512;
   const int avail = kMaxDynSmem - fixed - p.b_bytes;
   if (avail < 2 * p.slot_bytes) return false;
-  p.nslots = std::min(8, avail / p.slot_bytes);
+  p.nslots = std::min(8, avail / p.slot_bytes) & ~1;   // two producer warps alternate slots
   int cols = 32;
   while (cols < 2 * op.cout) cols *= 2;
   p.tmem_cols = cols;
@@ -540,23 +540,24 @@ int encode_patch(CUtensorMap* tm, const void* act, int N, int H, int W, int C, i
   return 0;
 }
 
-// all tensor maps of a patch op: one activation map and one weight map per chunk width in use
+// all tensor maps of a patch op: one 64-channel activation map and one weight map per block width in use
 int encode_patch_maps(Op& op, const void* act, const void* w, int N) {
   const ConvPatchParams& p = op.pp;
+  int rc = encode_patch(&op.tmPA[0], act, N, p.H, p.W, p.Cin, 64);
+  if (rc) return rc;
+  op.tmPA[1] = op.tmPA[2] = op.tmPA[0];
   bool have[3] = {false, false, false};
   for (int j = 0; j < p.nchunks; ++j) have[p.mapi[j]] = true;
   const int kcs[3] = {64, 32, 16};
   int first = -1;
   for (int i = 0; i < 3; ++i) {
     if (!have[i]) continue;
-    int rc = encode_patch(&op.tmPA[i], act, N, p.H, p.W, p.Cin, kcs[i]);
-    if (rc) return rc;
     rc = encode_weights(&op.tmPB[i], w, p.Cout, 9 * p.Cin, kcs[i], p.Cout);
     if (rc) return rc;
     if (first < 0) first = i;
   }
   for (int i = 0; i < 3; ++i)
-    if (!have[i]) { op.tmPA[i] = op.tmPA[first]; op.tmPB[i] = op.tmPB[first]; }
+    if (!have[i]) op.tmPB[i] = op.tmPB[first];
   return 0;
 }
 
@@ -783,7 +784,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.ksize = op.k; p.stride = op.stride; p.pad_h = plh; p.pad_w = plw;
         p.sub = sub; p.sub_a = sa; p.sub_b = sb;
         p.Cin = op.cin; p.Cout = op.cout;
-        p.kc = op.tc.kc; p.cpt = op.cin / op.tc.kc; p.nkb = op.k * op.k * p.cpt; p.bps = op.tc.bps;
+        p.kc = op.tc.kc; p.cpt = (op.cin + op.tc.kc - 1) / op.tc.kc; p.nkb = op.k * op.k * p.cpt; p.bps = op.tc.bps;
         p.n_tile = op.tc.n_tile; p.n_tiles = op.cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
         p.cs = op.tc.cs;
         p.stages = op.tc.stages; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
@@ -959,9 +960,10 @@ struct DbgTimers {
     cudaFree(dev);
     double a[16] = {0};
     for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
-    fprintf(stderr, "[dbg] %s grid=%d tiles=%d (%.2f/CTA) cycles/CTA: producer wait_empty=%.0f issue=%.0f total=%.0f | "
-            "mma wait_full=%.0f wait_tmem=%.0f issue=%.0f total=%.0f | epilogue wait_acc=%.0f work=%.0f total=%.0f\n",
-            what, grid, tiles, (double)tiles / grid, a[0], a[1], a[2], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+    fprintf(stderr, "[dbg] %s grid=%d tiles=%d (%.2f/CTA) cycles/CTA: producer0 wait_empty=%.0f issue=%.0f total=%.0f | "
+            "producer1 wait_empty=%.0f issue=%.0f | mma wait_full=%.0f wait_tmem=%.0f issue=%.0f total=%.0f | "
+            "epilogue(wg0) wait_acc=%.0f work=%.0f total=%.0f\n",
+            what, grid, tiles, (double)tiles / grid, a[0], a[1], a[2], a[11], a[12], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
   }
 };
 
@@ -1013,7 +1015,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     ConvTcParams p{};
     p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
     p.ksize = ksize; p.stride = stride; p.pad_h = op.pad; p.pad_w = op.pad; p.Cin = cin; p.Cout = cout;
-    p.kc = op.tc.kc; p.cpt = cin / op.tc.kc; p.nkb = ksize * ksize * p.cpt; p.bps = op.tc.bps;
+    p.kc = op.tc.kc; p.cpt = (cin + op.tc.kc - 1) / op.tc.kc; p.nkb = ksize * ksize * p.cpt; p.bps = op.tc.bps;
     p.n_tile = op.tc.n_tile; p.n_tiles = cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
     p.cs = op.tc.cs;
     p.stages = op.tc.stages; p.relu = relu; p.out_f32 = out_f32; p.tmem_cols = op.tc.tmem_cols;
