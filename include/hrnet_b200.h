@@ -107,6 +107,11 @@ int hrnet_forward(HrnetPlan* plan, const float* in_nchw_f32, int n, float* heatm
 int hrnet_forward_host(HrnetPlan* plan, const float* in_nchw_f32_host, int n, float* heatmaps_host,
                        float* joints_host, int32_t* argmax_idx_host, const float* boxes_host, void* stream);
 
+/* Per-op device time: runs the plan's ops one after the other on `stream` (no graph, no branch concurrency) with a
+ * CUDA event pair around every launch; usec_per_op[i] = median over `iters` passes for op i of hrnet_plan_describe.
+ * Used by bench.py for the per-layer-class breakdown.  Synchronises. */
+int hrnet_profile_ops(HrnetPlan* plan, const float* in_nchw_f32, int n, float* usec_per_op, int iters, void* stream);
+
 /* Number of kernels one hrnet_forward(n) launches (for bench.py's gpu_launches). */
 int hrnet_plan_launch_count(const HrnetPlan* plan);
 

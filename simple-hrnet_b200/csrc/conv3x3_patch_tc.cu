@@ -22,6 +22,8 @@
 // weight block of a chunk is as wide as its real channels need (64 / 32 / 16 -> 128 / 64 / 32 B swizzle).
 // Warp roles (2 producers, 1 MMA issuer, 2 epilogue warpgroups), TMEM double buffering and the epilogue as in
 // conv_igemm_tc.cu.
+#include <cstdlib>
+
 #include "hrnet_internal.h"
 #include "epilogue.cuh"
 
@@ -52,6 +54,7 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
   uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   const int warp = ptx::warp_idx_uniform();   // warp-uniform by construction (see ptx::elect_one)
   const int lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();               // the next kernel of the stream may begin its prologue
 
   const uint32_t b_base = smem_base;                              // resident weights
   const uint32_t a_base = smem_base + (uint32_t)p.b_bytes;        // patch slots
@@ -103,6 +106,7 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
       }
       __syncwarp();
     }
+    ptx::pdl_wait();                      // weights are constants; activations need the previous kernel
     int L = 0;                            // running slot-load index over all (tile, chunk) of this CTA
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int img = tile / tiles_per_img;
@@ -186,6 +190,7 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int dh = row >> 3, dw = row & 7;
+    ptx::pdl_wait();                      // residual reads / output writes need the previous kernel
     long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -235,8 +240,22 @@ cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, 
   PatchMaps m;
   m.a = tmA3[0];
   for (int i = 0; i < 3; ++i) m.b[i] = tmB3[i];
-  conv3x3_patch_tc_kernel<<<grid, kPThreads, smem_bytes, st>>>(m, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kPThreads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  int na = 0;
+  static int pdl = -1;
+  if (pdl < 0) pdl = getenv("HRNET_B200_NO_PDL") ? 0 : 1;
+  if (pdl) {   // resident-weight loads and the rest of the prologue overlap the previous kernel's tail
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = (unsigned)na;
+  return cudaLaunchKernelEx(&cfg, conv3x3_patch_tc_kernel, m, p);
 }
 
 }  // namespace hrnet

@@ -27,6 +27,7 @@
 // reference models_/modules.py:56-72 (BasicBlock), :20-40 (Bottleneck) and models_/hrnet.py:23-51,
 // 98-145 (fuse / transition convs).
 #include <algorithm>
+#include <cstdlib>
 
 #include "hrnet_internal.h"
 #include "epilogue.cuh"
@@ -57,6 +58,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   const int warp = ptx::warp_idx_uniform();   // warp-uniform by construction (see ptx::elect_one)
   const int lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();               // the next kernel of the stream may begin its prologue
 
   const int a_stage_bytes = p.bps * p.a_blk_bytes;
   const int b_stage_bytes = p.bps * p.b_blk_bytes;
@@ -92,13 +94,14 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
   if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < p.Cout; i += 256) {
+    for (int i = threadIdx.x - 128; i < p.Cout; i += 256) {   // constants: safe before pdl_wait
       s_scale[i] = p.scale[i];
       s_bias[i] = p.bias[i];
     }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  ptx::pdl_wait();                       // from here on the previous kernel's outputs are visible
   if (cs > 1) ptx::cluster_sync_all();   // peers' barriers must be initialised before any remote arrive / multicast
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
@@ -297,21 +300,32 @@ int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms) {
   return std::min(need, max_clusters) * cs;
 }
 
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("HRNET_B200_NO_PDL") ? 0 : 1;
+  return v == 1;
+}
+
 cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int smem_bytes,
                            int grid, cudaStream_t st) {
-  if (p.cs <= 1) {
-    conv_igemm_tc_kernel<<<grid, kThreads, smem_bytes, st>>>(tmA, tmB, p);
-    return cudaGetLastError();
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)p.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (p.cs > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)p.cs; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {   // prologue overlaps the tail of the previous kernel in the stream (ptx::pdl_wait)
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = (unsigned)na;
   return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel, tmA, tmB, p);
 }
 

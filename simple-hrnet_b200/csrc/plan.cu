@@ -751,7 +751,8 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
     case OP_STEM:
     case OP_STEM7: {
       const ParamInfo& pi = P->params[op.param];
-      auto fn = op.kind == OP_STEM ? launch_stem : launch_stem7;
+      // conv1 runs on the tensor cores unless the SIMT cross-check path is forced
+      auto fn = op.kind == OP_STEM ? ((P->desc.flags & HRNET_FLAG_FORCE_SIMT) ? launch_stem : launch_stem_tc) : launch_stem7;
       CK(fn(in_ext, (const float*)(P->wbase + pi.w_offset), (const float*)(P->wbase + pi.scale_offset),
             (const float*)(P->wbase + pi.bias_offset), (__half*)tptr(op.out), n, P->desc.height, P->desc.width, st));
       return 0;
@@ -911,6 +912,36 @@ int hrnet_forward(HrnetPlan* P, const float* in, int n, float* heatmaps, float* 
     rc = launch_op(P, op, n, in, heatmaps, joints, argmax_idx, boxes, s0);
     if (rc) return rc;
   }
+  return HRNET_OK;
+}
+
+int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, int iters, void* stream) {
+  if (!P || !in || !usec_per_op || iters <= 0) return fail(HRNET_E_INVALID, "bad argument");
+  if (!P->bound) return fail(HRNET_E_STATE, "hrnet_plan_bind must be called first");
+  if (n <= 0 || n > P->desc.max_batch) return fail(HRNET_E_INVALID, "n out of range");
+  cudaStream_t s0 = (cudaStream_t)stream;
+  const int nops = (int)P->ops.size();
+  float* joints = (float*)(P->abase + P->off_joints);
+  int32_t* idx = (int32_t*)(P->abase + P->off_idx);
+  std::vector<cudaEvent_t> ev(nops + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  std::vector<std::vector<float>> t(nops, std::vector<float>(iters));
+  for (int it = -1; it < iters; ++it) {   // iteration -1 = warm-up
+    CK(cudaEventRecord(ev[0], s0));
+    for (int i = 0; i < nops; ++i) {
+      int rc = launch_op(P, P->ops[i], n, in, nullptr, joints, idx, nullptr, s0);
+      if (rc) return rc;
+      CK(cudaEventRecord(ev[i + 1], s0));
+    }
+    CK(cudaStreamSynchronize(s0));
+    if (it >= 0)
+      for (int i = 0; i < nops; ++i) { CK(cudaEventElapsedTime(&t[i][it], ev[i], ev[i + 1])); }
+  }
+  for (int i = 0; i < nops; ++i) {
+    std::sort(t[i].begin(), t[i].end());
+    usec_per_op[i] = t[i][iters / 2] * 1000.f;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
   return HRNET_OK;
 }
 

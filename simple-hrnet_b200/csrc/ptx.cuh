@@ -84,6 +84,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its stream predecessor is still draining; everything before pdl_wait() (barrier init, TMEM alloc, descriptor
+// prefetch, weight loads) overlaps the predecessor's tail, everything after it sees the predecessor's memory.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

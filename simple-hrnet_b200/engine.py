@@ -197,6 +197,16 @@ class B200Engine(Plan):
                                          stream), self.lib)
         return joints, idx, hm
 
+    def profile_ops(self, images, iters=5):
+        """[(op name, op dict, usec)] with one CUDA-event pair per kernel (serial execution, no graph)."""
+        x = self._check_input(images)
+        desc = self.describe()
+        out = (ctypes.c_float * len(desc["ops"]))()
+        with torch.cuda.device(self.device):
+            check(self.lib.hrnet_profile_ops(self._plan, x.data_ptr(), x.shape[0], out, int(iters),
+                                             torch.cuda.current_stream(self.device).cuda_stream), self.lib)
+        return [(op["name"], op, float(t)) for op, t in zip(desc["ops"], out)], desc
+
     def __call__(self, images):
         """Drop-in for `self.model(images)` (SimpleHRNet.py:286): returns the heat-maps."""
         return self.forward_decode(images, return_heatmaps=True)[2]
