@@ -47,6 +47,22 @@ struct PatchMaps {
   CUtensorMap b[3];   // weights, box {64 | 32 | 16, Cout}
 };
 
+// All MMAs of one channel chunk: tap (r, s) = the same patch viewed from pixel row r * 10 + s (8-row core groups are one
+// patch row apart); K advances 32 B (+2 in the descriptor's address field) per K16 step.
+template <int NK>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t bstep, uint32_t idesc,
+                                           uint32_t accumulate_first) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const uint64_t at = a0 + (uint64_t)(((t / 3) * kPatchPW + (t % 3)) * 8);
+    const uint64_t bt = b0 + (uint64_t)(t * bstep);
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+      ptx::mma_f16_ss(d_tmem, at + (uint64_t)(2 * k), bt + (uint64_t)(2 * k), idesc,
+                      (t | k) != 0 ? 1u : accumulate_first);
+  }
+}
+
 __global__ void __launch_bounds__(kPThreads, 1)
 conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -161,16 +177,16 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
         const uint32_t brow = (uint32_t)p.bkc[j] * 2u;          // weight block row bytes == its swizzle span
         const int nk = p.kreal[j] / 16;
         if (ptx::elect_one()) {
-#pragma unroll 1
-          for (int t = 0; t < 9; ++t) {
-            const int r = t / 3, s = t - 3 * r;
-            // tap (r, s) = the same patch viewed from pixel row r * 10 + s; 8-row groups are one patch row apart
-            const uint64_t adesc = ptx::umma_desc_kmajor(a_slot + (uint32_t)(r * kPatchPW + s) * 128u, 128u,
-                                                         (uint32_t)kPatchPW * 128u);
-            const uint64_t bdesc = ptx::umma_desc_kmajor(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), brow, 8u * brow);
-            for (int k = 0; k < nk; ++k)
-              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                              (uint32_t)((j | t | k) != 0));
+          // 9 taps x NK K16-steps, fully unrolled: every descriptor is base + compile-time offset
+          const uint64_t a0 = ptx::umma_desc_kmajor(a_slot, 128u, (uint32_t)kPatchPW * 128u);
+          const uint64_t b0 = ptx::umma_desc_kmajor(b_base + (uint32_t)p.boff[j], brow, 8u * brow);
+          const uint32_t bstep = (uint32_t)p.bblk[j] >> 4;
+          const uint32_t first = (uint32_t)(j != 0);
+          switch (nk) {
+            case 4: issue_taps<4>(d_tmem, a0, b0, bstep, idesc, first); break;
+            case 3: issue_taps<3>(d_tmem, a0, b0, bstep, idesc, first); break;
+            case 2: issue_taps<2>(d_tmem, a0, b0, bstep, idesc, first); break;
+            default: issue_taps<1>(d_tmem, a0, b0, bstep, idesc, first); break;
           }
           ptx::mma_commit(ptx::smem_u32(&bars->a_empty[slot]));
         }
