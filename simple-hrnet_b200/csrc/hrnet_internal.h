@@ -127,6 +127,8 @@ struct Op {
   int stream = 0;
   std::vector<int> deps;       // ops that must complete before this one
   bool needs_event = false;    // some dependant runs on another stream
+  float sm_frac = 1.f;         // share of the SMs this op's persistent grid may occupy (branch-level SM partitioning)
+  int group = -1;              // ops with the same group id run concurrently on different streams and split the SMs
   // tcgen05 path
   bool use_tc = false;
   ConvTcCfg tc;

@@ -281,7 +281,9 @@ int build_hrnet(HrnetPlan& P) {
       for (int k = 0; k < 4; ++k) {
         const std::string p = prefix + ".branches." + std::to_string(i) + "." + std::to_string(k);
         b.conv(p + ".conv1", p + ".conv1", p + ".bn1", cur, ti.C, 3, 1, true, -1, t, arena, i);
+        P.ops.back().group = module_idx;
         b.conv(p + ".conv2", p + ".conv2", p + ".bn2", t, ti.C, 3, 1, true, cur, y[k & 1], arena, i);
+        P.ops.back().group = module_idx;
         cur = y[k & 1];
       }
       ys[i] = cur;
@@ -442,6 +444,30 @@ void finalize_schedule(HrnetPlan& P) {
   for (auto& op : P.ops) {
     choose_tc_cfg(op, P.desc.flags);
     if (op.use_tc && op.in >= 0) choose_patch_cfg(op, P.tensors[op.in].H, P.tensors[op.in].W, P.desc.flags);
+  }
+  // Branch-level SM partitioning: the S branch chains of a StageModule run concurrently on S streams; capping each
+  // branch's persistent grid to its share of the SMs (proportional to its estimated work) lets the chains progress
+  // side by side, so per-kernel prologues / tails / wave quantisation of one branch hide behind the others' MMAs.
+  if (!(P.desc.flags & (HRNET_FLAG_SERIAL | HRNET_FLAG_NO_PARTITION))) {
+    std::map<int, std::map<int, double>> work;   // group -> stream -> estimated SM-cycles of one conv
+    auto est = [&](const Op& op) {
+      const TensorInfo& ti = P.tensors[op.in];
+      const double px = (double)P.desc.max_batch * ti.H * ti.W;
+      const double tiles = std::ceil(px / 128.0);
+      const int n = op.use_patch ? op.cout : op.tc.n_tile;
+      const double nsplit = op.use_patch ? 1.0 : (double)op.cout / n;
+      const double k16 = 9.0 * op.cin / 16.0;
+      const double mma = std::max(n / 2.0, 32.0 + n / 4.0) + (op.use_patch ? 6.0 : (128.0 + n) / 4.0);
+      return tiles * nsplit * (k16 * mma + 900.0);   // calibrated on profiles/r01_dbg_role_timers_v3_kernels_v2.log
+    };
+    for (auto& op : P.ops)
+      if (op.group >= 0 && op.use_tc) work[op.group][op.stream] = est(op);
+    for (auto& op : P.ops) {
+      if (op.group < 0 || !op.use_tc) continue;
+      double tot = 0;
+      for (auto& kv : work[op.group]) tot += kv.second;
+      op.sm_frac = (float)(work[op.group][op.stream] / tot);
+    }
   }
   // every stream's last op must be joined back into stream 0 before the head runs
   int head = -1;
@@ -658,7 +684,7 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     o << "{\"kind\":" << op.kind << ",\"name\":\"" << op.name << "\",\"in\":" << op.in << ",\"out\":" << op.out
       << ",\"res\":" << op.res << ",\"param\":" << op.param << ",\"cin\":" << op.cin << ",\"cout\":" << op.cout
       << ",\"k\":" << op.k << ",\"stride\":" << op.stride << ",\"pad\":" << op.pad << ",\"relu\":" << op.relu
-      << ",\"stream\":" << op.stream << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
+      << ",\"stream\":" << op.stream << ",\"sm_frac\":" << op.sm_frac << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
       << op.src[0] << "," << op.src[1] << "," << op.src[2] << "," << op.src[3] << "],\"shift\":[" << op.shift[0] << ","
       << op.shift[1] << "," << op.shift[2] << "," << op.shift[3] << "],\"deps\":[";
     for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
@@ -778,7 +804,8 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
         p.out = tptr(op.out);
         if (p.total_tiles == 0) return 0;
-        CK(launch_conv_patch(op.tmPA, op.tmPB, p, op.patch_smem, std::min(p.total_tiles, P->num_sms), st));
+        const int cap = std::max(1, (int)std::lround(op.sm_frac * P->num_sms));
+        CK(launch_conv_patch(op.tmPA, op.tmPB, p, op.patch_smem, std::min(p.total_tiles, cap), st));
       } else if (op.use_tc) {
         ConvTcParams p{};
         p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
@@ -797,7 +824,8 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.out = tptr(op.out);
         const int tiles = p.m_tiles * p.n_tiles;
         if (tiles == 0) return 0;
-        CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, conv_tc_grid(p, op.tc.smem_bytes, P->num_sms), st));
+        const int cap = std::max(p.cs, (int)std::lround(op.sm_frac * P->num_sms) / p.cs * p.cs);
+        CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, std::min(cap, conv_tc_grid(p, op.tc.smem_bytes, P->num_sms)), st));
       } else {
         if (sub) return fail(HRNET_E_INVALID, "transposed-conv phases are not wired to the SIMT kernel yet");
         ConvSimtParams p{};
