@@ -44,7 +44,7 @@ extern "C" {
 #define HRNET_FLAG_FUSE_F16 4u     /* store exchange-unit partial terms in fp16 instead of fp32     */
 #define HRNET_FLAG_SERIAL 8u       /* debug: run all branches on the caller's stream                */
 #define HRNET_FLAG_NO_PATCH 16u    /* debug: disable the halo-patch 3x3 kernel (im2col kernel everywhere) */
-#define HRNET_FLAG_NO_PARTITION 32u /* debug: every kernel may use all SMs (no branch-level SM partitioning) */
+#define HRNET_FLAG_PARTITION 32u   /* experiment: split the SMs between the concurrent branch chains (slower) */
 
 typedef struct HrnetPlan HrnetPlan;
 

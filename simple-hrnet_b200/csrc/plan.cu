@@ -445,10 +445,13 @@ void finalize_schedule(HrnetPlan& P) {
     choose_tc_cfg(op, P.desc.flags);
     if (op.use_tc && op.in >= 0) choose_patch_cfg(op, P.tensors[op.in].H, P.tensors[op.in].W, P.desc.flags);
   }
+  // (Opt-in, HRNET_FLAG_PARTITION; measured SLOWER than letting every kernel use all SMs: 12.85 vs 9.9 ms per
+  // W48/64 forward, profiles/r01_exp_variants_partition_pdl.log -- total work is unchanged and the low-resolution
+  // branches lose more to extra tile rounds than the overlap of prologues wins back.)
   // Branch-level SM partitioning: the S branch chains of a StageModule run concurrently on S streams; capping each
   // branch's persistent grid to its share of the SMs (proportional to its estimated work) lets the chains progress
   // side by side, so per-kernel prologues / tails / wave quantisation of one branch hide behind the others' MMAs.
-  if (!(P.desc.flags & (HRNET_FLAG_SERIAL | HRNET_FLAG_NO_PARTITION))) {
+  if ((P.desc.flags & HRNET_FLAG_PARTITION) && !(P.desc.flags & HRNET_FLAG_SERIAL)) {
     std::map<int, std::map<int, double>> work;   // group -> stream -> estimated SM-cycles of one conv
     auto est = [&](const Op& op) {
       const TensorInfo& ti = P.tensors[op.in];
@@ -1053,6 +1056,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.N = n; p.total_tiles = n * p.tiles_w * p.tiles_h; p.relu = relu; p.out_f32 = out_f32;
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
     if (p.total_tiles == 0) return HRNET_OK;
+    if (const char* e = getenv("HRNET_B200_GRID_CAP")) sms = std::max(1, std::min(sms, atoi(e)));   // experiments
     DbgTimers dt; dt.begin(std::min(p.total_tiles, sms)); p.dbg = dt.dev;
     CK(launch_conv_patch(op.tmPA, op.tmPB, p, op.patch_smem, std::min(p.total_tiles, sms), st));
     dt.end(st, "patch", p.total_tiles);
@@ -1071,6 +1075,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (const char* e = getenv("HRNET_B200_GRID_CAP")) sms = std::max(2, std::min(sms, atoi(e)));   // experiments
     ConvTcParams p{};
     p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
     p.ksize = ksize; p.stride = stride; p.pad_h = op.pad; p.pad_w = op.pad; p.Cin = cin; p.Cout = cout;
