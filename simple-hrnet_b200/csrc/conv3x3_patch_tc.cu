@@ -71,6 +71,7 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
   const int warp = ptx::warp_idx_uniform();   // warp-uniform by construction (see ptx::elect_one)
   const int lane = threadIdx.x & 31;
   ptx::pdl_launch_dependents();               // the next kernel of the stream may begin its prologue
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 16] = (long long)ptx::globaltimer();
 
   const uint32_t b_base = smem_base;                              // resident weights
   const uint32_t a_base = smem_base + (uint32_t)p.b_bytes;        // patch slots
@@ -103,6 +104,7 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 17] = (long long)ptx::globaltimer();
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp < 2) {
@@ -147,9 +149,9 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
       }
     }
     if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 16 + 0 + 11 * warp] = dbg_wait;
-      p.dbg[blockIdx.x * 16 + 1 + 11 * warp] = dbg_issue;
-      p.dbg[blockIdx.x * 16 + 2 + 11 * warp] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 32 + 0 + 11 * warp] = dbg_wait;
+      p.dbg[blockIdx.x * 32 + 1 + 11 * warp] = dbg_issue;
+      p.dbg[blockIdx.x * 32 + 2 + 11 * warp] = clock64() - dbg_t0;
     }
   } else if (warp == 2) {
     // ===================================================================== MMA issuer
@@ -171,7 +173,7 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
         const uint32_t phase = (uint32_t)((L / p.nslots) & 1);
         if (p.dbg) tq0 = clock64();
         ptx::mbar_wait(ptx::smem_u32(&bars->a_full[slot]), phase);
-        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; }
+        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (L == 0 && lane == 0) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
         ptx::tc_fence_after_sync();
         const uint32_t a_slot = a_base + (uint32_t)(slot * p.slot_bytes);
         const uint32_t brow = (uint32_t)p.bkc[j] * 2u;          // weight block row bytes == its swizzle span
@@ -197,8 +199,9 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
       __syncwarp();
     }
     if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 16 + 4] = dbg_wfull; p.dbg[blockIdx.x * 16 + 5] = dbg_wtm;
-      p.dbg[blockIdx.x * 16 + 6] = dbg_mma; p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 32 + 19] = (long long)ptx::globaltimer();
+      p.dbg[blockIdx.x * 32 + 4] = dbg_wfull; p.dbg[blockIdx.x * 32 + 5] = dbg_wtm;
+      p.dbg[blockIdx.x * 32 + 6] = dbg_mma; p.dbg[blockIdx.x * 32 + 7] = clock64() - dbg_t0;
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue (two warpgroups, alternating tiles)
@@ -234,17 +237,19 @@ conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchP
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
     }
     if (p.dbg && threadIdx.x == 128) {
-      p.dbg[blockIdx.x * 16 + 8] = dbg_wacc; p.dbg[blockIdx.x * 16 + 9] = dbg_work;
-      p.dbg[blockIdx.x * 16 + 10] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
+      p.dbg[blockIdx.x * 32 + 10] = clock64() - dbg_t0;
     }
   }
 
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 20] = (long long)ptx::globaltimer();
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 21] = (long long)ptx::globaltimer();
 }
 
 cudaError_t conv_patch_set_attributes(int max_smem) {

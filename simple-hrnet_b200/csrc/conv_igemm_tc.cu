@@ -10,7 +10,13 @@
 //     is not a multiple of 64 the last block of a tap overhangs the channel dimension: TMA zero-fills the tail and
 //     the MMA loop only runs the K16 steps that hold real channels (64 B / 32 B swizzled operands measured ~3x
 //     slower per MMA than 128 B ones, profiles/r01_dbg_role_timers_v2_uniform_issue.log).
-//   B (weights [Cout][k*k*Cin] fp16): plain 2D tiled TMA, same swizzle; optionally multicast across a CTA cluster.
+//   B (weights [Cout][k*k*Cin] fp16): plain 2D tiled TMA, same swizzle.
+//   CTA-pair mode (cs == 2, `tcgen05.mma.cta_group::2`): two CTAs of a cluster own neighbouring M-tiles of the same
+//     N-tile; one MMA instruction issued by the leader spans both (M = 256), each CTA feeds its own A tile and only HALF
+//     of the B tile from its shared memory -> per-SM weight traffic (TMA writes + MMA reads of shared memory, the
+//     measured bound of this kernel) halves.  Both CTAs' TMA loads credit the leader's `full` barrier; the leader's
+//     commits are multicast to both CTAs' `empty` / `tmem_full` barriers; both epilogues arrive on the leader's
+//     `tmem_empty`.
 //   D: fp32 accumulators in TMEM, double buffered (2 x n_tile columns) so the epilogue of tile i overlaps the MMAs of
 //     tile i+1.
 //
@@ -59,6 +65,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = ptx::warp_idx_uniform();   // warp-uniform by construction (see ptx::elect_one)
   const int lane = threadIdx.x & 31;
   ptx::pdl_launch_dependents();               // the next kernel of the stream may begin its prologue
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 16] = (long long)ptx::globaltimer();
 
   const int a_stage_bytes = p.bps * p.a_blk_bytes;
   const int b_stage_bytes = p.bps * p.b_blk_bytes;
@@ -68,9 +75,9 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   float* s_bias = s_scale + p.Cout;
   PipeBars* bars = reinterpret_cast<PipeBars*>(s_bias + p.Cout);
 
-  // Cluster of `cs` CTAs = cs consecutive M-tiles of the same N-tile: every CTA loads 1/cs of each weight
-  // k-block and multicasts it to the whole cluster (weights cross the L2->SM path once per cluster).
+  // cs == 2: CTA pair = two consecutive M-tiles of the same N-tile driven by cta_group::2 MMAs (see header).
   const int cs = p.cs;
+  const bool pair = cs == 2;
   const uint32_t crank = cs > 1 ? ptx::cluster_ctarank() : 0u;
   const int cluster_id = blockIdx.x / cs;
   const int num_clusters = gridDim.x / cs;
@@ -83,16 +90,19 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     for (int i = 0; i < p.stages; ++i) {
-      ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), (uint32_t)cs);
+      ptx::mbar_init(ptx::smem_u32(&bars->full[i]), (uint32_t)cs);   // pair: one expect_tx arrival per CTA (leader's barrier)
+      ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128);
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128u * (uint32_t)cs);   // pair: both CTAs' epilogues
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+  if (warp == 2) {
+    if (pair) ptx::tmem_alloc_2cta(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+    else ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+  }
   if (warp >= 4) {
     for (int i = threadIdx.x - 128; i < p.Cout; i += 256) {   // constants: safe before pdl_wait
       s_scale[i] = p.scale[i];
@@ -105,12 +115,12 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (cs > 1) ptx::cluster_sync_all();   // peers' barriers must be initialised before any remote arrive / multicast
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 17] = (long long)ptx::globaltimer();
 
   if (warp < 2) {
     // ===================================================================== TMA producers (stage parity = warp)
     long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    const int b_slice_rows = p.n_tile / cs;
-    const uint32_t b_slice_off = crank * (uint32_t)(b_slice_rows * kKC * 2);
+    const int b_rows = p.n_tile / cs;   // pair: this CTA stages only its half of the weight tile
     int L = 0;                            // running stage-load index over all tiles of this CTA
     for (int st = cluster_id; st < total_super; st += num_clusters) {
       const int nt = st / m_super;
@@ -135,21 +145,34 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t full = ptx::smem_u32(&bars->full[stage]);
         const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
         const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
+        const uint32_t tx = (uint32_t)(nblk * (kTileM * kKC * 2 + b_rows * kKC * 2));
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(full, (uint32_t)(nblk * (kTileM * kKC * 2 + p.n_tile * kKC * 2)));
-          for (int j = 0; j < nblk; ++j) {
-            const int kb = kb0 + j;
-            const int tap = kb / p.cpt;
-            const int c0 = (kb - tap * p.cpt) * kKC;
-            const int r = tap / p.ksize;
-            const int s = tap - r * p.ksize;
-            ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, full, c0, bw, bh, img,
-                                    (uint16_t)s, (uint16_t)r);
-            if (cs == 1)
+          if (!pair) {
+            ptx::mbar_expect_tx(full, tx);
+            for (int j = 0; j < nblk; ++j) {
+              const int kb = kb0 + j;
+              const int tap = kb / p.cpt;
+              const int c0 = (kb - tap * p.cpt) * kKC;
+              const int r = tap / p.ksize;
+              const int s = tap - r * p.ksize;
+              ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, full, c0, bw, bh, img,
+                                      (uint16_t)s, (uint16_t)r);
               ptx::tma_load_2d(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, full, tap * p.Cin + c0, n0);
-            else
-              ptx::tma_load_2d_mc(b_dst + (uint32_t)(j * p.b_blk_bytes) + b_slice_off, &tmB, full, tap * p.Cin + c0,
-                                  n0 + (int)crank * b_slice_rows, mc_mask);
+            }
+          } else {
+            const uint32_t lfull = ptx::mapa_cluster(full, 0);   // the leader's barrier collects both CTAs' bytes
+            ptx::mbar_expect_tx_cluster(lfull, tx);
+            for (int j = 0; j < nblk; ++j) {
+              const int kb = kb0 + j;
+              const int tap = kb / p.cpt;
+              const int c0 = (kb - tap * p.cpt) * kKC;
+              const int r = tap / p.ksize;
+              const int s = tap - r * p.ksize;
+              ptx::tma_load_im2col_4d_2cta(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, lfull, c0, bw, bh, img,
+                                           (uint16_t)s, (uint16_t)r);
+              ptx::tma_load_2d_2cta(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, lfull, tap * p.Cin + c0,
+                                    n0 + (int)crank * b_rows);
+            }
           }
         }
         __syncwarp();
@@ -157,13 +180,13 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
     if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 16 + 0 + 11 * warp] = dbg_wait;
-      p.dbg[blockIdx.x * 16 + 1 + 11 * warp] = dbg_issue;
-      p.dbg[blockIdx.x * 16 + 2 + 11 * warp] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 32 + 0 + 11 * warp] = dbg_wait;
+      p.dbg[blockIdx.x * 32 + 1 + 11 * warp] = dbg_issue;
+      p.dbg[blockIdx.x * 32 + 2 + 11 * warp] = clock64() - dbg_t0;
     }
-  } else if (warp == 2) {
-    // ===================================================================== MMA issuer
-    const uint32_t idesc = ptx::umma_idesc_f16(kTileM, p.n_tile);
+  } else if (warp == 2 && (!pair || crank == 0)) {
+    // ===================================================================== MMA issuer (pair mode: leader CTA only)
+    const uint32_t idesc = ptx::umma_idesc_f16(pair ? 2 * kTileM : kTileM, p.n_tile);
     const int ctail = p.Cin - (p.cpt - 1) * kKC;          // real channels in the last k-block of a tap
     int L = 0;
     int it = 0;
@@ -183,7 +206,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int nblk = min(p.bps, p.nkb - kb0);
         if (p.dbg) tq0 = clock64();
         ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
-        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; }
+        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (L == 0 && lane == 0) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
         ptx::tc_fence_after_sync();
         const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
         const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
@@ -196,23 +219,31 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), 128u, 1024u);
             for (int k = 0; k < nk; ++k) {
               // advancing K by 16 fp16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-              ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                              (uint32_t)((ks | j | k) != 0));
+              if (!pair)
+                ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                (uint32_t)((ks | j | k) != 0));
+              else
+                ptx::mma_f16_ss_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                     (uint32_t)((ks | j | k) != 0));
             }
           }
-          // frees the smem slot (in every CTA of the cluster: peers multicast into it) when the MMAs retire
-          if (cs == 1) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
-          else ptx::mma_commit_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
+          // frees the smem slot (pair: in both CTAs) when the MMAs retire
+          if (!pair) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
+          else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
         }
         __syncwarp();
         if (p.dbg) dbg_mma += clock64() - tq0;
       }
-      if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));  // accumulator ready
+      if (ptx::elect_one()) {   // accumulator ready (pair: for both CTAs' epilogues)
+        if (!pair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+        else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->tmem_full[acc]), mc_mask);
+      }
       __syncwarp();
     }
     if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 16 + 4] = dbg_wfull; p.dbg[blockIdx.x * 16 + 5] = dbg_wtm;
-      p.dbg[blockIdx.x * 16 + 6] = dbg_mma; p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 32 + 19] = (long long)ptx::globaltimer();
+      p.dbg[blockIdx.x * 32 + 4] = dbg_wfull; p.dbg[blockIdx.x * 32 + 5] = dbg_wtm;
+      p.dbg[blockIdx.x * 32 + 6] = dbg_mma; p.dbg[blockIdx.x * 32 + 7] = clock64() - dbg_t0;
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue (two warpgroups, alternating tiles)
@@ -252,20 +283,23 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (p.dbg) dbg_work += clock64() - tq0;
       // all TMEM reads of this thread are complete (wait::ld inside): release the accumulator
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
+      if (!pair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
+      else ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[g]), 0);   // the leader's MMA warp waits for both CTAs
     }
     if (p.dbg && threadIdx.x == 128) {
-      p.dbg[blockIdx.x * 16 + 8] = dbg_wacc; p.dbg[blockIdx.x * 16 + 9] = dbg_work;
-      p.dbg[blockIdx.x * 16 + 10] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
+      p.dbg[blockIdx.x * 32 + 10] = clock64() - dbg_t0;
     }
   }
 
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 20] = (long long)ptx::globaltimer();
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (cs > 1) ptx::cluster_sync_all();   // no CTA may exit while peers can still multicast / arrive into it
   if (warp == 2) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (pair) ptx::tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 

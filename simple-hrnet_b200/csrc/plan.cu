@@ -11,6 +11,7 @@
 // with BN folded to a per-channel fp32 (scale, bias) epilogue, ReLU / residual-add fused into the
 // producing conv, and the four HRNet branches running concurrently on forked streams.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -160,8 +161,15 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   }
   c.n_tile = nt;
   c.bps = 1;
+  // CTA-pair mode (tcgen05 cta_group::2): each CTA stages half of the weight tile; worth it when the weight tile is a
+  // large share of the shared-memory traffic.  HRNET_B200_CS=1|2 overrides (experiments).
+  c.cs = nt >= 96 ? 2 : 1;
+  if (const char* e = getenv("HRNET_B200_CS")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2) c.cs = v;
+  }
   const int a_blk = (int)align_up((size_t)128 * c.kc * 2, 1024);
-  const int b_blk = (int)align_up((size_t)nt * c.kc * 2, 1024);
+  const int b_blk = (int)align_up((size_t)(nt / c.cs) * c.kc * 2, 1024);
   const int stage = c.bps * (a_blk + b_blk);
   const int fixed = 1024 + 2 * op.cout * 4 + 256;
   const int budget = 200 * 1024;
@@ -173,14 +181,6 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   int cols = 32;
   while (cols < 2 * nt) cols *= 2;
   c.tmem_cols = cols;
-  // weight multicast across a cluster of CTAs working on neighbouring M-tiles: worth it when the weight tile is a
-  // large share of the per-tile L2->SM traffic.  HRNET_B200_CS=1|2|4 overrides (experiments).
-  c.cs = nt >= 96 ? 2 : 1;
-  if (const char* e = getenv("HRNET_B200_CS")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2 || v == 4) c.cs = v;
-  }
-  while (c.cs > 1 && (nt % c.cs || (nt / c.cs) % 8)) c.cs /= 2;
   op.tc = c;
   op.use_tc = true;
 }
@@ -820,7 +820,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.cs = op.tc.cs;
         p.stages = op.tc.stages; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
         p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
-        p.b_blk_bytes = (int)align_up((size_t)p.n_tile * p.kc * 2, 1024);
+        p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
         p.scale = (const float*)(P->wbase + pi.scale_offset);
         p.bias = (const float*)(P->wbase + pi.bias_offset);
         p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
@@ -1011,17 +1011,26 @@ struct DbgTimers {
   void begin(int g) {
     if (!getenv("HRNET_B200_DBG")) return;
     grid = g;
-    if (cudaMalloc(&dev, (size_t)g * 16 * sizeof(long long)) != cudaSuccess) { dev = nullptr; return; }
-    cudaMemset(dev, 0, (size_t)g * 16 * sizeof(long long));
+    if (cudaMalloc(&dev, (size_t)g * 32 * sizeof(long long)) != cudaSuccess) { dev = nullptr; return; }
+    cudaMemset(dev, 0, (size_t)g * 32 * sizeof(long long));
   }
   void end(cudaStream_t st, const char* what, int tiles) {
     if (!dev) return;
     cudaStreamSynchronize(st);
-    std::vector<long long> h((size_t)grid * 16);
+    std::vector<long long> h((size_t)grid * 32);
     cudaMemcpy(h.data(), dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     cudaFree(dev);
     double a[16] = {0};
-    for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 16 + k] / grid;
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 16; ++k) a[k] += (double)h[(size_t)b * 32 + k] / grid;
+    // wall-clock (globaltimer, ns) milestones relative to the earliest CTA entry
+    long long t0 = LLONG_MAX, tmax[6] = {0, 0, 0, 0, 0, 0};
+    double tavg[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = 0; b < grid; ++b) t0 = std::min(t0, h[(size_t)b * 32 + 16]);
+    for (int b = 0; b < grid; ++b)
+      for (int k = 0; k < 6; ++k) { const long long v = h[(size_t)b * 32 + 16 + k] - t0; tmax[k] = std::max(tmax[k], v); tavg[k] += (double)v / grid; }
+    fprintf(stderr, "[dbg-ns] %s avg/max ns since first CTA entry: entry %.0f/%lld setup_done %.0f/%lld first_operands %.0f/%lld "
+            "mma_loop_end %.0f/%lld roles_done %.0f/%lld exit %.0f/%lld\n", what, tavg[0], tmax[0], tavg[1], tmax[1], tavg[2], tmax[2],
+            tavg[3], tmax[3], tavg[4], tmax[4], tavg[5], tmax[5]);
     fprintf(stderr, "[dbg] %s grid=%d tiles=%d (%.2f/CTA) cycles/CTA: producer0 wait_empty=%.0f issue=%.0f total=%.0f | "
             "producer1 wait_empty=%.0f issue=%.0f | mma wait_full=%.0f wait_tmem=%.0f issue=%.0f total=%.0f | "
             "epilogue(wg0) wait_acc=%.0f work=%.0f total=%.0f\n",
@@ -1084,7 +1093,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.cs = op.tc.cs;
     p.stages = op.tc.stages; p.relu = relu; p.out_f32 = out_f32; p.tmem_cols = op.tc.tmem_cols;
     p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
-    p.b_blk_bytes = (int)align_up((size_t)p.n_tile * p.kc * 2, 1024);
+    p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
     const int tiles = p.m_tiles * p.n_tiles;
     if (tiles == 0) return HRNET_OK;
