@@ -54,6 +54,9 @@ struct __align__(8) PipeBars {
   uint32_t pad;
 };
 
+// kPair is a template parameter (not a run-time flag): a kernel that contains cta_group::2 instructions can only be
+// launched as a cluster of CTA pairs ("cluster misconfiguration" otherwise).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const ConvTcParams p) {
@@ -76,9 +79,10 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   PipeBars* bars = reinterpret_cast<PipeBars*>(s_bias + p.Cout);
 
   // cs == 2: CTA pair = two consecutive M-tiles of the same N-tile driven by cta_group::2 MMAs (see header).
-  const int cs = p.cs;
-  const bool pair = cs == 2;
-  const uint32_t crank = cs > 1 ? ptx::cluster_ctarank() : 0u;
+  constexpr bool pair = kPair;
+  constexpr int cs = kPair ? 2 : 1;
+  uint32_t crank = 0u;
+  if constexpr (kPair) crank = ptx::cluster_ctarank();
   const int cluster_id = blockIdx.x / cs;
   const int num_clusters = gridDim.x / cs;
   const int m_super = (p.m_tiles + cs - 1) / cs;
@@ -100,7 +104,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
-    if (pair) ptx::tmem_alloc_2cta(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+    if constexpr (kPair) ptx::tmem_alloc_2cta(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
     else ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
   }
   if (warp >= 4) {
@@ -112,7 +116,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::pdl_wait();                       // from here on the previous kernel's outputs are visible
-  if (cs > 1) ptx::cluster_sync_all();   // peers' barriers must be initialised before any remote arrive / multicast
+  if constexpr (kPair) ptx::cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 17] = (long long)ptx::globaltimer();
@@ -147,7 +151,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
         const uint32_t tx = (uint32_t)(nblk * (kTileM * kKC * 2 + b_rows * kKC * 2));
         if (ptx::elect_one()) {
-          if (!pair) {
+          if constexpr (!kPair) {
             ptx::mbar_expect_tx(full, tx);
             for (int j = 0; j < nblk; ++j) {
               const int kb = kb0 + j;
@@ -219,7 +223,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), 128u, 1024u);
             for (int k = 0; k < nk; ++k) {
               // advancing K by 16 fp16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-              if (!pair)
+              if constexpr (!kPair)
                 ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                 (uint32_t)((ks | j | k) != 0));
               else
@@ -228,14 +232,14 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
           // frees the smem slot (pair: in both CTAs) when the MMAs retire
-          if (!pair) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
+          if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
           else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
         }
         __syncwarp();
         if (p.dbg) dbg_mma += clock64() - tq0;
       }
       if (ptx::elect_one()) {   // accumulator ready (pair: for both CTAs' epilogues)
-        if (!pair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+        if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
         else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->tmem_full[acc]), mc_mask);
       }
       __syncwarp();
@@ -284,7 +288,7 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // all TMEM reads of this thread are complete (wait::ld inside): release the accumulator
       ptx::tc_fence_before_sync();
       if (!pair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
-      else ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[g]), 0);   // the leader's MMA warp waits for both CTAs
+      else if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[g]), 0);   // the leader's MMA warp waits for both CTAs
     }
     if (p.dbg && threadIdx.x == 128) {
       p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
@@ -295,16 +299,18 @@ conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 20] = (long long)ptx::globaltimer();
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (cs > 1) ptx::cluster_sync_all();   // no CTA may exit while peers can still multicast / arrive into it
+  if constexpr (kPair) ptx::cluster_sync_all();   // no CTA may exit while its peer can still arrive on / read from it
   if (warp == 2) {
     ptx::tc_fence_after_sync();
-    if (pair) ptx::tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
+    if constexpr (kPair) ptx::tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
     else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
 cudaError_t conv_tc_set_attributes(int max_smem) {
-  return cudaFuncSetAttribute(conv_igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv_igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
 }
 
 // grid size for a persistent launch: as many clusters as can be co-resident (cudaOccupancyMaxActiveClusters), capped
@@ -326,7 +332,7 @@ int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms) {
       at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, conv_igemm_tc_kernel, &cfg) == cudaSuccess && nc > 0) cached[cs] = nc;
+      if (cudaOccupancyMaxActiveClusters(&nc, conv_igemm_tc_kernel<true>, &cfg) == cudaSuccess && nc > 0) cached[cs] = nc;
       else { cudaGetLastError(); cached[cs] = num_sms / cs; }
     }
     max_clusters = cached[cs];
@@ -360,7 +366,8 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     ++na;
   }
   cfg.attrs = at; cfg.numAttrs = (unsigned)na;
-  return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel, tmA, tmB, p);
+  if (p.cs > 1) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true>, tmA, tmB, p);
+  return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false>, tmA, tmB, p);
 }
 
 }  // namespace hrnet
