@@ -161,13 +161,19 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   }
   c.n_tile = nt;
   c.bps = 1;
-  // CTA-pair mode (tcgen05 cta_group::2): each CTA stages half of the weight tile; worth it when the weight tile is a
-  // large share of the shared-memory traffic.  HRNET_B200_CS=1|2 overrides (experiments).
-  c.cs = nt >= 96 ? 2 : 1;
+  // CTA-pair mode (tcgen05 cta_group::2): each CTA stages half of the weight tile.  Measured on B200 it makes the
+  // large-N kernels faster in isolation (stage-4 C=192/384 convs 46 -> 42.7 us, 2.3x fewer clk per GEMM row) but the
+  // whole W48/64 forward slower (9.76 vs 9.46 ms: pair clusters co-schedule worse with the other branches' kernels,
+  // profiles/r01_exp_pair_mode_scope.log), so it is opt-in: HRNET_B200_CS=2 (optionally HRNET_B200_CS_MINK=<K>).
+  c.cs = 1;
   if (const char* e = getenv("HRNET_B200_CS")) {
     const int v = atoi(e);
     if (v == 1 || v == 2) c.cs = v;
   }
+  if (const char* e = getenv("HRNET_B200_CS_MINK")) {   // experiments: pair mode only for convs with at least this K
+    if (op.k * op.k * op.cin < atoi(e)) c.cs = 1;
+  }
+  if (nt % 16 || (nt / 2) % 8) c.cs = 1;
   const int a_blk = (int)align_up((size_t)128 * c.kc * 2, 1024);
   const int b_blk = (int)align_up((size_t)(nt / c.cs) * c.kc * 2, 1024);
   const int stage = c.bps * (a_blk + b_blk);

@@ -86,6 +86,17 @@ def test_forward_variants_agree():
     assert np.abs(f16 - ref).max() < 1e-3 and np.abs(base - ref).max() < 1e-3
 
 
+def test_profile_ops_reports_every_launch():
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=4, bn="default")
+    e = _engine("hrnet", 32, (128, 96), 2, sd)
+    x = torch.randn(2, 3, 128, 96, generator=torch.Generator().manual_seed(1)).cuda()
+    ops, desc = e.profile_ops(x, iters=2)
+    assert len(ops) == e.launch_count == len(desc["ops"]) == 317
+    assert all(t > 0 for _, _, t in ops)
+    # profiling does not disturb the result
+    assert torch.equal(e(x), _engine("hrnet", 32, (128, 96), 2, sd)(x))
+
+
 def test_batch_invariance_and_chunking_full_size():
     """BASELINE-size property (W48 384x288, N=64): each person's result is independent of its batch
     neighbours (eval-mode BN) -> forward(batch)[i] == forward(batch[i:i+1]) bit-exactly,

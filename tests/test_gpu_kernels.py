@@ -76,6 +76,18 @@ def test_conv_patch_equals_im2col_kernel_bitwise_f32():
         G.run_conv(bad, use_tc=2)
 
 
+@pytest.mark.parametrize("shape", [(3, 24, 18, 192, 192, 3, 1), (5, 12, 9, 384, 384, 3, 1), (2, 24, 18, 192, 384, 3, 2),
+                                   (1, 16, 12, 256, 512, 1, 2), (2, 48, 36, 96, 96, 3, 1)], ids=lambda s: "x".join(map(str, s)))
+def test_conv_tc_pair_mode_matches_cpu(shape, monkeypatch):
+    """CTA-pair mode (tcgen05 cta_group::2, opt-in via HRNET_B200_CS=2): M=256 MMAs over a 2-CTA cluster, half weight
+    tile per CTA, odd tile counts (ghost CTA), N split."""
+    monkeypatch.setenv("HRNET_B200_CS", "2")
+    case = G.conv_case(*shape, relu=True, residual=(shape[6] == 1 and shape[3] == shape[4]), out_f32=False, seed=8)
+    out = G.run_conv(case, use_tc=1)
+    err = (out - case["ref"]).abs().max().item()
+    assert err <= G.conv_tolerance(case), f"max abs err {err}"
+
+
 @pytest.mark.parametrize("shape", [(2, 24, 18, 192, 48, 1, 1), (2, 48, 36, 96, 192, 3, 2)], ids=str)
 def test_conv_tc_f32_output_no_relu(shape):
     case = G.conv_case(*shape, relu=False, residual=False, out_f32=True, seed=2)
