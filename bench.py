@@ -47,6 +47,18 @@ def load_peaks():
     return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def load_traffic():
+    """ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, extracted from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json, written by tools/ncu_traffic.py); None if no capture exists."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -96,6 +108,25 @@ def make_weights():
     return O.make_state_dict(O.hrnet_param_spec(C, J), seed=0, bn="default")
 
 
+def best_cpu_threads(sd):
+    """The CPU arm gets its best thread count: oneDNN is often slower with every hardware thread of a big host
+    (measured 0.45-1.3 persons/s at 128 threads vs several at 16-32).  Quick calibration on a 4-person forward."""
+    from oracle import hrnet_oracle as O
+    ncpu = os.cpu_count() or 1
+    cands = sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True)
+    if len(cands) == 1:
+        return cands[0], {}
+    x = torch.randn(4, 3, H, W, generator=torch.Generator().manual_seed(0))
+    res = {}
+    for t in cands:
+        torch.set_num_threads(t)
+        O.hrnet_forward(sd, x[:1])
+        t0 = time.perf_counter()
+        O.hrnet_forward(sd, x)
+        res[t] = time.perf_counter() - t0
+    return min(res, key=res.get), {k: round(v, 2) for k, v in res.items()}
+
+
 def cpu_reference_persons_per_s(sd, n_persons, reps, threads):
     """The reference's CPU path (oracle port: same aten ops as models_/hrnet.py + the numpy decode)."""
     from oracle import hrnet_oracle as O
@@ -116,7 +147,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     sd = make_weights()
-    threads = os.cpu_count() or 1
+    threads, calib = best_cpu_threads(sd)
     n = 16
     cpu_reference_persons_per_s(sd, 2, 1, threads)
     ts = []
@@ -138,7 +169,8 @@ def run_reference(args, rank):
                                   "the reference PyTorch path), bounded sample of 16 persons per step",
                       "per_gpu_batch": PER_GPU_BATCH},
            "cpu_baseline": {"value": v, "unit": "persons/s", "cores": threads, "kind": "port",
-                            "sample": f"{n} persons x {len(ts)} steps, torch {torch.__version__} CPU, {threads} threads"},
+                            "sample": f"{n} persons x {len(ts)} steps, torch {torch.__version__} CPU, {threads} of {os.cpu_count()} "
+                                      f"threads (fastest of a 4-person calibration {calib})"},
            "e2e": {"value": v, "unit": "persons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -279,7 +311,7 @@ def main():
                               "pass of the whole network; achieved = algorithmic conv FLOPs / summed kernel time",
                     "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                     "frac": round(ach / peaks["tflops_sustained"], 4),
-                    "frac_of_burst_peak": round(ach / peaks["tflops"], 4), "traffic": None,
+                    "frac_of_burst_peak": round(ach / peaks["tflops"], 4), "traffic": load_traffic(),
                     "peak_source": peaks["source"] + ", sustained (kernels timed inside a long step)",
                     "launches": cls_n[k4], "us_total": round(cls_t[k4], 1),
                     "per_branch": [{"C": k[0], "map": k[1], "kernel": k[2], "launches": v[2], "us_avg": round(v[0] / v[2], 2),
@@ -289,11 +321,12 @@ def main():
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads, calib = best_cpu_threads(sd)
         v, ts = cpu_reference_persons_per_s(sd, 16, 2, threads)
         cpu = {"value": round(v, 3), "unit": "persons/s", "cores": threads, "kind": "port",
-               "sample": f"16 persons x 2 reps (after warm-up), oracle CPU fp32 forward + numpy decode, "
-                         f"{threads} threads, rep times {[round(t, 2) for t in ts]} s"}
+               "sample": f"16 persons x 2 reps (after warm-up), oracle CPU fp32 forward + numpy decode, {threads} of "
+                         f"{os.cpu_count()} threads (fastest of a 4-person calibration {calib}), rep times "
+                         f"{[round(t, 2) for t in ts]} s"}
 
     if rank == 0:
         step_tflops = GFLOP_PER_PERSON * value / 1e3
