@@ -113,7 +113,8 @@ def best_cpu_threads(sd):
     (measured 0.45-1.3 persons/s at 128 threads vs several at 16-32).  Quick calibration on a 4-person forward."""
     from oracle import hrnet_oracle as O
     ncpu = os.cpu_count() or 1
-    cands = sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True)
+    # capped at 64: a 4-person forward on all 128 threads of the round-1 GPU host took 123 s (oversubscribed oneDNN)
+    cands = sorted({min(ncpu, 64), min(ncpu, 32), min(ncpu, 16)}, reverse=True)
     if len(cands) == 1:
         return cands[0], {}
     x = torch.randn(4, 3, H, W, generator=torch.Generator().manual_seed(0))
@@ -248,15 +249,16 @@ def main():
     value = B * args.steps / (ms_total / 1e3)
 
     # ---- e2e: host (pinned) buffers through hrnet_forward_host, H2D + D2H inside the timed region
-    xh = [torch.randn(hi - lo, 3, H, W, generator=gen).pin_memory() for _ in range(2)]
+    # the reference-facing call: uint8 BGR crops at network resolution in (pinned) host memory -> joints in host memory
+    xh = [torch.randint(0, 256, (hi - lo, H, W, 3), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(2)]
     xh_np = [t.numpy() for t in xh]
     for i in range(3):
-        eng.forward_host(xh_np[i % 2])
+        eng.forward_host_u8(xh_np[i % 2])
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(3, args.steps // 2)
     for i in range(e2e_steps):
-        jh, ih, _ = eng.forward_host(xh_np[i % 2])
+        jh, ih, _ = eng.forward_host_u8(xh_np[i % 2])
         if world > 1:   # the gathered result is what a multi-GPU caller receives
             buf = torch.empty(B, J, 3, device=dev)
             buf[lo:hi].copy_(torch.from_numpy(jh), non_blocking=True)
@@ -267,7 +269,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = B * e2e_steps / float(e2e_s.item())
-    h2d = (hi - lo) * 3 * H * W * 4
+    h2d = (hi - lo) * 3 * H * W          # uint8 images; normalisation runs in the stem kernel
     d2h = (hi - lo) * J * 3 * 4 + (hi - lo) * J * 4
 
     # ---- dominant kernel: the stage-4 3x3 implicit-GEMM branch convs, timed live inside the network with one CUDA
@@ -340,7 +342,8 @@ def main():
                           "collective": "one NCCL all_gather_into_tensor of joints [B,17,3] f32 per step" if world > 1 else "none"},
                "clocks": clocks,
                "e2e": {"value": round(e2e_value, 2), "unit": "persons/s", "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                       "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                       "call": "hrnet_forward_host_u8: pinned uint8 BGR crops [n,384,288,3] -> H2D -> forward + decode -> D2H joints"},
                "gpu_launches": eng.launch_count * args.steps,
                "step_flops": {"tflops": round(step_tflops, 1), "per_gpu_tflops": round(step_tflops / world, 1),
                               "frac_of_sustained_peak": round(step_tflops / world / peaks["tflops_sustained"], 4),

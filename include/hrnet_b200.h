@@ -41,7 +41,7 @@ extern "C" {
 /* plan flags */
 #define HRNET_FLAG_FORCE_SIMT 1u   /* debug: run every conv on the SIMT cross-check kernel          */
 #define HRNET_FLAG_NO_GRAPH 2u     /* debug: launch kernels directly instead of replaying a graph   */
-#define HRNET_FLAG_FUSE_F16 4u     /* store exchange-unit partial terms in fp16 instead of fp32     */
+#define HRNET_FLAG_FUSE_F32 4u     /* store exchange-unit partial terms in fp32 (default fp16: same accuracy, faster) */
 #define HRNET_FLAG_SERIAL 8u       /* debug: run all branches on the caller's stream                */
 #define HRNET_FLAG_NO_PATCH 16u    /* debug: disable the halo-patch 3x3 kernel (im2col kernel everywhere) */
 #define HRNET_FLAG_PARTITION 32u   /* experiment: split the SMs between the concurrent branch chains (slower) */
@@ -107,6 +107,15 @@ int hrnet_forward(HrnetPlan* plan, const float* in_nchw_f32, int n, float* heatm
  * Synchronises `stream` before returning. */
 int hrnet_forward_host(HrnetPlan* plan, const float* in_nchw_f32_host, int n, float* heatmaps_host,
                        float* joints_host, int32_t* argmax_idx_host, const float* boxes_host, void* stream);
+
+/* Same two calls fed with the reference's pre-transform images: [n,H,W,3] BGR uint8 at network resolution (what
+ * SimpleHRNet hands to cv2.cvtColor + ToTensor + Normalize, SimpleHRNet.py:222,149-153).  The stem kernel applies
+ * BGR->RGB, /255 and the ImageNet mean/std with the same fp32 operation order, so results are bit-identical to the
+ * fp32 entry points while the host->device copy is 4x smaller.  HRNet only. */
+int hrnet_forward_u8(HrnetPlan* plan, const uint8_t* images_nhwc_bgr_u8, int n, float* heatmaps, float* joints,
+                     int32_t* argmax_idx, const float* boxes, void* stream);
+int hrnet_forward_host_u8(HrnetPlan* plan, const uint8_t* images_nhwc_bgr_u8_host, int n, float* heatmaps_host,
+                          float* joints_host, int32_t* argmax_idx_host, const float* boxes_host, void* stream);
 
 /* Per-op device time: runs the plan's ops one after the other on `stream` (no graph, no branch concurrency) with a
  * CUDA event pair around every launch; usec_per_op[i] = median over `iters` passes for op i of hrnet_plan_describe.

@@ -27,7 +27,7 @@ class HrnetParamInfo(ctypes.Structure):
 
 
 ARCH_HRNET, ARCH_POSERESNET = 0, 1
-FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F16, FLAG_SERIAL, FLAG_NO_PATCH, FLAG_PARTITION = 1, 2, 4, 8, 16, 32
+FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F32, FLAG_SERIAL, FLAG_NO_PATCH, FLAG_PARTITION = 1, 2, 4, 8, 16, 32
 
 # every symbol include/hrnet_b200.h declares: (name, restype, argtypes)
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
@@ -42,6 +42,8 @@ SYMBOLS = {
     "hrnet_plan_bind": (_i, [_vp, _vp, _sz, _vp, _sz]),
     "hrnet_forward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hrnet_forward_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hrnet_forward_u8": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hrnet_forward_host_u8": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hrnet_plan_launch_count": (_i, [_vp]),
     "hrnet_profile_ops": (_i, [_vp, _vp, _i, ctypes.POINTER(ctypes.c_float), _i, _vp]),
     "hrnet_conv_bn_act": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

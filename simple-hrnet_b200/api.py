@@ -17,7 +17,8 @@ class SimpleHRNet:
     def __init__(self, c, nof_joints, checkpoint_path, model_name='HRNet', resolution=(384, 288),
                  interpolation=None, multiperson=True, return_heatmaps=False, return_bounding_boxes=False,
                  max_batch_size=32, yolo_version='v3', yolo_model_def=None, yolo_class_path=None,
-                 yolo_weights_path=None, device=torch.device("cuda"), enable_tensorrt=False, engine_flags=0):
+                 yolo_weights_path=None, device=torch.device("cuda"), enable_tensorrt=False, engine_flags=0,
+                 device_preprocess=True):
         self.c = c
         self.nof_joints = nof_joints
         self.checkpoint_path = checkpoint_path
@@ -58,6 +59,9 @@ class SimpleHRNet:
             self.model.load_state_dict(checkpoint['model'])
         else:
             self.model.load_state_dict(checkpoint)
+        # device-side transform (uint8 in) for HRNet at a fixed resolution; set device_preprocess=False to feed the
+        # host-normalised fp32 tensor exactly like the reference does
+        self._u8_path = bool(device_preprocess) and arch == "hrnet" and self.resolution is not None
         self._mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1, 1)
         self._std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1, 1)
 
@@ -82,6 +86,29 @@ class SimpleHRNet:
             return self._predict_batch(image)
         else:
             raise ValueError('Wrong image format.')
+
+    def _resize_only(self, image):
+        import cv2
+        interp = cv2.INTER_CUBIC if self.interpolation is None else self.interpolation
+        if self.resolution is not None:
+            image = cv2.resize(image, (self.resolution[1], self.resolution[0]), interpolation=interp)
+        return image
+
+    def _run_u8(self, images_u8, boxes):
+        """HRNet fast path: the uint8 BGR crops go to the device as they are (4x fewer bytes than the fp32 tensor) and
+        cvtColor + ToTensor + Normalize happen inside the stem kernel, bit-identically to the host transform."""
+        n = images_u8.shape[0]
+        J, Hh, Wh = self.nof_joints, self.resolution[0] // 4, self.resolution[1] // 4
+        pts = np.empty((n, J, 3), dtype=np.float32)
+        heatmaps = np.zeros((n, J, Hh, Wh), dtype=np.float32)
+        dev = torch.from_numpy(np.ascontiguousarray(images_u8)).to(self.device)
+        for i in range(0, n, self.max_batch_size):
+            sl = slice(i, min(n, i + self.max_batch_size))
+            joints, _idx, hm = self.model.forward_decode_u8(dev[sl], boxes=boxes[sl], return_heatmaps=self.return_heatmaps)
+            pts[sl] = joints.cpu().numpy()
+            if hm is not None:
+                heatmaps[sl] = hm.cpu().numpy()
+        return heatmaps, pts
 
     def _run(self, images, boxes):
         n = images.shape[0]
@@ -109,19 +136,24 @@ class SimpleHRNet:
 
     def _predict_single(self, image):
         old_res = image.shape
-        images = self._prep(image).unsqueeze(dim=0)
         boxes = np.asarray([[0, 0, old_res[1], old_res[0]]], dtype=np.float32)   # [x1, y1, x2, y2]
-        heatmaps, pts = self._run(images, boxes)
+        if self._u8_path:
+            heatmaps, pts = self._run_u8(self._resize_only(image)[None], boxes)
+        else:
+            heatmaps, pts = self._run(self._prep(image).unsqueeze(dim=0), boxes)
         return self._pack(heatmaps, boxes, pts)
 
     def _predict_batch(self, images):
         if images.shape[0] == 0:
             raise ValueError  # the reference reaches `raise ValueError` for an empty non-multiperson batch (:487)
         old_res = images[0].shape
-        x = torch.empty(images.shape[0], 3, self.resolution[0], self.resolution[1])
-        for i, image in enumerate(images):
-            x[i] = self._prep(image)
         boxes = np.repeat(np.asarray([[0, 0, old_res[1], old_res[0]]], dtype=np.float32), len(images), axis=0)
-        heatmaps, pts = self._run(x, boxes)
+        if self._u8_path:
+            heatmaps, pts = self._run_u8(np.stack([self._resize_only(im) for im in images]), boxes)
+        else:
+            x = torch.empty(images.shape[0], 3, self.resolution[0], self.resolution[1])
+            for i, image in enumerate(images):
+                x[i] = self._prep(image)
+            heatmaps, pts = self._run(x, boxes)
         pts = np.expand_dims(pts, axis=1)                                # SimpleHRNet.py:475
         return self._pack(heatmaps, boxes, pts)

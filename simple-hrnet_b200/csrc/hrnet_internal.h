@@ -148,6 +148,8 @@ cudaError_t launch_stem(const float* in_nchw, const float* w, const float* scale
                         int N, int H, int W, cudaStream_t st);
 cudaError_t launch_stem_tc(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
                            int N, int H, int W, cudaStream_t st);
+cudaError_t launch_stem_tc_u8(const uint8_t* in_nhwc_bgr, const float* w, const float* scale, const float* bias,
+                              __half* out, int N, int H, int W, cudaStream_t st);
 cudaError_t launch_fuse(const FuseParams& p, cudaStream_t st);
 cudaError_t launch_head(const __half* in, const float* w, const float* bias, float* out_nchw, int N, int HW, int Cin,
                         int J, cudaStream_t st);

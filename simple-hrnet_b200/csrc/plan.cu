@@ -57,6 +57,7 @@ struct HrnetPlan {
   cudaEvent_t fork_ev = nullptr;
   std::map<int, cudaGraphExec_t> graphs;
   int launch_count = 0;
+  bool input_u8 = false;   // current call feeds NHWC BGR uint8 images (hrnet_forward_u8)
 };
 
 namespace {
@@ -76,7 +77,7 @@ struct Builder {
   std::vector<int> last_on_stream = std::vector<int>(4, -1);
   size_t wcur = 0;
 
-  explicit Builder(HrnetPlan& p) : P(p), maxb(p.desc.max_batch), fuse_f16((p.desc.flags & HRNET_FLAG_FUSE_F16) != 0) {}
+  explicit Builder(HrnetPlan& p) : P(p), maxb(p.desc.max_batch), fuse_f16((p.desc.flags & HRNET_FLAG_FUSE_F32) == 0) {}
 
   int new_tensor(int arena, int C, int H, int W, int dtype = DT_F16) {
     TensorInfo t;
@@ -787,6 +788,13 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
     case OP_STEM7: {
       const ParamInfo& pi = P->params[op.param];
       // conv1 runs on the tensor cores unless the SIMT cross-check path is forced
+      if (P->input_u8) {
+        if (op.kind != OP_STEM) return fail(HRNET_E_INVALID, "uint8 image input is implemented for the HRNet stem only");
+        CK(launch_stem_tc_u8((const uint8_t*)in_ext, (const float*)(P->wbase + pi.w_offset),
+                             (const float*)(P->wbase + pi.scale_offset), (const float*)(P->wbase + pi.bias_offset),
+                             (__half*)tptr(op.out), n, P->desc.height, P->desc.width, st));
+        return 0;
+      }
       auto fn = op.kind == OP_STEM ? ((P->desc.flags & HRNET_FLAG_FORCE_SIMT) ? launch_stem : launch_stem_tc) : launch_stem7;
       CK(fn(in_ext, (const float*)(P->wbase + pi.w_offset), (const float*)(P->wbase + pi.scale_offset),
             (const float*)(P->wbase + pi.bias_offset), (__half*)tptr(op.out), n, P->desc.height, P->desc.width, st));
@@ -949,6 +957,42 @@ int hrnet_forward(HrnetPlan* P, const float* in, int n, float* heatmaps, float* 
     rc = launch_op(P, op, n, in, heatmaps, joints, argmax_idx, boxes, s0);
     if (rc) return rc;
   }
+  return HRNET_OK;
+}
+
+int hrnet_forward_u8(HrnetPlan* P, const uint8_t* images_nhwc_bgr, int n, float* heatmaps, float* joints,
+                     int32_t* argmax_idx, const float* boxes, void* stream) {
+  if (!P) return fail(HRNET_E_INVALID, "null plan");
+  if (P->desc.arch != HRNET_ARCH_HRNET) return fail(HRNET_E_INVALID, "uint8 image input is implemented for HRNet only");
+  P->input_u8 = true;
+  const int rc = hrnet_forward(P, reinterpret_cast<const float*>(images_nhwc_bgr), n, heatmaps, joints, argmax_idx, boxes, stream);
+  P->input_u8 = false;
+  return rc;
+}
+
+int hrnet_forward_host_u8(HrnetPlan* P, const uint8_t* images_h, int n, float* heatmaps_h, float* joints_h,
+                          int32_t* idx_h, const float* boxes_h, void* stream) {
+  if (!P) return fail(HRNET_E_INVALID, "null plan");
+  if (!P->bound) return fail(HRNET_E_STATE, "hrnet_plan_bind must be called before hrnet_forward_host_u8");
+  if (n < 0 || n > P->desc.max_batch) return fail(HRNET_E_INVALID, "n out of range [0, max_batch]");
+  if (n == 0) return HRNET_OK;
+  if (!images_h || !joints_h) return fail(HRNET_E_INVALID, "null input / joints pointer");
+  cudaStream_t s0 = (cudaStream_t)stream;
+  const int J = P->desc.nof_joints;
+  uint8_t* in_d = P->abase + P->off_in_stage;
+  float* joints_d = (float*)(P->abase + P->off_joints);
+  int32_t* idx_d = (int32_t*)(P->abase + P->off_idx);
+  float* boxes_d = boxes_h ? (float*)(P->abase + P->off_boxes) : nullptr;
+  CK(cudaMemcpyAsync(in_d, images_h, (size_t)n * 3 * P->desc.height * P->desc.width, cudaMemcpyHostToDevice, s0));
+  if (boxes_h) CK(cudaMemcpyAsync(boxes_d, boxes_h, (size_t)n * 16, cudaMemcpyHostToDevice, s0));
+  int rc = hrnet_forward_u8(P, in_d, n, nullptr, joints_d, idx_d, boxes_d, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(joints_h, joints_d, (size_t)n * J * 12, cudaMemcpyDeviceToHost, s0));
+  if (idx_h) CK(cudaMemcpyAsync(idx_h, idx_d, (size_t)n * J * 4, cudaMemcpyDeviceToHost, s0));
+  if (heatmaps_h)
+    CK(cudaMemcpyAsync(heatmaps_h, P->abase + P->tensors[P->t_heatmaps].offset, (size_t)n * J * P->Hh * P->Wh * 4,
+                       cudaMemcpyDeviceToHost, s0));
+  CK(cudaStreamSynchronize(s0));
   return HRNET_OK;
 }
 

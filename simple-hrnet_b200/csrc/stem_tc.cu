@@ -31,9 +31,16 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int row, int chunk, const
   *reinterpret_cast<uint4*>(blk + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
 }
 
+// kU8 = true: the input is the reference's *pre-transform* image batch, NHWC BGR uint8 at network resolution, and the
+// kernel applies cvtColor(BGR2RGB) + ToTensor (/255) + Normalize(mean, std) (SimpleHRNet.py:222,149-153) on the fly with
+// the same fp32 operation order (IEEE div / sub / div), so the result is bit-identical to feeding the host-normalised
+// fp32 tensor -- while the host->device copy shrinks 4x (3 B instead of 12 B per input pixel).
+template <bool kU8>
 __global__ void __launch_bounds__(128)
-stem_conv3x3s2_tc_kernel(const float* __restrict__ in, const float* __restrict__ w, const float* __restrict__ scale,
+stem_conv3x3s2_tc_kernel(const void* __restrict__ in_any, const float* __restrict__ w, const float* __restrict__ scale,
                          const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W) {
+  const float* in = static_cast<const float*>(in_any);
+  const uint8_t* in8 = static_cast<const uint8_t*>(in_any);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (sbase - ptx::smem_u32(smem_raw));
@@ -67,6 +74,8 @@ stem_conv3x3s2_tc_kernel(const float* __restrict__ in, const float* __restrict__
       const int rem = (int)(pix - (long)n * OH * OW);
       const int oh = rem / OW, ow = rem - oh * OW;
       const float* ip = in + (size_t)n * 3 * H * W;
+      const uint8_t* ip8 = in8 + (size_t)n * H * W * 3;
+      const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};   // RGB, SimpleHRNet.py:152
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int ih = oh * 2 - 1 + r;
@@ -75,8 +84,18 @@ stem_conv3x3s2_tc_kernel(const float* __restrict__ in, const float* __restrict__
           const int iw = ow * 2 - 1 + s;
           const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci)
-            x[(r * 3 + s) * 3 + ci] = ok ? __ldg(ip + ((size_t)ci * H + ih) * W + iw) : 0.f;
+          for (int ci = 0; ci < 3; ++ci) {
+            float v = 0.f;    // zero padding applies to the normalised tensor
+            if (ok) {
+              if constexpr (kU8) {
+                const float u = (float)__ldg(ip8 + ((size_t)ih * W + iw) * 3 + (2 - ci));   // BGR -> RGB
+                v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), mean[ci]), stdv[ci]);
+              } else {
+                v = __ldg(ip + ((size_t)ci * H + ih) * W + iw);
+              }
+            }
+            x[(r * 3 + s) * 3 + ci] = v;
+          }
         }
       }
     }
@@ -156,19 +175,33 @@ stem_conv3x3s2_tc_kernel(const float* __restrict__ in, const float* __restrict__
   if (warp == 0) { ptx::tc_fence_after_sync(); ptx::tmem_dealloc(tmem, 64); }
 }
 
-cudaError_t launch_stem_tc(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
-                           int N, int H, int W, cudaStream_t st) {
+static cudaError_t launch_stem_tc_any(const void* in, bool u8, const float* w, const float* scale, const float* bias,
+                                      __half* out, int N, int H, int W, cudaStream_t st) {
   const long total = (long)N * (H / 2) * (W / 2);
   if (total == 0) return cudaSuccess;
   const int smem = 1024 + 49152 + 512 + 64;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(stem_conv3x3s2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(stem_conv3x3s2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(stem_conv3x3s2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  stem_conv3x3s2_tc_kernel<<<(unsigned)((total + 127) / 128), 128, smem, st>>>(in_nchw, w, scale, bias, out, N, H, W);
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  if (u8) stem_conv3x3s2_tc_kernel<true><<<grid, 128, smem, st>>>(in, w, scale, bias, out, N, H, W);
+  else stem_conv3x3s2_tc_kernel<false><<<grid, 128, smem, st>>>(in, w, scale, bias, out, N, H, W);
   return cudaGetLastError();
+}
+
+cudaError_t launch_stem_tc(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
+                           int N, int H, int W, cudaStream_t st) {
+  return launch_stem_tc_any(in_nchw, false, w, scale, bias, out, N, H, W, st);
+}
+
+cudaError_t launch_stem_tc_u8(const uint8_t* in_nhwc_bgr, const float* w, const float* scale, const float* bias,
+                              __half* out, int N, int H, int W, cudaStream_t st) {
+  return launch_stem_tc_any(in_nhwc_bgr, true, w, scale, bias, out, N, H, W, st);
 }
 
 }  // namespace hrnet

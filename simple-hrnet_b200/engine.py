@@ -197,6 +197,52 @@ class B200Engine(Plan):
                                          stream), self.lib)
         return joints, idx, hm
 
+    def forward_decode_u8(self, images_u8, boxes=None, return_heatmaps=False, joints_out=None):
+        """Same as forward_decode, fed with the reference's pre-transform images: [n,H,W,3] BGR uint8 on the device at
+        network resolution.  BGR->RGB, /255 and the ImageNet mean/std run inside the stem kernel (bit-identical to the
+        host transform of SimpleHRNet.py:149-153)."""
+        if self._weights is None:
+            raise HrnetError("load_state_dict must be called before running the engine")
+        x = images_u8
+        if x.dtype != torch.uint8 or x.dim() != 4 or tuple(x.shape[1:]) != (self.H, self.W, 3):
+            raise ValueError(f"expected uint8 [n,{self.H},{self.W},3], got {x.dtype} {tuple(x.shape)}")
+        if x.shape[0] > self.max_batch:
+            raise ValueError(f"batch {x.shape[0]} > max_batch {self.max_batch}")
+        if x.device != self.device:
+            raise ValueError(f"input on {x.device}, engine on {self.device}")
+        x = x.contiguous()
+        n = x.shape[0]
+        with torch.cuda.device(self.device):
+            joints = joints_out if joints_out is not None else torch.empty(n, self.J, 3, dtype=torch.float32, device=self.device)
+            idx = torch.empty(n, self.J, dtype=torch.int32, device=self.device)
+            hm = torch.empty(n, self.J, self.H // 4, self.W // 4, dtype=torch.float32, device=self.device) if return_heatmaps else None
+            bx = None
+            if boxes is not None:
+                bx = torch.as_tensor(boxes, dtype=torch.float32).to(self.device).contiguous()
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            check(self.lib.hrnet_forward_u8(self._plan, x.data_ptr(), n, hm.data_ptr() if hm is not None else None,
+                                            joints.data_ptr(), idx.data_ptr(), bx.data_ptr() if bx is not None else None,
+                                            stream), self.lib)
+        return joints, idx, hm
+
+    def forward_host_u8(self, images_u8_host, boxes_host=None, want_heatmaps=False):
+        """End-to-end call with HOST uint8 images [n,H,W,3] BGR (ideally pinned): H2D (3 B/pixel) + forward + D2H."""
+        if self._weights is None:
+            raise HrnetError("load_state_dict must be called before running the engine")
+        x = np.ascontiguousarray(images_u8_host, dtype=np.uint8)
+        assert x.ndim == 4 and x.shape[1:] == (self.H, self.W, 3)
+        n = x.shape[0]
+        joints = np.empty((n, self.J, 3), dtype=np.float32)
+        idx = np.empty((n, self.J), dtype=np.int32)
+        hm = np.empty((n, self.J, self.H // 4, self.W // 4), dtype=np.float32) if want_heatmaps else None
+        bx = np.ascontiguousarray(boxes_host, dtype=np.float32) if boxes_host is not None else None
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            check(self.lib.hrnet_forward_host_u8(self._plan, x.ctypes.data, n, hm.ctypes.data if hm is not None else None,
+                                                 joints.ctypes.data, idx.ctypes.data,
+                                                 bx.ctypes.data if bx is not None else None, stream), self.lib)
+        return joints, idx, hm
+
     def profile_ops(self, images, iters=5):
         """[(op name, op dict, usec)] with one CUDA-event pair per kernel (serial execution, no graph)."""
         x = self._check_input(images)

@@ -67,7 +67,7 @@ def test_forward_matches_reference_fixture(golden_dir, name, tol_scale):
 
 def test_forward_variants_agree():
     """graph vs direct launch vs serial streams are bit-identical; the SIMT cross-check path agrees to
-    accumulation-order noise; fp16 exchange terms stay inside the bar."""
+    accumulation-order noise; fp32 exchange terms (opt-in) and the default fp16 ones both stay inside the bar."""
     sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=4, bn="default")
     x = torch.randn(3, 3, 128, 96, generator=torch.Generator().manual_seed(1)).cuda()
     ref = O.hrnet_forward(sd, x.cpu()).numpy()
@@ -82,8 +82,8 @@ def test_forward_variants_agree():
     # different accumulation order flips fp16 roundings; through ~60 layers the two fp16 pipelines drift apart by
     # about as much as either drifts from the fp32 reference (measured 6.5e-4 on B200)
     assert np.abs(simt - base).max() < 1.5e-3 and np.abs(simt - ref).max() < 1e-3
-    f16 = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_FUSE_F16)(x).cpu().numpy()
-    assert np.abs(f16 - ref).max() < 1e-3 and np.abs(base - ref).max() < 1e-3
+    f32 = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_FUSE_F32)(x).cpu().numpy()
+    assert np.abs(f32 - ref).max() < 1e-3 and np.abs(base - ref).max() < 1e-3
 
 
 def test_profile_ops_reports_every_launch():
@@ -162,6 +162,27 @@ def test_simplehrnet_predict_api(golden_dir):
         SimpleHRNet(32, 17, sd, model_name="vgg", multiperson=False)
     with pytest.raises(ValueError, match="Wrong device name"):
         SimpleHRNet(32, 17, sd, multiperson=False, device=torch.device("cpu"))
+
+
+def test_uint8_input_path_is_bit_identical_to_host_transform(golden_dir):
+    """hrnet_forward_u8: cvtColor + ToTensor + Normalize inside the stem kernel == the reference's host transform."""
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=0, bn="default")
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 256, (5, 256, 192, 3), dtype=np.uint8)
+    imgs[0] = 0; imgs[1] = 255                                           # extremes
+    e = _engine("hrnet", 32, (256, 192), 8, sd)
+    x = O.preprocess(imgs, (256, 192))                                   # reference host transform (no resize needed)
+    jf, idf, hf = e.forward_decode(x.cuda(), return_heatmaps=True)
+    ju, idu, hu = e.forward_decode_u8(torch.from_numpy(imgs).cuda(), return_heatmaps=True)
+    assert torch.equal(hf, hu) and torch.equal(jf, ju) and torch.equal(idf, idu)
+    jh, ih, hh = e.forward_host_u8(imgs, want_heatmaps=True)
+    assert np.array_equal(jh, ju.cpu().numpy()) and np.array_equal(hh, hu.cpu().numpy())
+    # public API: device_preprocess on/off give identical results
+    a = SimpleHRNet(32, 17, sd, resolution=(256, 192), multiperson=False, max_batch_size=8, device=torch.device("cuda:0"))
+    b = SimpleHRNet(32, 17, sd, resolution=(256, 192), multiperson=False, max_batch_size=8, device=torch.device("cuda:0"),
+                    device_preprocess=False)
+    assert np.array_equal(a.predict(imgs), b.predict(imgs))
+    assert np.array_equal(a.predict(imgs[2]), b.predict(imgs[2]))
 
 
 def test_poseresnet_forward_matches_reference_fixture(golden_dir):
