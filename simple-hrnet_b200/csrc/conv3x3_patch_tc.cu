@@ -1,255 +1,14 @@
-// 3x3 stride-1 convolution with halo-patch operand reuse on tcgen05 (sm_100a).
-//
-// The im2col kernel (conv_igemm_tc.cu) re-fetches every input pixel nine times (once per filter tap) and
-// streams the weights once per 128-pixel tile; measured on B200 it is bound by the L2->SM path
-// (~28 B/clk/SM, ~4 clk per TMA row) at 5-26 % of tensor peak.  This kernel removes that traffic:
-//
-//   * output tile = 8 (w) x 16 (h) pixels of one image = 128 GEMM rows; its 10 x 18 input patch
-//     (1-pixel halo, zero-filled out of bounds by TMA) is loaded ONCE per channel chunk by a tiled 4-D
-//     TMA into swizzled shared memory, [18][10] pixels x (kc * 2) bytes.
-//   * each of the 9 filter taps is then just a *row-shifted view* of that patch: the UMMA shared-memory
-//     descriptor starts at patch + (r * 10 + s) pixel rows and steps 10 rows between 8-row core groups
-//     (SBO = 10 * row bytes).  tcgen05 applies the swizzle to absolute shared-memory address bits, so a
-//     descriptor that starts on a 128 B (not 1024 B) boundary reads exactly what TMA wrote
-//     (profiles/r01_exp_shifted_umma_descriptor.log).
-//   * the weights of all 9 taps stay resident in shared memory for the whole persistent CTA.
-//
-// L2->SM traffic per tile drops from 9 x (128 x Cin) + 9 x Cin x Cout to 180 x Cin elements.
-//
-// Channel chunks: the patch of every chunk is a 64-channel (128 B per pixel, SWIZZLE_128B) slot; when Cin is not a
-// multiple of 64 the last chunk overhangs the channel dimension, TMA zero-fills the tail and only the K16 steps
-// holding real channels are issued (64 B / 32 B swizzled A operands measured ~3x slower per MMA).  The resident
-// weight block of a chunk is as wide as its real channels need (64 / 32 / 16 -> 128 / 64 / 32 B swizzle).
-// Warp roles (2 producers, 1 MMA issuer, 2 epilogue warpgroups), TMEM double buffering and the epilogue as in
-// conv_igemm_tc.cu.
+// Single-problem launch of the halo-patch 3x3 conv (body and documentation: conv3x3_patch_body.cuh).
 #include <cstdlib>
 
-#include "hrnet_internal.h"
-#include "epilogue.cuh"
+#include "conv3x3_patch_body.cuh"
 
 namespace hrnet {
-
-constexpr int kPThreads = 384;
-constexpr int kPMaxSlots = 8;
-
-struct __align__(8) PatchBars {
-  uint64_t b_full;
-  uint64_t a_full[kPMaxSlots];
-  uint64_t a_empty[kPMaxSlots];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
-  uint32_t tmem_base;
-  uint32_t pad;
-};
-
-struct PatchMaps {
-  CUtensorMap a;      // activations, box {64, 10, 18, 1}, SWIZZLE_128B
-  CUtensorMap b[3];   // weights, box {64 | 32 | 16, Cout}
-};
-
-// All MMAs of one channel chunk: tap (r, s) = the same patch viewed from pixel row r * 10 + s (8-row core groups are one
-// patch row apart); K advances 32 B (+2 in the descriptor's address field) per K16 step.
-template <int NK>
-__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t bstep, uint32_t idesc,
-                                           uint32_t accumulate_first) {
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const uint64_t at = a0 + (uint64_t)(((t / 3) * kPatchPW + (t % 3)) * 8);
-    const uint64_t bt = b0 + (uint64_t)(t * bstep);
-#pragma unroll
-    for (int k = 0; k < NK; ++k)
-      ptx::mma_f16_ss(d_tmem, at + (uint64_t)(2 * k), bt + (uint64_t)(2 * k), idesc,
-                      (t | k) != 0 ? 1u : accumulate_first);
-  }
-}
 
 __global__ void __launch_bounds__(kPThreads, 1)
 conv3x3_patch_tc_kernel(const __grid_constant__ PatchMaps maps, const ConvPatchParams p) {
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  const int warp = ptx::warp_idx_uniform();   // warp-uniform by construction (see ptx::elect_one)
-  const int lane = threadIdx.x & 31;
-  ptx::pdl_launch_dependents();               // the next kernel of the stream may begin its prologue
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 16] = (long long)ptx::globaltimer();
-
-  const uint32_t b_base = smem_base;                              // resident weights
-  const uint32_t a_base = smem_base + (uint32_t)p.b_bytes;        // patch slots
-  float* s_scale = reinterpret_cast<float*>(smem_aligned + (size_t)p.b_bytes + (size_t)p.nslots * p.slot_bytes);
-  float* s_bias = s_scale + p.Cout;
-  PatchBars* bars = reinterpret_cast<PatchBars*>(s_bias + p.Cout);
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&maps.a);
-    for (int i = 0; i < 3; ++i) ptx::prefetch_tmap(&maps.b[i]);
-    ptx::mbar_init(ptx::smem_u32(&bars->b_full), 1);
-    for (int i = 0; i < p.nslots; ++i) {
-      ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[i]), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
-  if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < p.Cout; i += 256) {
-      s_scale[i] = p.scale[i];
-      s_bias[i] = p.bias[i];
-    }
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = bars->tmem_base;
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 17] = (long long)ptx::globaltimer();
-  const int tiles_per_img = p.tiles_w * p.tiles_h;
-
-  if (warp < 2) {
-    // ===================================================================== TMA producers (slot parity = warp)
-    long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    if (warp == 0) {
-      // resident weights: 9 taps x nchunks blocks of [Cout rows x bkc channels]
-      uint32_t btx = 0;
-      for (int j = 0; j < p.nchunks; ++j) btx += 9u * (uint32_t)(p.Cout * p.bkc[j] * 2);
-      const uint32_t bfull = ptx::smem_u32(&bars->b_full);
-      if (ptx::elect_one()) {
-        ptx::mbar_expect_tx(bfull, btx);
-        for (int j = 0; j < p.nchunks; ++j)
-          for (int t = 0; t < 9; ++t)
-            ptx::tma_load_2d(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), &maps.b[p.mapi[j]], bfull,
-                             t * p.Cin + p.c0[j], 0);
-      }
-      __syncwarp();
-    }
-    ptx::pdl_wait();                      // weights are constants; activations need the previous kernel
-    int L = 0;                            // running slot-load index over all (tile, chunk) of this CTA
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int img = tile / tiles_per_img;
-      const int rem = tile - img * tiles_per_img;
-      const int th = rem / p.tiles_w;
-      const int tw = rem - th * p.tiles_w;
-      for (int j = 0; j < p.nchunks; ++j, ++L) {
-        if ((L & 1) != warp) continue;
-        const int slot = L % p.nslots;
-        const uint32_t phase = (uint32_t)((L / p.nslots) & 1);
-        long long tq0 = 0; if (p.dbg) tq0 = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[slot]), phase ^ 1u);
-        if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
-        const uint32_t full = ptx::smem_u32(&bars->a_full[slot]);
-        if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 128));
-          ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a, full, p.c0[j], tw * kPatchTW - 1,
-                           th * kPatchTH - 1, img);
-        }
-        __syncwarp();
-        if (p.dbg) dbg_issue += clock64() - tq0;
-      }
-    }
-    if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 32 + 0 + 11 * warp] = dbg_wait;
-      p.dbg[blockIdx.x * 32 + 1 + 11 * warp] = dbg_issue;
-      p.dbg[blockIdx.x * 32 + 2 + 11 * warp] = clock64() - dbg_t0;
-    }
-  } else if (warp == 2) {
-    // ===================================================================== MMA issuer
-    const uint32_t idesc = ptx::umma_idesc_f16(128, p.Cout);
-    ptx::mbar_wait(ptx::smem_u32(&bars->b_full), 0);
-    int L = 0;
-    int it = 0;
-    long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      long long tq0 = 0; if (p.dbg) tq0 = clock64();
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
-      if (p.dbg) dbg_wtm += clock64() - tq0;
-      ptx::tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
-      for (int j = 0; j < p.nchunks; ++j, ++L) {
-        const int slot = L % p.nslots;
-        const uint32_t phase = (uint32_t)((L / p.nslots) & 1);
-        if (p.dbg) tq0 = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->a_full[slot]), phase);
-        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (L == 0 && lane == 0) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
-        ptx::tc_fence_after_sync();
-        const uint32_t a_slot = a_base + (uint32_t)(slot * p.slot_bytes);
-        const uint32_t brow = (uint32_t)p.bkc[j] * 2u;          // weight block row bytes == its swizzle span
-        const int nk = p.kreal[j] / 16;
-        if (ptx::elect_one()) {
-          // 9 taps x NK K16-steps, fully unrolled: every descriptor is base + compile-time offset
-          const uint64_t a0 = ptx::umma_desc_kmajor(a_slot, 128u, (uint32_t)kPatchPW * 128u);
-          const uint64_t b0 = ptx::umma_desc_kmajor(b_base + (uint32_t)p.boff[j], brow, 8u * brow);
-          const uint32_t bstep = (uint32_t)p.bblk[j] >> 4;
-          const uint32_t first = (uint32_t)(j != 0);
-          switch (nk) {
-            case 4: issue_taps<4>(d_tmem, a0, b0, bstep, idesc, first); break;
-            case 3: issue_taps<3>(d_tmem, a0, b0, bstep, idesc, first); break;
-            case 2: issue_taps<2>(d_tmem, a0, b0, bstep, idesc, first); break;
-            default: issue_taps<1>(d_tmem, a0, b0, bstep, idesc, first); break;
-          }
-          ptx::mma_commit(ptx::smem_u32(&bars->a_empty[slot]));
-        }
-        __syncwarp();
-        if (p.dbg) dbg_mma += clock64() - tq0;
-      }
-      if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
-      __syncwarp();
-    }
-    if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 32 + 19] = (long long)ptx::globaltimer();
-      p.dbg[blockIdx.x * 32 + 4] = dbg_wfull; p.dbg[blockIdx.x * 32 + 5] = dbg_wtm;
-      p.dbg[blockIdx.x * 32 + 6] = dbg_mma; p.dbg[blockIdx.x * 32 + 7] = clock64() - dbg_t0;
-    }
-  } else if (warp >= 4) {
-    // ===================================================================== epilogue (two warpgroups, alternating tiles)
-    const int g = (warp - 4) >> 2;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int dh = row >> 3, dw = row & 7;
-    ptx::pdl_wait();                      // residual reads / output writes need the previous kernel
-    long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != g) continue;
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int img = tile / tiles_per_img;
-      const int rem = tile - img * tiles_per_img;
-      const int th = rem / p.tiles_w;
-      const int tw = rem - th * p.tiles_w;
-      const int oh = th * kPatchTH + dh, ow = tw * kPatchTW + dw;
-      const bool valid = oh < p.H && ow < p.W;
-      EpiRow e;
-      e.s_scale = s_scale; e.s_bias = s_bias; e.residual = p.residual; e.out = p.out;
-      e.row_off = (((size_t)img * p.H + oh) * p.W + ow) * p.Cout;
-      e.ch0 = 0; e.ncols = p.Cout; e.relu = p.relu; e.out_f32 = p.out_f32; e.valid = valid;
-      uint4 rres[8];
-      epi_load_residual(rres, e, 0);            // in flight while the MMAs of this tile finish
-      long long tq0 = 0; if (p.dbg) tq0 = clock64();
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
-      if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
-      ptx::tc_fence_after_sync();
-      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cout));
-      if (p.dbg) dbg_work += clock64() - tq0;
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
-    }
-    if (p.dbg && threadIdx.x == 128) {
-      p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
-      p.dbg[blockIdx.x * 32 + 10] = clock64() - dbg_t0;
-    }
-  }
-
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 20] = (long long)ptx::globaltimer();
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 2) {
-    ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-  }
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 21] = (long long)ptx::globaltimer();
+  conv3x3_patch_body(maps, p, (int)blockIdx.x, (int)gridDim.x, smem_raw);
 }
 
 cudaError_t conv_patch_set_attributes(int max_smem) {

@@ -1,310 +1,17 @@
-// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05) for sm_100a.
-//
-//   out[p, co] = act( scale[co] * sum_{r,s,ci} in[pix(p) + (r,s), ci] * w[co, r, s, ci] + bias[co] (+ residual[p, co]) )
-//
-// GEMM view: M = output pixels (n, oh, ow) flattened (NHWC), N = Cout, K = k*k*Cin (tap-major).
-//   A (activations): never materialised.  Each k-block (one filter tap x 64 input channels) of a 128-pixel M-tile
-//     is fetched by ONE TMA im2col load (cp.async.bulk.tensor.4d...im2col): the hardware walks 128 consecutive
-//     output pixels across row / image boundaries, applies the tap offset and the conv stride, and zero-fills the
-//     padding halo.  It lands in shared memory in the 128B-swizzled K-major layout tcgen05.mma consumes.  When Cin
-//     is not a multiple of 64 the last block of a tap overhangs the channel dimension: TMA zero-fills the tail and
-//     the MMA loop only runs the K16 steps that hold real channels (64 B / 32 B swizzled operands measured ~3x
-//     slower per MMA than 128 B ones, profiles/r01_dbg_role_timers_v2_uniform_issue.log).
-//   B (weights [Cout][k*k*Cin] fp16): plain 2D tiled TMA, same swizzle.
-//   CTA-pair mode (cs == 2, `tcgen05.mma.cta_group::2`): two CTAs of a cluster own neighbouring M-tiles of the same
-//     N-tile; one MMA instruction issued by the leader spans both (M = 256), each CTA feeds its own A tile and only HALF
-//     of the B tile from its shared memory -> per-SM weight traffic (TMA writes + MMA reads of shared memory, the
-//     measured bound of this kernel) halves.  Both CTAs' TMA loads credit the leader's `full` barrier; the leader's
-//     commits are multicast to both CTAs' `empty` / `tmem_full` barriers; both epilogues arrive on the leader's
-//     `tmem_empty`.
-//   D: fp32 accumulators in TMEM, double buffered (2 x n_tile columns) so the epilogue of tile i overlaps the MMAs of
-//     tile i+1.
-//
-// Persistent, warp-specialised CTA (384 threads, 1 CTA/SM):
-//   warps 0-1 : TMA producers, alternating pipeline stages (one producer's wait -> expect_tx -> issue chain costs
-//               ~480 + 80/TMA clk per stage, profiles/r01_exp_tma_issue.log; two chains run concurrently)
-//   warp  2   : TMEM alloc + MMA issuer (tcgen05.mma / tcgen05.commit)
-//   warp  3   : idle
-//   warps 4-7 / 8-11 : two epilogue warpgroups, alternating tiles: tcgen05.ld -> BN scale/bias (fp32) -> +residual
-//               -> ReLU -> fp16/fp32 NHWC store
-// All role loops are warp-uniform with one elected lane issuing (ptx::elect_one).
-//
-// Replaces, for the hot path, every nn.Conv2d + nn.BatchNorm2d (+ReLU, + `out += residual`) pair of
-// reference models_/modules.py:56-72 (BasicBlock), :20-40 (Bottleneck) and models_/hrnet.py:23-51,
-// 98-145 (fuse / transition convs).
+// Single-problem launches of the TMA-im2col implicit-GEMM conv (body and documentation: conv_igemm_body.cuh).
 #include <algorithm>
 #include <cstdlib>
 
-#include "hrnet_internal.h"
-#include "epilogue.cuh"
+#include "conv_igemm_body.cuh"
 
 namespace hrnet {
 
-constexpr int kTileM = 128;
-constexpr int kThreads = 384;
-constexpr int kMaxStages = 8;
-constexpr int kKC = 64;                 // channels per k-block: 128-byte swizzled rows
-
-struct __align__(8) PipeBars {
-  uint64_t full[kMaxStages];
-  uint64_t empty[kMaxStages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
-  uint32_t tmem_base;
-  uint32_t pad;
-};
-
-// kPair is a template parameter (not a run-time flag): a kernel that contains cta_group::2 instructions can only be
-// launched as a cluster of CTA pairs ("cluster misconfiguration" otherwise).
 template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  // stage buffers need swizzle-atom (1024 B) alignment
-  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-
-  const int warp = ptx::warp_idx_uniform();   // warp-uniform by construction (see ptx::elect_one)
-  const int lane = threadIdx.x & 31;
-  ptx::pdl_launch_dependents();               // the next kernel of the stream may begin its prologue
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 16] = (long long)ptx::globaltimer();
-
-  const int a_stage_bytes = p.bps * p.a_blk_bytes;
-  const int b_stage_bytes = p.bps * p.b_blk_bytes;
-  const int stage_bytes = a_stage_bytes + b_stage_bytes;
-  // layout: [stages x (A blocks | B blocks)] [scale Cout f32] [bias Cout f32] [barriers]
-  float* s_scale = reinterpret_cast<float*>(smem_aligned + (size_t)p.stages * stage_bytes);
-  float* s_bias = s_scale + p.Cout;
-  PipeBars* bars = reinterpret_cast<PipeBars*>(s_bias + p.Cout);
-
-  // cs == 2: CTA pair = two consecutive M-tiles of the same N-tile driven by cta_group::2 MMAs (see header).
-  constexpr bool pair = kPair;
-  constexpr int cs = kPair ? 2 : 1;
-  uint32_t crank = 0u;
-  if constexpr (kPair) crank = ptx::cluster_ctarank();
-  const int cluster_id = blockIdx.x / cs;
-  const int num_clusters = gridDim.x / cs;
-  const int m_super = (p.m_tiles + cs - 1) / cs;
-  const int total_super = m_super * p.n_tiles;
-  const uint16_t mc_mask = (uint16_t)((1u << cs) - 1u);
-  const int nstages_k = (p.nkb + p.bps - 1) / p.bps;  // pipeline stages consumed per tile
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA);
-    ptx::prefetch_tmap(&tmB);
-    for (int i = 0; i < p.stages; ++i) {
-      ptx::mbar_init(ptx::smem_u32(&bars->full[i]), (uint32_t)cs);   // pair: one expect_tx arrival per CTA (leader's barrier)
-      ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128u * (uint32_t)cs);   // pair: both CTAs' epilogues
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 2) {
-    if constexpr (kPair) ptx::tmem_alloc_2cta(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
-    else ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
-  }
-  if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < p.Cout; i += 256) {   // constants: safe before pdl_wait
-      s_scale[i] = p.scale[i];
-      s_bias[i] = p.bias[i];
-    }
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  ptx::pdl_wait();                       // from here on the previous kernel's outputs are visible
-  if constexpr (kPair) ptx::cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive
-  ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = bars->tmem_base;
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 17] = (long long)ptx::globaltimer();
-
-  if (warp < 2) {
-    // ===================================================================== TMA producers (stage parity = warp)
-    long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    const int b_rows = p.n_tile / cs;   // pair: this CTA stages only its half of the weight tile
-    int L = 0;                            // running stage-load index over all tiles of this CTA
-    for (int st = cluster_id; st < total_super; st += num_clusters) {
-      const int nt = st / m_super;
-      const int mt = min((st - nt * m_super) * cs + (int)crank, p.m_tiles - 1);  // ghost CTAs redo the last tile
-      const int m0 = mt * kTileM;
-      const int img = m0 / p.OHW;
-      const int rem = m0 - img * p.OHW;
-      const int oh0 = rem / p.OW;
-      const int ow0 = rem - oh0 * p.OW;
-      const int bw = ow0 * p.stride - p.pad_w;
-      const int bh = oh0 * p.stride - p.pad_h;
-      const int n0 = nt * p.n_tile;
-      for (int ks = 0; ks < nstages_k; ++ks, ++L) {
-        if ((L & 1) != warp) continue;
-        const int stage = L % p.stages;
-        const uint32_t phase = (uint32_t)((L / p.stages) & 1);
-        const int kb0 = ks * p.bps;
-        const int nblk = min(p.bps, p.nkb - kb0);
-        long long tq0 = 0; if (p.dbg) tq0 = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
-        if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
-        const uint32_t full = ptx::smem_u32(&bars->full[stage]);
-        const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
-        const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
-        const uint32_t tx = (uint32_t)(nblk * (kTileM * kKC * 2 + b_rows * kKC * 2));
-        if (ptx::elect_one()) {
-          if constexpr (!kPair) {
-            ptx::mbar_expect_tx(full, tx);
-            for (int j = 0; j < nblk; ++j) {
-              const int kb = kb0 + j;
-              const int tap = kb / p.cpt;
-              const int c0 = (kb - tap * p.cpt) * kKC;
-              const int r = tap / p.ksize;
-              const int s = tap - r * p.ksize;
-              ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, full, c0, bw, bh, img,
-                                      (uint16_t)s, (uint16_t)r);
-              ptx::tma_load_2d(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, full, tap * p.Cin + c0, n0);
-            }
-          } else {
-            const uint32_t lfull = ptx::mapa_cluster(full, 0);   // the leader's barrier collects both CTAs' bytes
-            ptx::mbar_expect_tx_cluster(lfull, tx);
-            for (int j = 0; j < nblk; ++j) {
-              const int kb = kb0 + j;
-              const int tap = kb / p.cpt;
-              const int c0 = (kb - tap * p.cpt) * kKC;
-              const int r = tap / p.ksize;
-              const int s = tap - r * p.ksize;
-              ptx::tma_load_im2col_4d_2cta(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, lfull, c0, bw, bh, img,
-                                           (uint16_t)s, (uint16_t)r);
-              ptx::tma_load_2d_2cta(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, lfull, tap * p.Cin + c0,
-                                    n0 + (int)crank * b_rows);
-            }
-          }
-        }
-        __syncwarp();
-        if (p.dbg) dbg_issue += clock64() - tq0;
-      }
-    }
-    if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 32 + 0 + 11 * warp] = dbg_wait;
-      p.dbg[blockIdx.x * 32 + 1 + 11 * warp] = dbg_issue;
-      p.dbg[blockIdx.x * 32 + 2 + 11 * warp] = clock64() - dbg_t0;
-    }
-  } else if (warp == 2 && (!pair || crank == 0)) {
-    // ===================================================================== MMA issuer (pair mode: leader CTA only)
-    const uint32_t idesc = ptx::umma_idesc_f16(pair ? 2 * kTileM : kTileM, p.n_tile);
-    const int ctail = p.Cin - (p.cpt - 1) * kKC;          // real channels in the last k-block of a tap
-    int L = 0;
-    int it = 0;
-    long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    for (int st = cluster_id; st < total_super; st += num_clusters, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      long long tq0 = 0; if (p.dbg) tq0 = clock64();
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
-      if (p.dbg) dbg_wtm += clock64() - tq0;
-      ptx::tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-      for (int ks = 0; ks < nstages_k; ++ks, ++L) {
-        const int stage = L % p.stages;
-        const uint32_t phase = (uint32_t)((L / p.stages) & 1);
-        const int kb0 = ks * p.bps;
-        const int nblk = min(p.bps, p.nkb - kb0);
-        if (p.dbg) tq0 = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
-        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (L == 0 && lane == 0) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
-        ptx::tc_fence_after_sync();
-        const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
-        const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
-        if (ptx::elect_one()) {
-          for (int j = 0; j < nblk; ++j) {
-            const int kb = kb0 + j;
-            const int cblk = kb % p.cpt;
-            const int nk = (cblk == p.cpt - 1 ? ctail : kKC) / 16;
-            const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)(j * p.a_blk_bytes), 128u, 1024u);
-            const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), 128u, 1024u);
-            for (int k = 0; k < nk; ++k) {
-              // advancing K by 16 fp16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-              if constexpr (!kPair)
-                ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                (uint32_t)((ks | j | k) != 0));
-              else
-                ptx::mma_f16_ss_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                     (uint32_t)((ks | j | k) != 0));
-            }
-          }
-          // frees the smem slot (pair: in both CTAs) when the MMAs retire
-          if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
-          else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
-        }
-        __syncwarp();
-        if (p.dbg) dbg_mma += clock64() - tq0;
-      }
-      if (ptx::elect_one()) {   // accumulator ready (pair: for both CTAs' epilogues)
-        if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
-        else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->tmem_full[acc]), mc_mask);
-      }
-      __syncwarp();
-    }
-    if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 32 + 19] = (long long)ptx::globaltimer();
-      p.dbg[blockIdx.x * 32 + 4] = dbg_wfull; p.dbg[blockIdx.x * 32 + 5] = dbg_wtm;
-      p.dbg[blockIdx.x * 32 + 6] = dbg_mma; p.dbg[blockIdx.x * 32 + 7] = clock64() - dbg_t0;
-    }
-  } else if (warp >= 4) {
-    // ===================================================================== epilogue (two warpgroups, alternating tiles)
-    const int g = (warp - 4) >> 2;        // warpgroup == accumulator buffer it drains
-    const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;        // accumulator row == output pixel within the tile
-    long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    int it = 0;
-    for (int st = cluster_id; st < total_super; st += num_clusters, ++it) {
-      if ((it & 1) != g) continue;
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int nt = st / m_super;
-      const int mt_raw = (st - nt * m_super) * cs + (int)crank;
-      const int mt = min(mt_raw, p.m_tiles - 1);
-      const int m = mt * kTileM + row;
-      const int n0 = nt * p.n_tile;
-      const bool valid = m < p.M_total && mt_raw < p.m_tiles;
-      size_t opix = (size_t)m;
-      if (p.sub) {  // sub-pixel phase of a stride-2 transposed conv: (n, i, j) -> (n, 2i+a, 2j+b)
-        const int img = m / p.OHW;
-        const int rem = m - img * p.OHW;
-        const int i = rem / p.OW;
-        const int j = rem - i * p.OW;
-        opix = ((size_t)img * (2 * p.OH) + (size_t)(2 * i + p.sub_a)) * (size_t)(2 * p.OW) + (size_t)(2 * j + p.sub_b);
-      }
-      EpiRow e;
-      e.s_scale = s_scale; e.s_bias = s_bias; e.residual = p.residual; e.out = p.out;
-      e.row_off = opix * p.Cout + n0;
-      e.ch0 = n0; e.ncols = p.n_tile; e.relu = p.relu; e.out_f32 = p.out_f32; e.valid = valid;
-      uint4 rres[8];
-      epi_load_residual(rres, e, 0);            // in flight while the MMAs of this tile finish
-      long long tq0 = 0; if (p.dbg) tq0 = clock64();
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
-      if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
-      ptx::tc_fence_after_sync();
-      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile));
-      if (p.dbg) dbg_work += clock64() - tq0;
-      // all TMEM reads of this thread are complete (wait::ld inside): release the accumulator
-      ptx::tc_fence_before_sync();
-      if (!pair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
-      else if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[g]), 0);   // the leader's MMA warp waits for both CTAs
-    }
-    if (p.dbg && threadIdx.x == 128) {
-      p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
-      p.dbg[blockIdx.x * 32 + 10] = clock64() - dbg_t0;
-    }
-  }
-
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 20] = (long long)ptx::globaltimer();
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  if constexpr (kPair) ptx::cluster_sync_all();   // no CTA may exit while its peer can still arrive on / read from it
-  if (warp == 2) {
-    ptx::tc_fence_after_sync();
-    if constexpr (kPair) ptx::tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
-    else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-  }
+  conv_igemm_body<kPair>(tmA, tmB, p, (int)blockIdx.x, (int)gridDim.x, smem_raw);
 }
 
 cudaError_t conv_tc_set_attributes(int max_smem) {

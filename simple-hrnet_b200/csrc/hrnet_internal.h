@@ -127,6 +127,8 @@ struct Op {
   int stream = 0;
   std::vector<int> deps;       // ops that must complete before this one
   bool needs_event = false;    // some dependant runs on another stream
+  int grp = -1;                // grouped launch id: the k-th convs of all branches of a StageModule run in one kernel
+  double work = 0;             // estimated SM-cycles (CTA split of grouped launches)
   float sm_frac = 1.f;         // share of the SMs this op's persistent grid may occupy (branch-level SM partitioning)
   int group = -1;              // ops with the same group id run concurrently on different streams and split the SMs
   // tcgen05 path
@@ -139,6 +141,20 @@ struct Op {
   int patch_smem = 0;
   CUtensorMap tmPA[3], tmPB[3];
 };
+
+// host-side description of one grouped launch (conv_group.cu): up to 2 halo-patch + 2 im2col problems
+struct GroupLaunch {
+  int n_patch = 0, n_igemm = 0;
+  int patch_ctas[2] = {0, 0}, igemm_ctas[2] = {0, 0};
+  const CUtensorMap* patch_maps_a[2] = {nullptr, nullptr};   // -> Op::tmPA
+  const CUtensorMap* patch_maps_b[2] = {nullptr, nullptr};   // -> Op::tmPB
+  ConvPatchParams pp[2];
+  CUtensorMap igemm_map_a[2], igemm_map_b[2];
+  ConvTcParams ip[2];
+  int smem_bytes = 0;
+};
+cudaError_t launch_conv_group(const GroupLaunch& g, cudaStream_t st);
+cudaError_t conv_group_set_attributes(int max_smem);
 
 // launchers (implemented in the .cu files)
 cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int smem_bytes,

@@ -11,6 +11,7 @@
 // with BN folded to a per-channel fp32 (scale, bias) epilogue, ReLU / residual-add fused into the
 // producing conv, and the four HRNet branches running concurrently on forked streams.
 #include <algorithm>
+#include <array>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -275,25 +276,40 @@ int build_hrnet(HrnetPlan& P) {
   xs.push_back(b.conv("transition1.1", "transition1.1.0.0", "transition1.1.0.1", x, 2 * c, 3, 2, true, -1, -1, 2, 1));
 
   int module_idx = 0;
+  int grp_counter = 0;
   auto stage_module = [&](const std::string& prefix, int S, int O) {
     const int arena = 1 + (module_idx & 1);
     b.reset_arena(arena);
     ++module_idx;
     std::vector<int> ys(S);
-    for (int i = 0; i < S; ++i) {
-      const TensorInfo ti = P.tensors[xs[i]];
-      int t = b.new_tensor(arena, ti.C, ti.H, ti.W);
-      int y[2] = {b.new_tensor(arena, ti.C, ti.H, ti.W), b.new_tensor(arena, ti.C, ti.H, ti.W)};
-      int cur = xs[i];
-      for (int k = 0; k < 4; ++k) {
-        const std::string p = prefix + ".branches." + std::to_string(i) + "." + std::to_string(k);
-        b.conv(p + ".conv1", p + ".conv1", p + ".bn1", cur, ti.C, 3, 1, true, -1, t, arena, i);
-        P.ops.back().group = module_idx;
-        b.conv(p + ".conv2", p + ".conv2", p + ".bn2", t, ti.C, 3, 1, true, cur, y[k & 1], arena, i);
-        P.ops.back().group = module_idx;
-        cur = y[k & 1];
+    {
+      // branch convs are emitted level by level (k-th conv of every branch next to each other) so that one level can
+      // be issued as ONE grouped launch (conv_group.cu); each branch keeps its private t / y0 / y1 rotation.
+      std::vector<int> tbuf(S), cur(S);
+      std::vector<std::array<int, 2>> ybuf(S);
+      for (int i = 0; i < S; ++i) {
+        const TensorInfo ti = P.tensors[xs[i]];
+        tbuf[i] = b.new_tensor(arena, ti.C, ti.H, ti.W);
+        ybuf[i] = {b.new_tensor(arena, ti.C, ti.H, ti.W), b.new_tensor(arena, ti.C, ti.H, ti.W)};
+        cur[i] = xs[i];
       }
-      ys[i] = cur;
+      for (int k = 0; k < 4; ++k) {
+        for (int half = 0; half < 2; ++half) {
+          const int grp = grp_counter++;
+          for (int i = 0; i < S; ++i) {
+            const int C = P.tensors[xs[i]].C;
+            const std::string p = prefix + ".branches." + std::to_string(i) + "." + std::to_string(k);
+            if (half == 0)
+              b.conv(p + ".conv1", p + ".conv1", p + ".bn1", cur[i], C, 3, 1, true, -1, tbuf[i], arena, i);
+            else
+              b.conv(p + ".conv2", p + ".conv2", p + ".bn2", tbuf[i], C, 3, 1, true, cur[i], ybuf[i][k & 1], arena, i);
+            P.ops.back().group = module_idx;
+            P.ops.back().grp = grp;
+          }
+        }
+        for (int i = 0; i < S; ++i) cur[i] = ybuf[i][k & 1];
+      }
+      for (int i = 0; i < S; ++i) ys[i] = cur[i];
     }
     std::vector<int> outs(O);
     for (int i = 0; i < O; ++i) {
@@ -479,6 +495,37 @@ void finalize_schedule(HrnetPlan& P) {
       op.sm_frac = (float)(work[op.group][op.stream] / tot);
     }
   }
+  // Grouped launches (conv_group.cu): the k-th convs of all branches of a StageModule form one launch when they fit the
+  // kernel's slots (<= 2 halo-patch + <= 2 im2col problems, no CTA-pair mode).  Per-tile cost model (clk) for the CTA
+  // split, calibrated on profiles/r01_dbg_role_timers_v3_kernels_v2.log / r01_exp_mma_rate.log.
+  {
+    std::map<int, std::vector<int>> groups;
+    for (size_t i = 0; i < P.ops.size(); ++i) {
+      Op& op = P.ops[i];
+      if (op.kind != OP_CONV || !op.use_tc) { op.grp = -1; continue; }
+      const int n = op.use_patch ? op.cout : op.tc.n_tile;
+      const double k16 = (double)op.k * op.k * ((op.cin + 15) / 16);
+      const double mma = std::max(n / 2.0, 32.0 + n / 4.0);
+      op.work = op.use_patch ? k16 * mma * 1.15 + 650.0 : k16 * (mma + (128.0 + n) / 4.0) + 1500.0;
+      if (op.grp >= 0) groups[op.grp].push_back((int)i);
+    }
+    const bool enabled = !(P.desc.flags & (HRNET_FLAG_NO_GROUP | HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_SERIAL));
+    for (auto& kv : groups) {
+      int np = 0, ni = 0;
+      bool ok = enabled && kv.second.size() >= 2;
+      for (int i : kv.second) {
+        const Op& op = P.ops[i];
+        if (op.use_patch) ++np; else ++ni;
+        if (!op.use_patch && op.tc.cs != 1) ok = false;
+      }
+      for (size_t k = 1; k < kv.second.size(); ++k) if (kv.second[k] != kv.second[k - 1] + 1) ok = false;
+      if (np > 2 || ni > 2) ok = false;
+      for (int i : kv.second) {
+        if (!ok) P.ops[i].grp = -1;
+        else P.ops[i].stream = 0;      // the whole level is one kernel on the caller's stream
+      }
+    }
+  }
   // every stream's last op must be joined back into stream 0 before the head runs
   int head = -1;
   for (size_t i = 0; i < P.ops.size(); ++i) if (P.ops[i].kind == OP_HEAD) head = (int)i;
@@ -490,7 +537,9 @@ void finalize_schedule(HrnetPlan& P) {
   for (auto& op : P.ops)
     for (int dpi : op.deps)
       if (P.ops[dpi].stream != op.stream) P.ops[dpi].needs_event = true;
-  P.launch_count = (int)P.ops.size();
+  P.launch_count = 0;
+  for (size_t i = 0; i < P.ops.size(); ++i)
+    if (P.ops[i].grp < 0 || i == 0 || P.ops[i - 1].grp != P.ops[i].grp) ++P.launch_count;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -694,7 +743,7 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     o << "{\"kind\":" << op.kind << ",\"name\":\"" << op.name << "\",\"in\":" << op.in << ",\"out\":" << op.out
       << ",\"res\":" << op.res << ",\"param\":" << op.param << ",\"cin\":" << op.cin << ",\"cout\":" << op.cout
       << ",\"k\":" << op.k << ",\"stride\":" << op.stride << ",\"pad\":" << op.pad << ",\"relu\":" << op.relu
-      << ",\"stream\":" << op.stream << ",\"sm_frac\":" << op.sm_frac << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
+      << ",\"stream\":" << op.stream << ",\"grp\":" << op.grp << ",\"sm_frac\":" << op.sm_frac << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
       << op.src[0] << "," << op.src[1] << "," << op.src[2] << "," << op.src[3] << "],\"shift\":[" << op.shift[0] << ","
       << op.shift[1] << "," << op.shift[2] << "," << op.shift[3] << "],\"deps\":[";
     for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
@@ -748,6 +797,10 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
       max_patch_smem = std::max(max_patch_smem, op.patch_smem);
     }
   }
+  {
+    cudaError_t e = conv_group_set_attributes(kMaxDynSmem);
+    if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute(group): ") + cudaGetErrorString(e));
+  }
   if (max_patch_smem) {
     cudaError_t e = conv_patch_set_attributes(kMaxDynSmem);
     if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute(patch): ") + cudaGetErrorString(e));
@@ -779,6 +832,89 @@ namespace {
     cudaError_t e__ = (call);                                                                      \
     if (e__ != cudaSuccess) return fail(HRNET_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
   } while (0)
+
+ConvPatchParams fill_patch_params(HrnetPlan* P, const Op& op, int n) {
+  const TensorInfo& to = P->tensors[op.out];
+  const ParamInfo& pi = P->params[op.param];
+  ConvPatchParams p = op.pp;
+  p.N = n; p.total_tiles = n * p.tiles_w * p.tiles_h;
+  p.out_f32 = to.dtype == DT_F32;
+  p.scale = (const float*)(P->wbase + pi.scale_offset);
+  p.bias = (const float*)(P->wbase + pi.bias_offset);
+  p.residual = op.res >= 0 ? (const __half*)(P->abase + P->tensors[op.res].offset) : nullptr;
+  p.out = P->abase + to.offset;
+  return p;
+}
+
+ConvTcParams fill_tc_params(HrnetPlan* P, const Op& op, int n) {
+  const TensorInfo& ti = P->tensors[op.in];
+  const TensorInfo& to = P->tensors[op.out];
+  const ParamInfo& pi = P->params[op.param];
+  int plh, phh, plw, phw, sub, sa, sb;
+  conv_geometry(op, plh, phh, plw, phw, sub, sa, sb);
+  const int OH = sub ? ti.H : ti.H / op.stride, OW = sub ? ti.W : ti.W / op.stride;
+  ConvTcParams p{};
+  p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
+  p.ksize = op.k; p.stride = op.stride; p.pad_h = plh; p.pad_w = plw;
+  p.sub = sub; p.sub_a = sa; p.sub_b = sb;
+  p.Cin = op.cin; p.Cout = op.cout;
+  p.kc = op.tc.kc; p.cpt = (op.cin + op.tc.kc - 1) / op.tc.kc; p.nkb = op.k * op.k * p.cpt; p.bps = op.tc.bps;
+  p.n_tile = op.tc.n_tile; p.n_tiles = op.cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
+  p.cs = op.tc.cs;
+  p.stages = op.tc.stages; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
+  p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
+  p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
+  p.scale = (const float*)(P->wbase + pi.scale_offset);
+  p.bias = (const float*)(P->wbase + pi.bias_offset);
+  p.residual = op.res >= 0 ? (const __half*)(P->abase + P->tensors[op.res].offset) : nullptr;
+  p.out = P->abase + to.offset;
+  return p;
+}
+
+// ops [first, last) form one grouped launch; returns the per-member estimated cost (for time attribution)
+int launch_group(HrnetPlan* P, int first, int last, int n, cudaStream_t st, std::vector<double>* cost_out) {
+  GroupLaunch g;
+  std::vector<double> units, ucost;
+  std::vector<int*> slot;
+  for (int i = first; i < last; ++i) {
+    const Op& op = P->ops[i];
+    if (op.use_patch) {
+      const int k = g.n_patch++;
+      g.pp[k] = fill_patch_params(P, op, n);
+      g.patch_maps_a[k] = op.tmPA; g.patch_maps_b[k] = op.tmPB;
+      units.push_back((double)g.pp[k].total_tiles); slot.push_back(&g.patch_ctas[k]);
+      g.smem_bytes = std::max(g.smem_bytes, op.patch_smem);
+    } else {
+      const int k = g.n_igemm++;
+      g.ip[k] = fill_tc_params(P, op, n);
+      g.igemm_map_a[k] = op.tmA; g.igemm_map_b[k] = op.tmB;
+      units.push_back((double)g.ip[k].m_tiles * g.ip[k].n_tiles); slot.push_back(&g.igemm_ctas[k]);
+      g.smem_bytes = std::max(g.smem_bytes, op.tc.smem_bytes);
+    }
+    ucost.push_back(op.work);
+  }
+  // CTA split: greedily hand each SM to the problem that currently finishes last (whole tile rounds)
+  const int np = (int)units.size();
+  std::vector<int> c(np, 1);
+  auto t = [&](int k) { return std::ceil(units[k] / c[k]) * ucost[k]; };
+  for (int k = 0; k < np; ++k) c[k] = 1;
+  int left = P->num_sms - np;
+  while (left > 0) {
+    int worst = 0;
+    for (int k = 1; k < np; ++k) if (t(k) > t(worst)) worst = k;
+    if (c[worst] >= (int)units[worst]) {            // cannot use more CTAs than tiles: give it to the next worst that can
+      int alt = -1;
+      for (int k = 0; k < np; ++k) if (c[k] < (int)units[k] && (alt < 0 || t(k) > t(alt))) alt = k;
+      if (alt < 0) break;
+      worst = alt;
+    }
+    ++c[worst]; --left;
+  }
+  for (int k = 0; k < np; ++k) *slot[k] = c[k];
+  if (cost_out) { cost_out->clear(); for (int k = 0; k < np; ++k) cost_out->push_back(units[k] * ucost[k]); }
+  CK(launch_conv_group(g, st));
+  return 0;
+}
 
 int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_ext, float* joints, int32_t* idx,
               const float* boxes, cudaStream_t st) {
@@ -891,6 +1027,19 @@ int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, flo
   for (int i = first; i < last; ++i) {
     const Op& op = P->ops[i];
     cudaStream_t st = stream_of(op.stream);
+    if (op.grp >= 0) {
+      int j = i;
+      while (j < last && P->ops[j].grp == op.grp) ++j;
+      for (int m = i; m < j; ++m)
+        for (int dpi : P->ops[m].deps)
+          if (P->ops[dpi].stream != P->ops[m].stream) CK(cudaStreamWaitEvent(st, P->events[dpi], 0));
+      int rc = launch_group(P, i, j, n, st, nullptr);
+      if (rc) return rc;
+      for (int m = i; m < j; ++m)
+        if (P->ops[m].needs_event) CK(cudaEventRecord(P->events[m], st));
+      i = j - 1;
+      continue;
+    }
     for (int dpi : op.deps)
       if (P->ops[dpi].stream != op.stream) CK(cudaStreamWaitEvent(st, P->events[dpi], 0));
     int rc = launch_op(P, op, n, in_ext, hm_ext, joints, idx, boxes, st);
@@ -1009,14 +1158,37 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
   std::vector<std::vector<float>> t(nops, std::vector<float>(iters));
   for (int it = -1; it < iters; ++it) {   // iteration -1 = warm-up
     CK(cudaEventRecord(ev[0], s0));
+    std::vector<std::pair<int, int>> spans;          // grouped launches: [first, last)
+    std::vector<std::vector<double>> span_cost;
     for (int i = 0; i < nops; ++i) {
-      int rc = launch_op(P, P->ops[i], n, in, nullptr, joints, idx, nullptr, s0);
+      const Op& op = P->ops[i];
+      if (op.grp >= 0) {
+        int j = i;
+        while (j < nops && P->ops[j].grp == op.grp) ++j;
+        std::vector<double> cost;
+        int rc = launch_group(P, i, j, n, s0, &cost);
+        if (rc) return rc;
+        for (int m = i; m < j; ++m) CK(cudaEventRecord(ev[m + 1], s0));
+        spans.push_back({i, j}); span_cost.push_back(cost);
+        i = j - 1;
+        continue;
+      }
+      int rc = launch_op(P, op, n, in, nullptr, joints, idx, nullptr, s0);
       if (rc) return rc;
       CK(cudaEventRecord(ev[i + 1], s0));
     }
     CK(cudaStreamSynchronize(s0));
-    if (it >= 0)
+    if (it >= 0) {
       for (int i = 0; i < nops; ++i) { CK(cudaEventElapsedTime(&t[i][it], ev[i], ev[i + 1])); }
+      for (size_t gi = 0; gi < spans.size(); ++gi) {   // one kernel for the whole span: split its time by estimated cost
+        float total = 0.f;
+        CK(cudaEventElapsedTime(&total, ev[spans[gi].first], ev[spans[gi].second]));
+        double csum = 0;
+        for (double c : span_cost[gi]) csum += c;
+        for (int m = spans[gi].first; m < spans[gi].second; ++m)
+          t[m][it] = (float)(total * span_cost[gi][m - spans[gi].first] / csum);
+      }
+    }
   }
   for (int i = 0; i < nops; ++i) {
     std::sort(t[i].begin(), t[i].end());
