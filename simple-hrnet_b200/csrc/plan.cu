@@ -506,7 +506,8 @@ void finalize_schedule(HrnetPlan& P) {
       const int n = op.use_patch ? op.cout : op.tc.n_tile;
       const double k16 = (double)op.k * op.k * ((op.cin + 15) / 16);
       const double mma = std::max(n / 2.0, 32.0 + n / 4.0);
-      op.work = op.use_patch ? k16 * mma * 1.15 + 650.0 : k16 * (mma + (128.0 + n) / 4.0) + 1500.0;
+      // wall clk per tile incl. barrier waits, measured inside a grouped launch (profiles/r01_dbg_group_split_v1.log)
+      op.work = op.use_patch ? k16 * mma * 1.45 + 650.0 : k16 * (mma + (128.0 + n) / 4.0) * 1.5 + 1500.0;
       if (op.grp >= 0) groups[op.grp].push_back((int)i);
     }
     const bool enabled = !(P.desc.flags & (HRNET_FLAG_NO_GROUP | HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_SERIAL));
@@ -912,6 +913,37 @@ int launch_group(HrnetPlan* P, int first, int last, int n, cudaStream_t st, std:
   }
   for (int k = 0; k < np; ++k) *slot[k] = c[k];
   if (cost_out) { cost_out->clear(); for (int k = 0; k < np; ++k) cost_out->push_back(units[k] * ucost[k]); }
+  if (getenv("HRNET_B200_DBG_GROUP")) {   // debug: per-problem finish times of one grouped launch
+    long long* dev = nullptr;
+    const int grid = P->num_sms;
+    if (cudaMalloc(&dev, (size_t)grid * 32 * sizeof(long long)) == cudaSuccess) {
+      cudaMemset(dev, 0, (size_t)grid * 32 * sizeof(long long));
+      for (int k = 0; k < g.n_patch; ++k) g.pp[k].dbg = dev;
+      for (int k = 0; k < g.n_igemm; ++k) g.ip[k].dbg = dev;
+      CK(launch_conv_group(g, st));
+      cudaStreamSynchronize(st);
+      std::vector<long long> h((size_t)grid * 32);
+      cudaMemcpy(h.data(), dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaFree(dev);
+      long long t0 = LLONG_MAX;
+      for (int b = 0; b < grid; ++b) if (h[(size_t)b * 32 + 16]) t0 = std::min(t0, h[(size_t)b * 32 + 16]);
+      int begin = 0;
+      fprintf(stderr, "[dbg-group] first=%s n=%d:", P->ops[first].name.c_str(), n);
+      for (int k = 0; k < np; ++k) {
+        long long done = 0, ops0 = 0; double mma = 0;
+        for (int b = begin; b < begin + c[k]; ++b) {
+          done = std::max(done, h[(size_t)b * 32 + 20] - t0);
+          ops0 = std::max(ops0, h[(size_t)b * 32 + 18] - t0);
+          mma += (double)h[(size_t)b * 32 + 6] / c[k];
+        }
+        fprintf(stderr, " [%s ctas=%d units=%.0f ucost=%.0f est=%.0f clk | first_operands=%lld ns roles_done=%lld ns mma_issue=%.0f clk]",
+                P->ops[first + k].use_patch ? "patch" : "igemm", c[k], units[k], ucost[k], std::ceil(units[k] / c[k]) * ucost[k], ops0, done, mma);
+        begin += c[k];
+      }
+      fprintf(stderr, "\n");
+      return 0;
+    }
+  }
   CK(launch_conv_group(g, st));
   return 0;
 }
