@@ -44,7 +44,7 @@ extern "C" {
 #define HRNET_FLAG_FUSE_F32 4u     /* store exchange-unit partial terms in fp32 (default fp16: same accuracy, faster) */
 #define HRNET_FLAG_SERIAL 8u       /* debug: run all branches on the caller's stream                */
 #define HRNET_FLAG_NO_PATCH 16u    /* debug: disable the halo-patch 3x3 kernel (im2col kernel everywhere) */
-#define HRNET_FLAG_NO_GROUP 64u    /* debug: launch every branch conv on its own (no grouped multi-problem kernel) */
+#define HRNET_FLAG_GROUP 64u       /* experiment: issue the k-th convs of all branches as one multi-problem kernel (same speed) */
 #define HRNET_FLAG_PARTITION 32u   /* experiment: split the SMs between the concurrent branch chains (slower) */
 
 typedef struct HrnetPlan HrnetPlan;

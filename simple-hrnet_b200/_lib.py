@@ -27,7 +27,7 @@ class HrnetParamInfo(ctypes.Structure):
 
 
 ARCH_HRNET, ARCH_POSERESNET = 0, 1
-FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F32, FLAG_SERIAL, FLAG_NO_PATCH, FLAG_PARTITION, FLAG_NO_GROUP = 1, 2, 4, 8, 16, 32, 64
+FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F32, FLAG_SERIAL, FLAG_NO_PATCH, FLAG_PARTITION, FLAG_GROUP = 1, 2, 4, 8, 16, 32, 64
 
 # every symbol include/hrnet_b200.h declares: (name, restype, argtypes)
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t

@@ -12,7 +12,8 @@
 //     (SBO = 10 * row bytes).  tcgen05 applies the swizzle to absolute shared-memory address bits, so a
 //     descriptor that starts on a 128 B (not 1024 B) boundary reads exactly what TMA wrote
 //     (profiles/r01_exp_shifted_umma_descriptor.log).
-//   * the weights of all 9 taps stay resident in shared memory for the whole persistent CTA.
+//   * the weights of all 9 taps stay resident in shared memory for the whole persistent CTA; when they do not fit
+//     (e.g. transition1.0, 256 -> 48: 221 KB) the 9-tap block of a channel chunk is streamed with that chunk's patch.
 //
 // L2->SM traffic per tile drops from 9 x (128 x Cin) + 9 x Cin x Cout to 180 x Cin elements.
 //
@@ -110,7 +111,7 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
   if (warp < 2) {
     // ===================================================================== TMA producers (slot parity = warp)
     long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    if (warp == 0) {
+    if (warp == 0 && !p.b_stream) {
       // resident weights: 9 taps x nchunks blocks of [Cout rows x bkc channels]
       uint32_t btx = 0;
       for (int j = 0; j < p.nchunks; ++j) btx += 9u * (uint32_t)(p.Cout * p.bkc[j] * 2);
@@ -140,9 +141,16 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
         if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
         const uint32_t full = ptx::smem_u32(&bars->a_full[slot]);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 128));
-          ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a, full, p.c0[j], tw * kPatchTW - 1,
-                           th * kPatchTH - 1, img);
+          const uint32_t slot_addr = a_base + (uint32_t)(slot * p.slot_bytes);
+          if (!p.b_stream) {
+            ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 128));
+          } else {   // the chunk's 9-tap weight block rides in the same slot
+            ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 128 + 9 * p.Cout * p.bkc[j] * 2));
+            for (int t = 0; t < 9; ++t)
+              ptx::tma_load_2d(slot_addr + (uint32_t)(p.a_slot_bytes + t * p.bblk[j]), &maps.b[p.mapi[j]], full,
+                               t * p.Cin + p.c0[j], 0);
+          }
+          ptx::tma_load_4d(slot_addr, &maps.a, full, p.c0[j], tw * kPatchTW - 1, th * kPatchTH - 1, img);
         }
         __syncwarp();
         if (p.dbg) dbg_issue += clock64() - tq0;
@@ -156,7 +164,7 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
   } else if (warp == 2) {
     // ===================================================================== MMA issuer
     const uint32_t idesc = ptx::umma_idesc_f16(128, p.Cout);
-    ptx::mbar_wait(ptx::smem_u32(&bars->b_full), 0);
+    if (!p.b_stream) ptx::mbar_wait(ptx::smem_u32(&bars->b_full), 0);
     int L = 0;
     int it = 0;
     long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
@@ -181,7 +189,8 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
         if (ptx::elect_one()) {
           // 9 taps x NK K16-steps, fully unrolled: every descriptor is base + compile-time offset
           const uint64_t a0 = ptx::umma_desc_kmajor(a_slot, 128u, (uint32_t)kPatchPW * 128u);
-          const uint64_t b0 = ptx::umma_desc_kmajor(b_base + (uint32_t)p.boff[j], brow, 8u * brow);
+          const uint64_t b0 = ptx::umma_desc_kmajor(p.b_stream ? a_slot + (uint32_t)p.a_slot_bytes : b_base + (uint32_t)p.boff[j],
+                                                    brow, 8u * brow);
           const uint32_t bstep = (uint32_t)p.bblk[j] >> 4;
           const uint32_t first = (uint32_t)(j != 0);
           switch (nk) {

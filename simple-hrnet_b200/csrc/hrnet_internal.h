@@ -83,7 +83,9 @@ struct ConvPatchParams {
   int c0[4], kreal[4];         // first channel, real channels in the chunk (multiple of 16)
   int bkc[4], mapi[4];         // weight block width (64 / 32 / 16) and its tensor-map index (0 / 1 / 2)
   int boff[4], bblk[4];        // resident-weight block offset / per-tap block size in shared memory
-  int b_bytes;                 // shared memory reserved for the resident weights
+  int b_bytes;                 // shared memory reserved for the resident weights (0 when streamed)
+  int b_stream;                // 1: the 9-tap weight block of a chunk travels with its patch slot (weights too big to stay)
+  int a_slot_bytes;            // bytes of the patch part of a slot (weights of a streamed chunk follow it)
   int slot_bytes, nslots;      // ring of patch slots (one channel chunk of one tile each)
   int relu, out_f32, tmem_cols;
   const float* scale;

@@ -218,11 +218,22 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
     c += 64; ++n;
   }
   p.nchunks = n;
-  p.b_bytes = (int)boff;
-  p.slot_bytes = (int)align_up((size_t)kPatchRows * 128, 1024);
+  p.a_slot_bytes = (int)align_up((size_t)kPatchRows * 128, 1024);
   const int fixed = 1024 + 2 * op.cout * 4 + 512;
-  const int avail = kMaxDynSmem - fixed - p.b_bytes;
-  if (avail < 2 * p.slot_bytes) return false;
+  p.b_stream = 0;
+  p.b_bytes = (int)boff;
+  p.slot_bytes = p.a_slot_bytes;
+  int avail = kMaxDynSmem - fixed - p.b_bytes;
+  if (avail < 2 * p.slot_bytes) {
+    // weights too big to stay resident: stream each chunk's 9-tap block with its patch
+    int maxblk = 0;
+    for (int j = 0; j < n; ++j) maxblk = std::max(maxblk, p.bblk[j]);
+    p.b_stream = 1;
+    p.b_bytes = 0;
+    p.slot_bytes = p.a_slot_bytes + 9 * maxblk;
+    avail = kMaxDynSmem - fixed;
+    if (avail < 2 * p.slot_bytes) return false;
+  }
   p.nslots = std::min(8, avail / p.slot_bytes) & ~1;   // two producer warps alternate slots
   int cols = 32;
   while (cols < 2 * op.cout) cols *= 2;
@@ -510,7 +521,9 @@ void finalize_schedule(HrnetPlan& P) {
       op.work = op.use_patch ? k16 * mma * 1.45 + 650.0 : k16 * (mma + (128.0 + n) / 4.0) * 1.5 + 1500.0;
       if (op.grp >= 0) groups[op.grp].push_back((int)i);
     }
-    const bool enabled = !(P.desc.flags & (HRNET_FLAG_NO_GROUP | HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_SERIAL));
+    // opt-in (HRNET_FLAG_GROUP): measured equal to per-branch launches on four streams, whose kernels the hardware
+    // already co-schedules (9.42 vs 9.35 ms per W48/64 forward, profiles/r01_exp_variants_group.log)
+    const bool enabled = (P.desc.flags & HRNET_FLAG_GROUP) && !(P.desc.flags & (HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_SERIAL));
     for (auto& kv : groups) {
       int np = 0, ni = 0;
       bool ok = enabled && kv.second.size() >= 2;

@@ -76,7 +76,7 @@ def test_forward_variants_agree():
     assert np.array_equal(base, again)
     nopatch = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_NO_PATCH)(x).cpu().numpy()
     assert np.abs(nopatch - base).max() < 1.5e-3 and np.abs(nopatch - ref).max() < 1e-3
-    for flags in (_lib.FLAG_NO_GRAPH, _lib.FLAG_SERIAL, _lib.FLAG_NO_GRAPH | _lib.FLAG_SERIAL, _lib.FLAG_NO_GROUP):
+    for flags in (_lib.FLAG_NO_GRAPH, _lib.FLAG_SERIAL, _lib.FLAG_NO_GRAPH | _lib.FLAG_SERIAL, _lib.FLAG_GROUP):
         assert np.array_equal(_engine("hrnet", 32, (128, 96), 4, sd, flags)(x).cpu().numpy(), base), flags
     simt = _engine("hrnet", 32, (128, 96), 4, sd, _lib.FLAG_FORCE_SIMT | _lib.FLAG_NO_GRAPH)(x).cpu().numpy()
     # different accumulation order flips fp16 roundings; through ~60 layers the two fp16 pipelines drift apart by
@@ -88,7 +88,7 @@ def test_forward_variants_agree():
 
 def test_profile_ops_reports_every_launch():
     sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=4, bn="default")
-    e = _engine("hrnet", 32, (128, 96), 2, sd)
+    e = _engine("hrnet", 32, (128, 96), 2, sd, _lib.FLAG_GROUP)
     x = torch.randn(2, 3, 128, 96, generator=torch.Generator().manual_seed(1)).cuda()
     ops, desc = e.profile_ops(x, iters=2)
     assert len(ops) == len(desc["ops"]) == 317

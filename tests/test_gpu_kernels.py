@@ -51,6 +51,8 @@ PATCH_SHAPES = [
     (2, 64, 48, 32, 32, 3, 1),      # W32 branch 0
     (3, 32, 24, 64, 64, 3, 1),      # W32 branch 1
     (2, 64, 48, 256, 32, 3, 1),     # W32 transition1.0 (4 chunks of 64)
+    (2, 96, 72, 256, 48, 3, 1),     # W48 transition1.0: weights (221 KB) streamed with the patch slots
+    (2, 32, 16, 192, 64, 3, 1),     # streamed weights, 3 chunks
     (1, 16, 8, 16, 16, 3, 1),       # exactly one tile
     (5, 48, 24, 48, 96, 3, 1),      # Cin != Cout, 3x3 tiles per image
 ]

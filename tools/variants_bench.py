@@ -8,7 +8,7 @@ from simple_hrnet_b200 import B200Engine, _lib
 
 sd = O.make_state_dict(O.hrnet_param_spec(48, 17), seed=0, bn="default")
 x = torch.randn(64, 3, 384, 288, generator=torch.Generator().manual_seed(1)).cuda()
-names = {0: "default", 32: "PARTITION", 2: "NO_GRAPH", 34: "NO_GRAPH|PARTITION", 8: "SERIAL", 16: "NO_PATCH", 4: "FUSE_F32", 64: "NO_GROUP", 66: "NO_GROUP|NO_GRAPH"}
+names = {0: "default", 32: "PARTITION", 2: "NO_GRAPH", 34: "NO_GRAPH|PARTITION", 8: "SERIAL", 16: "NO_PATCH", 4: "FUSE_F32", 64: "GROUP", 66: "GROUP|NO_GRAPH"}
 flags_list = [int(a) for a in sys.argv[1:]] or [0, 32, 2, 34, 8]
 for flags in flags_list:
     eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), flags=flags)
