@@ -106,6 +106,12 @@ __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 
+// ---------------------------------------------------------------- L2 prefetch
+// asynchronously pull `bytes` (multiple of 16) of global memory into L2 (no destination, no completion tracking)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA loads
 // 2D tiled: coordinates (c0 = innermost, c1)
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
