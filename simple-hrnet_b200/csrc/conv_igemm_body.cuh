@@ -135,20 +135,6 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       const int bw = ow0 * p.stride - p.pad_w;
       const int bh = oh0 * p.stride - p.pad_h;
       const int n0 = nt * p.n_tile;
-      // The epilogue adds residual rows [m0, m0+128) x Cout: 128*Cout*2 contiguous bytes when one N-tile covers Cout.
-      // For the 256-channel layer1 tensors they come from HBM (226 MB at N=64), and the epilogue threads cannot keep
-      // enough loads in flight to hide that latency (136 us per conv3, 57 % of the HBM roofline): producer 0 pulls the
-      // NEXT tile's residual into L2 while this tile is being computed.
-      if (warp == 0 && p.residual != nullptr && p.n_tiles == 1 && !p.sub) {
-        const int st_next = st + num_clusters;
-        if (st_next < total_super && ptx::elect_one()) {
-          const int mtn = min((st_next % m_super) * cs + (int)crank, p.m_tiles - 1);
-          const long rows = min(128L, (long)p.M_total - (long)mtn * kTileM);
-          if (rows > 0)
-            ptx::l2_prefetch_bulk(p.residual + (size_t)mtn * kTileM * p.Cout, (uint32_t)(rows * p.Cout * 2));
-        }
-        __syncwarp();
-      }
       for (int ks = 0; ks < nstages_k; ++ks, ++L) {
         if ((L & 1) != warp) continue;
         const int stage = L % p.stages;
