@@ -38,6 +38,7 @@ struct __align__(8) PatchBars {
   uint64_t a_empty[kPMaxSlots];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[2];     // TMA-loaded residual tile of each epilogue warpgroup (staged epilogue)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -45,6 +46,7 @@ struct __align__(8) PatchBars {
 struct PatchMaps {
   CUtensorMap a;      // activations, box {64, 10, 18, 1}, SWIZZLE_128B
   CUtensorMap b[3];   // weights, box {64 | 32 | 16, Cout}
+  CUtensorMap o, r;   // staged epilogue: output / residual, box {64, 8, 16, 1}, SWIZZLE_128B
 };
 
 // All MMAs of one channel chunk: tap (r, s) = the same patch viewed from pixel row r * 10 + s (8-row core groups are one
@@ -65,6 +67,9 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t a0, uint64_
 
 // Body of one CTA working on problem `p` as CTA `cta` of `nctas` (its own persistent tile loop); shared by the
 // single-problem kernel and the grouped multi-problem kernel (conv_group.cu).
+// kEpiTma selects the staged TMA-store epilogue at compile time (p.epi_tma must agree): keeping both epilogues in one
+// kernel cost the direct path registers (spills) and ~15 % of its speed.
+template <bool kEpiTma>
 __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const ConvPatchParams& p, const int cta,
                                                    const int nctas, uint8_t* smem_raw) {
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -76,13 +81,16 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
 
   const uint32_t b_base = smem_base;                              // resident weights
   const uint32_t a_base = smem_base + (uint32_t)p.b_bytes;        // patch slots
-  float* s_scale = reinterpret_cast<float*>(smem_aligned + (size_t)p.b_bytes + (size_t)p.nslots * p.slot_bytes);
+  const uint32_t epi_base = a_base + (uint32_t)(p.nslots * p.slot_bytes);   // staged-epilogue tiles (1024 B aligned)
+  float* s_scale = reinterpret_cast<float*>(smem_aligned + (size_t)p.b_bytes + (size_t)p.nslots * p.slot_bytes +
+                                            (size_t)p.epi_bytes);
   float* s_bias = s_scale + p.Cout;
   PatchBars* bars = reinterpret_cast<PatchBars*>(s_bias + p.Cout);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&maps.a);
     for (int i = 0; i < 3; ++i) ptx::prefetch_tmap(&maps.b[i]);
+    if constexpr (kEpiTma) { ptx::prefetch_tmap(&maps.o); ptx::prefetch_tmap(&maps.r); }
     ptx::mbar_init(ptx::smem_u32(&bars->b_full), 1);
     for (int i = 0; i < p.nslots; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 1);
@@ -91,6 +99,7 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128);
+      ptx::mbar_init(ptx::smem_u32(&bars->res_full[i]), 1);
     }
     ptx::fence_mbar_init();
   }
@@ -220,6 +229,8 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
     const int dh = row >> 3, dw = row & 7;
     ptx::pdl_wait();                      // residual reads / output writes need the previous kernel
     long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
+    const bool leader = (q == 0) && (lane == 0);
+    uint32_t res_phase = 0;
     int it = 0;
     for (int tile = cta; tile < p.total_tiles; tile += nctas, ++it) {
       if ((it & 1) != g) continue;
@@ -228,6 +239,25 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
       const int rem = tile - img * tiles_per_img;
       const int th = rem / p.tiles_w;
       const int tw = rem - th * p.tiles_w;
+      if constexpr (kEpiTma) {
+        EpiTma e;
+        e.tm_out = &maps.o; e.tm_res = &maps.r; e.dims4 = 1; e.c_row0 = 0;
+        e.c_w0 = tw * kPatchTW; e.c_h0 = th * kPatchTH; e.c_img = img;
+        e.ch0 = 0; e.ncols = p.Cout; e.has_res = p.residual != nullptr; e.relu = p.relu; e.store = true;
+        e.s_scale = s_scale; e.s_bias = s_bias;
+        e.stage_out = epi_base + (uint32_t)g * (uint32_t)(p.epi_bytes >> 1);
+        e.stage_res = e.stage_out + 16384u;
+        e.res_bar = ptx::smem_u32(&bars->res_full[g]); e.bar_id = 1 + g;
+        if (e.has_res && leader) epi_tma_issue_residual(e, 0);   // in flight while the MMAs of this tile finish
+        long long tq0 = 0; if (p.dbg) tq0 = clock64();
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
+        if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
+        ptx::tc_fence_after_sync();
+        epi_tma_tile(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.Cout), row, leader, res_phase);
+        if (p.dbg) dbg_work += clock64() - tq0;
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
+      } else {
       const int oh = th * kPatchTH + dh, ow = tw * kPatchTW + dw;
       const bool valid = oh < p.H && ow < p.W;
       EpiRow e;
@@ -244,7 +274,9 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
       if (p.dbg) dbg_work += clock64() - tq0;
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
+      }
     }
+    if (kEpiTma && leader) ptx::tma_store_wait_all();   // shared memory must outlive the bulk stores
     if (p.dbg && threadIdx.x == 128) {
       p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
       p.dbg[blockIdx.x * 32 + 10] = clock64() - dbg_t0;

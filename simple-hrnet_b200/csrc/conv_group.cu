@@ -27,13 +27,13 @@ __global__ void __launch_bounds__(384, 1) conv_group_kernel(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const int b = (int)blockIdx.x;
   if (b < a.cta_end[0]) {
-    conv3x3_patch_body(a.pm[0], a.pp[0], b, a.cta_end[0], smem_raw);
+    conv3x3_patch_body<false>(a.pm[0], a.pp[0], b, a.cta_end[0], smem_raw);
   } else if (b < a.cta_end[1]) {
-    conv3x3_patch_body(a.pm[1], a.pp[1], b - a.cta_end[0], a.cta_end[1] - a.cta_end[0], smem_raw);
+    conv3x3_patch_body<false>(a.pm[1], a.pp[1], b - a.cta_end[0], a.cta_end[1] - a.cta_end[0], smem_raw);
   } else if (b < a.cta_end[2]) {
-    conv_igemm_body<false>(a.ia[0], a.ib[0], a.ip[0], b - a.cta_end[1], a.cta_end[2] - a.cta_end[1], smem_raw);
+    conv_igemm_body<false, false>(a.ia[0], a.ib[0], nullptr, nullptr, a.ip[0], b - a.cta_end[1], a.cta_end[2] - a.cta_end[1], smem_raw);
   } else {
-    conv_igemm_body<false>(a.ia[1], a.ib[1], a.ip[1], b - a.cta_end[2], a.cta_end[3] - a.cta_end[2], smem_raw);
+    conv_igemm_body<false, false>(a.ia[1], a.ib[1], nullptr, nullptr, a.ip[1], b - a.cta_end[2], a.cta_end[3] - a.cta_end[2], smem_raw);
   }
 }
 
@@ -48,6 +48,7 @@ cudaError_t launch_conv_group(const GroupLaunch& g, cudaStream_t st) {
     if (i < g.n_patch) {
       a.pm[i].a = g.patch_maps_a[i][0];
       for (int k = 0; k < 3; ++k) a.pm[i].b[k] = g.patch_maps_b[i][k];
+      a.pm[i].o = a.pm[i].r = a.pm[i].a;   // grouped launches use the direct-store epilogue
       a.pp[i] = g.pp[i];
       end += g.patch_ctas[i];
     } else {

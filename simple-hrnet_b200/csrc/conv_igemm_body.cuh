@@ -48,6 +48,7 @@ struct __align__(8) PipeBars {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[2];     // TMA-loaded residual tile of each epilogue warpgroup (staged epilogue)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -56,9 +57,11 @@ struct __align__(8) PipeBars {
 // launched as a cluster of CTA pairs ("cluster misconfiguration" otherwise).
 // Body of one CTA working on problem `p` as CTA `cta` of `nctas`; shared by the single-problem kernels and the grouped
 // multi-problem kernel (conv_group.cu, kPair = false only).
-template <bool kPair>
-__device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p,
-                                                const int cta, const int nctas, uint8_t* smem_raw) {
+// kEpiTma selects the staged TMA-store epilogue at compile time (p.epi_tma must agree).
+template <bool kPair, bool kEpiTma>
+__device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO,
+                                                const CUtensorMap* tmR, const ConvTcParams& p, const int cta,
+                                                const int nctas, uint8_t* smem_raw) {
   // stage buffers need swizzle-atom (1024 B) alignment
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -71,8 +74,9 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
   const int a_stage_bytes = p.bps * p.a_blk_bytes;
   const int b_stage_bytes = p.bps * p.b_blk_bytes;
   const int stage_bytes = a_stage_bytes + b_stage_bytes;
-  // layout: [stages x (A blocks | B blocks)] [scale Cout f32] [bias Cout f32] [barriers]
-  float* s_scale = reinterpret_cast<float*>(smem_aligned + (size_t)p.stages * stage_bytes);
+  // layout: [stages x (A blocks | B blocks)] [epilogue staging tiles] [scale Cout f32] [bias Cout f32] [barriers]
+  const uint32_t epi_base = smem_base + (uint32_t)(p.stages * stage_bytes);
+  float* s_scale = reinterpret_cast<float*>(smem_aligned + (size_t)p.stages * stage_bytes + (size_t)p.epi_bytes);
   float* s_bias = s_scale + p.Cout;
   PipeBars* bars = reinterpret_cast<PipeBars*>(s_bias + p.Cout);
 
@@ -98,6 +102,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128u * (uint32_t)cs);   // pair: both CTAs' epilogues
+      ptx::mbar_init(ptx::smem_u32(&bars->res_full[i]), 1);
     }
     ptx::fence_mbar_init();
   }
@@ -253,6 +258,9 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;        // accumulator row == output pixel within the tile
     long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
+    const bool leader = (q == 0) && (lane == 0);
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile);
+    uint32_t res_phase = 0;
     int it = 0;
     for (int st = cluster_id; st < total_super; st += num_clusters, ++it) {
       if ((it & 1) != g) continue;
@@ -262,6 +270,26 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       const int mt = min(mt_raw, p.m_tiles - 1);
       const int m = mt * kTileM + row;
       const int n0 = nt * p.n_tile;
+      if constexpr (kEpiTma) {
+        EpiTma e;
+        e.tm_out = tmO; e.tm_res = tmR; e.dims4 = 0; e.c_row0 = mt * kTileM; e.c_w0 = e.c_h0 = e.c_img = 0;
+        e.ch0 = n0; e.ncols = p.n_tile; e.has_res = p.residual != nullptr; e.relu = p.relu;
+        e.store = mt_raw < p.m_tiles;
+        e.s_scale = s_scale; e.s_bias = s_bias;
+        e.stage_out = epi_base + (uint32_t)g * (uint32_t)(p.epi_bytes >> 1);
+        e.stage_res = e.stage_out + 16384u;
+        e.res_bar = ptx::smem_u32(&bars->res_full[g]); e.bar_id = 1 + g;
+        if (e.has_res && leader) epi_tma_issue_residual(e, 0);   // in flight while the MMAs of this tile finish
+        long long tq0 = 0; if (p.dbg) tq0 = clock64();
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
+        if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
+        ptx::tc_fence_after_sync();
+        epi_tma_tile(e, t_row, row, leader, res_phase);
+        if (p.dbg) dbg_work += clock64() - tq0;
+        ptx::tc_fence_before_sync();
+        if (!pair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
+        else if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[g]), 0);
+      } else {
       const bool valid = m < p.M_total && mt_raw < p.m_tiles;
       size_t opix = (size_t)m;
       if (p.sub) {  // sub-pixel phase of a stride-2 transposed conv: (n, i, j) -> (n, 2i+a, 2j+b)
@@ -281,13 +309,15 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
       if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
       ptx::tc_fence_after_sync();
-      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile));
+      epi_store_row(rres, e, t_row);
       if (p.dbg) dbg_work += clock64() - tq0;
       // all TMEM reads of this thread are complete (wait::ld inside): release the accumulator
       ptx::tc_fence_before_sync();
       if (!pair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
       else if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[g]), 0);   // the leader's MMA warp waits for both CTAs
+      }
     }
+    if (kEpiTma && leader) ptx::tma_store_wait_all();   // shared memory must outlive the bulk stores
     if (p.dbg && threadIdx.x == 128) {
       p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
       p.dbg[blockIdx.x * 32 + 10] = clock64() - dbg_t0;

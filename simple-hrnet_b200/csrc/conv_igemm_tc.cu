@@ -6,18 +6,21 @@
 
 namespace hrnet {
 
-template <bool kPair>
+template <bool kPair, bool kEpiTma>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                      const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  conv_igemm_body<kPair>(tmA, tmB, p, (int)blockIdx.x, (int)gridDim.x, smem_raw);
+  conv_igemm_body<kPair, kEpiTma>(tmA, tmB, &tmO, &tmR, p, (int)blockIdx.x, (int)gridDim.x, smem_raw);
 }
 
 cudaError_t conv_tc_set_attributes(int max_smem) {
-  cudaError_t e = cudaFuncSetAttribute(conv_igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  return e;
 }
 
 // grid size for a persistent launch: as many clusters as can be co-resident (cudaOccupancyMaxActiveClusters), capped
@@ -39,7 +42,7 @@ int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms) {
       at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, conv_igemm_tc_kernel<true>, &cfg) == cudaSuccess && nc > 0) cached[cs] = nc;
+      if (cudaOccupancyMaxActiveClusters(&nc, conv_igemm_tc_kernel<true, false>, &cfg) == cudaSuccess && nc > 0) cached[cs] = nc;
       else { cudaGetLastError(); cached[cs] = num_sms / cs; }
     }
     max_clusters = cached[cs];
@@ -53,8 +56,11 @@ static bool pdl_enabled() {
   return v == 1;
 }
 
-cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int smem_bytes,
-                           int grid, cudaStream_t st) {
+cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOR, const ConvTcParams& p,
+                           int smem_bytes, int grid, cudaStream_t st) {
+  // without the staged epilogue the two extra maps are never dereferenced: pass any valid descriptor
+  const CUtensorMap& tmO = p.epi_tma ? tmOR[0] : tmA;
+  const CUtensorMap& tmR = p.epi_tma ? tmOR[1] : tmA;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
@@ -73,8 +79,12 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     ++na;
   }
   cfg.attrs = at; cfg.numAttrs = (unsigned)na;
-  if (p.cs > 1) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true>, tmA, tmB, p);
-  return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false>, tmA, tmB, p);
+  if (p.cs > 1) {
+    if (p.epi_tma) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true, true>, tmA, tmB, tmO, tmR, p);
+    return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true, false>, tmA, tmB, tmO, tmR, p);
+  }
+  if (p.epi_tma) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, true>, tmA, tmB, tmO, tmR, p);
+  return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, false>, tmA, tmB, tmO, tmR, p);
 }
 
 }  // namespace hrnet

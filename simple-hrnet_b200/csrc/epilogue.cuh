@@ -102,4 +102,121 @@ __device__ __forceinline__ void epi_store_row(uint4 (&r)[8], const EpiRow& e, ui
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Shared-memory-staged epilogue with TMA stores (fp16 output, no sub-pixel remap).
+//
+// The thread-per-row stores above touch 32 different cache lines per warp instruction; for wide tiles (N = 256:
+// layer1 conv3 / downsample) that, not HBM, bounds the kernel (19k clk of epilogue per 128x256 tile,
+// profiles/r01_dbg_role_timers_other_layers.log).  Here each warpgroup owns two 16 KB staging tiles of
+// [128 rows][64 channels] in the SWIZZLE_128B layout TMA expects:
+//   residual: one elected thread TMA-loads the tile's 64-channel chunk (prefetched one chunk ahead), every thread then
+//             reads its own row from shared memory;
+//   output  : every thread writes its row's 64 channels, one elected thread TMA-stores the tile (rows / channels
+//             outside the tensor are clipped by the descriptor, so no validity masks are needed).
+struct EpiTma {
+  const void* tm_out;        // 2-D {C, rows} box {64, 128}  or  4-D {C, W, H, N} box {64, 8, 16, 1}
+  const void* tm_res;        // same geometry over the residual tensor (unused when has_res == 0)
+  int dims4;                 // 0: 2-D coordinates (ch, row0); 1: 4-D coordinates (ch, w0, h0, img)
+  int c_row0, c_w0, c_h0, c_img;
+  int ch0, ncols;            // absolute first channel / channels of this tile
+  int has_res, relu;
+  bool store;                // false for ghost tiles (CTA-pair mode): compute but do not store
+  const float* s_scale;
+  const float* s_bias;
+  uint32_t stage_out, stage_res;   // shared-memory addresses (1024 B aligned) of this warpgroup's staging tiles
+  uint32_t res_bar;                // mbarrier for the residual loads of this warpgroup
+  int bar_id;                      // named barrier id of this warpgroup (128 threads)
+};
+
+__device__ __forceinline__ void epi_tma_issue_residual(const EpiTma& e, int c64) {
+  ptx::mbar_expect_tx(e.res_bar, 128u * 128u);
+  if (e.dims4) ptx::tma_load_4d(e.stage_res, e.tm_res, e.res_bar, e.ch0 + c64, e.c_w0, e.c_h0, e.c_img);
+  else ptx::tma_load_2d(e.stage_res, e.tm_res, e.res_bar, e.ch0 + c64, e.c_row0);
+}
+
+// row = this thread's accumulator row (0..127), leader = one fixed thread of the warpgroup.
+// res_phase: running phase bit of e.res_bar (updated).  The first residual chunk must have been issued by the leader
+// (epi_tma_issue_residual(e, 0)) before the wait on the accumulator barrier.
+__device__ __forceinline__ void epi_tma_tile(const EpiTma& e, uint32_t t_row, int row, bool leader, uint32_t& res_phase) {
+  const uint32_t my_out = e.stage_out + (uint32_t)row * 128u;
+  const uint32_t my_res = e.stage_res + (uint32_t)row * 128u;
+  const uint32_t sw = (uint32_t)(row & 7);
+  for (int c64 = 0; c64 < e.ncols; c64 += 64) {
+    const int nc = min(64, e.ncols - c64);     // 16, 32, 48 or 64 (warp-uniform)
+    uint4 cur[8];
+    if (e.has_res) {
+      ptx::mbar_wait(e.res_bar, res_phase);
+      res_phase ^= 1u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (8 * k < nc)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(cur[k].x), "=r"(cur[k].y), "=r"(cur[k].z), "=r"(cur[k].w)
+                       : "r"(my_res + (((uint32_t)k ^ sw) << 4)));
+    }
+    if (leader) ptx::tma_store_wait_read();      // the previous chunk's store no longer reads stage_out
+    ptx::bar_sync(e.bar_id, 128);                // residual tile consumed by everyone, stage_out free
+    if (e.has_res && leader && c64 + 64 < e.ncols) epi_tma_issue_residual(e, c64 + 64);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c64 + 32 * h;
+      if (32 * h < nc) {                         // warp-uniform
+        uint32_t v0[16], v1[16];
+        const bool two = 32 * h + 16 < nc;
+        ptx::tmem_ld16(t_row + (uint32_t)c, v0);
+        if (two) ptx::tmem_ld16(t_row + (uint32_t)(c + 16), v1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && !two) break;
+          const uint32_t* v = half ? v1 : v0;
+          const int cc = c + 16 * half;
+          const float4* sc = reinterpret_cast<const float4*>(e.s_scale + e.ch0 + cc);
+          const float4* bi = reinterpret_cast<const float4*>(e.s_bias + e.ch0 + cc);
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 s4 = sc[i], b4 = bi[i];
+            y[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), s4.x, b4.x);
+            y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), s4.y, b4.y);
+            y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), s4.z, b4.z);
+            y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), s4.w, b4.w);
+          }
+          if (e.has_res) {
+            const __half2* h0 = reinterpret_cast<const __half2*>(&cur[4 * h + 2 * half]);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&cur[4 * h + 2 * half + 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
+              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
+              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
+            }
+          }
+          if (e.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          uint4 o[2];
+          __half2* oh2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) oh2[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t chunk = (uint32_t)(4 * h + 2 * half + k);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(my_out + ((chunk ^ sw) << 4)), "r"(o[k].x), "r"(o[k].y), "r"(o[k].z), "r"(o[k].w) : "memory");
+          }
+        }
+      }
+    }
+    ptx::fence_proxy_async_smem();               // generic-proxy writes -> visible to the TMA engine
+    ptx::bar_sync(e.bar_id, 128);
+    if (leader && e.store) {
+      if (e.dims4) ptx::tma_store_4d(e.tm_out, e.stage_out, e.ch0 + c64, e.c_w0, e.c_h0, e.c_img);
+      else ptx::tma_store_2d(e.tm_out, e.stage_out, e.ch0 + c64, e.c_row0);
+      ptx::tma_store_commit();
+    }
+  }
+}
+
 }  // namespace hrnet

@@ -48,7 +48,8 @@ struct ConvTcCfg {
   int stages = 0;
   int smem_bytes = 0;
   int tmem_cols = 0;
-  int cs = 1;        // cluster size (weight multicast)
+  int cs = 1;        // 2: CTA-pair mode (cta_group::2)
+  int epi_bytes = 0; // shared memory of the TMA-store epilogue staging tiles (0: direct stores)
 };
 
 
@@ -65,6 +66,7 @@ struct ConvTcParams {
   int relu, out_f32;
   int tmem_cols;
   int a_blk_bytes, b_blk_bytes;
+  int epi_tma, epi_bytes;   // staged epilogue with TMA stores (epilogue.cuh): staging tiles follow the pipeline stages
   const float* scale;
   const float* bias;
   const __half* residual;
@@ -88,6 +90,7 @@ struct ConvPatchParams {
   int a_slot_bytes;            // bytes of the patch part of a slot (weights of a streamed chunk follow it)
   int slot_bytes, nslots;      // ring of patch slots (one channel chunk of one tile each)
   int relu, out_f32, tmem_cols;
+  int epi_tma, epi_bytes;      // staged epilogue with TMA stores: staging tiles follow the patch slots
   const float* scale;
   const float* bias;
   const __half* residual;
@@ -142,6 +145,8 @@ struct Op {
   ConvPatchParams pp{};
   int patch_smem = 0;
   CUtensorMap tmPA[3], tmPB[3];
+  // TMA-store epilogue: output / residual maps (2-D {C, pixels} for the im2col kernel, 4-D {C, W, H, N} for the patch kernel)
+  CUtensorMap tmOR[2];
 };
 
 // host-side description of one grouped launch (conv_group.cu): up to 2 halo-patch + 2 im2col problems
@@ -159,8 +164,8 @@ cudaError_t launch_conv_group(const GroupLaunch& g, cudaStream_t st);
 cudaError_t conv_group_set_attributes(int max_smem);
 
 // launchers (implemented in the .cu files)
-cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcParams& p, int smem_bytes,
-                           int grid, cudaStream_t st);
+cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOR, const ConvTcParams& p,
+                           int smem_bytes, int grid, cudaStream_t st);
 cudaError_t launch_conv_simt(const ConvSimtParams& p, cudaStream_t st);
 cudaError_t launch_stem(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
                         int N, int H, int W, cudaStream_t st);
@@ -178,8 +183,8 @@ cudaError_t launch_stem7(const float* in_nchw, const float* w, const float* scal
                          int N, int H, int W, cudaStream_t st);
 cudaError_t conv_tc_set_attributes(int max_smem);
 int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms);
-cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, const ConvPatchParams& p, int smem_bytes,
-                              int grid, cudaStream_t st);
+cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, const CUtensorMap* tmOR,
+                              const ConvPatchParams& p, int smem_bytes, int grid, cudaStream_t st);
 cudaError_t conv_patch_set_attributes(int max_smem);
 
 }  // namespace hrnet

@@ -245,6 +245,44 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
   return true;
 }
 
+// Staged epilogue with TMA stores (epilogue.cuh): fp16 outputs only, not for the sub-pixel phases of a transposed
+// conv.  HRNET_B200_EPI_TMA = 0: never, 1: tiles at least 128 channels wide (where the thread-per-row stores
+// bound the kernel), 2 (default): every eligible conv (W48/64 forward 10.19 / 9.87 / 9.25 ms for 0 / 1 / 2).  The staging tiles are carved out of the pipeline's shared memory.
+int epi_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HRNET_B200_EPI_TMA");
+    v = e ? atoi(e) : 3;
+  }
+  return v;
+}
+void choose_epi(Op& op, bool out_f32, bool sub, bool has_res) {
+  const int mode = epi_mode();
+  if (!op.use_tc || mode == 0 || out_f32 || sub) return;
+  const int reserve = has_res ? 65536 : 32768;   // per warpgroup: one output tile (+ one residual tile) of 128 x 64 fp16
+  if (op.use_patch) {
+    ConvPatchParams& p = op.pp;
+    if ((mode == 1 && p.Cout < 128) || (mode == 3 && p.Cout < 256)) return;
+    const int fixed = 1024 + 2 * op.cout * 4 + 512;
+    const int avail = kMaxDynSmem - fixed - p.b_bytes - reserve;
+    const int ns = std::min(8, avail / p.slot_bytes) & ~1;
+    if (ns < 2) return;
+    p.nslots = std::min(p.nslots, ns);
+    p.epi_tma = 1; p.epi_bytes = reserve;
+    op.patch_smem = fixed + p.b_bytes + p.nslots * p.slot_bytes + reserve;
+  } else {
+    ConvTcCfg& c = op.tc;
+    if ((mode == 1 && c.n_tile < 128) || (mode == 3 && c.n_tile < 256)) return;
+    if (op.cout / c.n_tile > 1 && c.n_tile % 64) return;   // a partial last 64-channel chunk would spill into the next N-tile
+    const int fixed = 1024 + 2 * op.cout * 4 + 256;
+    const int stage = (c.smem_bytes - fixed) / c.stages;
+    const int ns = std::min(c.stages, ((kMaxDynSmem - fixed - reserve) / stage) & ~1);
+    if (ns < std::min(c.stages, 4)) return;
+    c.stages = ns; c.epi_bytes = reserve;
+    c.smem_bytes = fixed + ns * stage + reserve;
+  }
+}
+
 // ---- HRNet ------------------------------------------------------------------------------------
 int build_hrnet(HrnetPlan& P) {
   const HrnetDesc& d = P.desc;
@@ -478,6 +516,8 @@ void finalize_schedule(HrnetPlan& P) {
   for (auto& op : P.ops) {
     choose_tc_cfg(op, P.desc.flags);
     if (op.use_tc && op.in >= 0) choose_patch_cfg(op, P.tensors[op.in].H, P.tensors[op.in].W, P.desc.flags);
+    if (op.use_tc && op.out >= 0 && !(P.desc.flags & HRNET_FLAG_GROUP))
+      choose_epi(op, P.tensors[op.out].dtype == DT_F32, op.pad >= 100, op.res >= 0);
   }
   // (Opt-in, HRNET_FLAG_PARTITION; measured SLOWER than letting every kernel use all SMs: 12.85 vs 9.9 ms per
   // W48/64 forward, profiles/r01_exp_variants_partition_pdl.log -- total work is unchanged and the low-resolution
@@ -639,6 +679,46 @@ int encode_patch(CUtensorMap* tm, const void* act, int N, int H, int W, int C, i
   return 0;
 }
 
+// output / residual NHWC fp16 as seen by the staged epilogue: 2-D {C, pixels}, box 64 channels x 128 pixels
+int encode_out2d(CUtensorMap* tm, const void* ptr, size_t rows, int C) {
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HRNET_E_CUDA, "cuTensorMapEncodeTiled(out 2d) failed: " + std::to_string((int)r));
+  return 0;
+}
+// ... and for the halo-patch kernel: 4-D {C, W, H, N}, box = one 8 x 16 output tile of 64 channels
+int encode_out4d(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kPatchTW, (cuuint32_t)kPatchTH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HRNET_E_CUDA, "cuTensorMapEncodeTiled(out 4d) failed: " + std::to_string((int)r));
+  return 0;
+}
+// maps of the staged epilogue of `op` (residual == nullptr: the output map stands in, it is never used)
+int encode_epi_maps(Op& op, const void* out, const void* residual, int N, int OH, int OW) {
+  const void* res = residual ? residual : out;
+  int rc;
+  if (op.use_patch) {
+    if (!op.pp.epi_tma) return 0;
+    rc = encode_out4d(&op.tmOR[0], out, N, OH, OW, op.cout);
+    if (!rc) rc = encode_out4d(&op.tmOR[1], res, N, OH, OW, op.cout);
+  } else {
+    if (!op.tc.epi_bytes) return 0;
+    rc = encode_out2d(&op.tmOR[0], out, (size_t)N * OH * OW, op.cout);
+    if (!rc) rc = encode_out2d(&op.tmOR[1], res, (size_t)N * OH * OW, op.cout);
+  }
+  return rc;
+}
+
 // all tensor maps of a patch op: one 64-channel activation map and one weight map per block width in use
 int encode_patch_maps(Op& op, const void* act, const void* w, int N) {
   const ConvPatchParams& p = op.pp;
@@ -763,7 +843,7 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
     o << "],\"tc\":{\"kc\":" << op.tc.kc << ",\"bps\":" << op.tc.bps << ",\"n_tile\":" << op.tc.n_tile
       << ",\"cs\":" << op.tc.cs << ",\"stages\":" << op.tc.stages << ",\"smem\":" << op.tc.smem_bytes << ",\"tmem_cols\":" << op.tc.tmem_cols
-      << "}}";
+      << ",\"epi\":" << (op.use_patch ? op.pp.epi_bytes : op.tc.epi_bytes) << "}}";
   }
   o << "]}";
   const std::string s = o.str();
@@ -810,6 +890,12 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
       if (rc) return rc;
       max_patch_smem = std::max(max_patch_smem, op.patch_smem);
     }
+    {
+      const TensorInfo& to = P->tensors[op.out];
+      rc = encode_epi_maps(op, P->abase + to.offset, op.res >= 0 ? P->abase + P->tensors[op.res].offset : nullptr,
+                           P->desc.max_batch, to.H, to.W);
+      if (rc) return rc;
+    }
   }
   {
     cudaError_t e = conv_group_set_attributes(kMaxDynSmem);
@@ -820,7 +906,7 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
     if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute(patch): ") + cudaGetErrorString(e));
   }
   if (max_smem) {
-    cudaError_t e = conv_tc_set_attributes(std::max(max_smem, 200 * 1024 + 4096));
+    cudaError_t e = conv_tc_set_attributes(kMaxDynSmem);
     if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   }
   if (!P->side[0]) {
@@ -882,6 +968,7 @@ ConvTcParams fill_tc_params(HrnetPlan* P, const Op& op, int n) {
   p.bias = (const float*)(P->wbase + pi.bias_offset);
   p.residual = op.res >= 0 ? (const __half*)(P->abase + P->tensors[op.res].offset) : nullptr;
   p.out = P->abase + to.offset;
+  p.epi_tma = op.tc.epi_bytes ? 1 : 0; p.epi_bytes = op.tc.epi_bytes;
   return p;
 }
 
@@ -1003,7 +1090,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.out = tptr(op.out);
         if (p.total_tiles == 0) return 0;
         const int cap = std::max(1, (int)std::lround(op.sm_frac * P->num_sms));
-        CK(launch_conv_patch(op.tmPA, op.tmPB, p, op.patch_smem, std::min(p.total_tiles, cap), st));
+        CK(launch_conv_patch(op.tmPA, op.tmPB, op.tmOR, p, op.patch_smem, std::min(p.total_tiles, cap), st));
       } else if (op.use_tc) {
         ConvTcParams p{};
         p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
@@ -1020,10 +1107,11 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.bias = (const float*)(P->wbase + pi.bias_offset);
         p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
         p.out = tptr(op.out);
+        p.epi_tma = op.tc.epi_bytes ? 1 : 0; p.epi_bytes = op.tc.epi_bytes;
         const int tiles = p.m_tiles * p.n_tiles;
         if (tiles == 0) return 0;
         const int cap = std::max(p.cs, (int)std::lround(op.sm_frac * P->num_sms) / p.cs * p.cs);
-        CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, std::min(cap, conv_tc_grid(p, op.tc.smem_bytes, P->num_sms)), st));
+        CK(launch_conv_tc(op.tmA, op.tmB, op.tmOR, p, op.tc.smem_bytes, std::min(cap, conv_tc_grid(p, op.tc.smem_bytes, P->num_sms)), st));
       } else {
         if (sub) return fail(HRNET_E_INVALID, "transposed-conv phases are not wired to the SIMT kernel yet");
         ConvSimtParams p{};
@@ -1324,6 +1412,9 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     if (rc) return rc;
     rc = encode_patch_maps(op, in, w, n);
     if (rc) return rc;
+    choose_epi(op, out_f32 != 0, false, residual != nullptr);
+    rc = encode_epi_maps(op, out, residual, n, OH, OW);
+    if (rc) return rc;
     CK(conv_patch_set_attributes(kMaxDynSmem));
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
@@ -1334,7 +1425,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     if (p.total_tiles == 0) return HRNET_OK;
     if (const char* e = getenv("HRNET_B200_GRID_CAP")) sms = std::max(1, std::min(sms, atoi(e)));   // experiments
     DbgTimers dt; dt.begin(std::min(p.total_tiles, sms)); p.dbg = dt.dev;
-    CK(launch_conv_patch(op.tmPA, op.tmPB, p, op.patch_smem, std::min(p.total_tiles, sms), st));
+    CK(launch_conv_patch(op.tmPA, op.tmPB, op.tmOR, p, op.patch_smem, std::min(p.total_tiles, sms), st));
     dt.end(st, "patch", p.total_tiles);
     return HRNET_OK;
   }
@@ -1343,11 +1434,14 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     if (!op.use_tc) return fail(HRNET_E_INVALID, "shape not supported by the tcgen05 path (cin, cout must be multiples of 16)");
     int rc = load_driver_fns();
     if (rc) return rc;
+    choose_epi(op, out_f32 != 0, false, residual != nullptr);
+    rc = encode_epi_maps(op, out, residual, n, OH, OW);
+    if (rc) return rc;
     rc = encode_im2col(&op.tmA, in, n, ih, iw, cin, op.tc.kc, ksize, stride, op.pad, op.pad, op.pad, op.pad);
     if (rc) return rc;
     rc = encode_weights(&op.tmB, w, cout, ksize * ksize * cin, op.tc.kc, op.tc.n_tile / op.tc.cs);
     if (rc) return rc;
-    CK(conv_tc_set_attributes(200 * 1024 + 4096));
+    CK(conv_tc_set_attributes(kMaxDynSmem));
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1362,10 +1456,11 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
     p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
+    p.epi_tma = op.tc.epi_bytes ? 1 : 0; p.epi_bytes = op.tc.epi_bytes;
     const int tiles = p.m_tiles * p.n_tiles;
     if (tiles == 0) return HRNET_OK;
     DbgTimers dt; dt.begin(conv_tc_grid(p, op.tc.smem_bytes, sms)); p.dbg = dt.dev;
-    CK(launch_conv_tc(op.tmA, op.tmB, p, op.tc.smem_bytes, conv_tc_grid(p, op.tc.smem_bytes, sms), st));
+    CK(launch_conv_tc(op.tmA, op.tmB, op.tmOR, p, op.tc.smem_bytes, conv_tc_grid(p, op.tc.smem_bytes, sms), st));
     dt.end(st, "im2col", tiles);
   } else {
     ConvSimtParams p{};
