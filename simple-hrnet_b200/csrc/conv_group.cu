@@ -27,13 +27,13 @@ __global__ void __launch_bounds__(384, 1) conv_group_kernel(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const int b = (int)blockIdx.x;
   if (b < a.cta_end[0]) {
-    conv3x3_patch_body<false>(a.pm[0], a.pp[0], b, a.cta_end[0], smem_raw);
+    conv3x3_patch_body<false, 0>(a.pm[0], a.pp[0], b, a.cta_end[0], smem_raw);
   } else if (b < a.cta_end[1]) {
-    conv3x3_patch_body<false>(a.pm[1], a.pp[1], b - a.cta_end[0], a.cta_end[1] - a.cta_end[0], smem_raw);
+    conv3x3_patch_body<false, 0>(a.pm[1], a.pp[1], b - a.cta_end[0], a.cta_end[1] - a.cta_end[0], smem_raw);
   } else if (b < a.cta_end[2]) {
-    conv_igemm_body<false, false>(a.ia[0], a.ib[0], nullptr, nullptr, a.ip[0], b - a.cta_end[1], a.cta_end[2] - a.cta_end[1], smem_raw);
+    conv_igemm_body<false, 0>(a.ia[0], a.ib[0], nullptr, nullptr, a.ip[0], b - a.cta_end[1], a.cta_end[2] - a.cta_end[1], smem_raw);
   } else {
-    conv_igemm_body<false, false>(a.ia[1], a.ib[1], nullptr, nullptr, a.ip[1], b - a.cta_end[2], a.cta_end[3] - a.cta_end[2], smem_raw);
+    conv_igemm_body<false, 0>(a.ia[1], a.ib[1], nullptr, nullptr, a.ip[1], b - a.cta_end[2], a.cta_end[3] - a.cta_end[2], smem_raw);
   }
 }
 

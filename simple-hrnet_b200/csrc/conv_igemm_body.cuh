@@ -42,6 +42,7 @@ constexpr int kTileM = 128;
 constexpr int kThreads = 384;
 constexpr int kMaxStages = 8;
 constexpr int kKC = 64;                 // channels per k-block: 128-byte swizzled rows
+constexpr int kMaxKBlocks = 128;        // k-blocks per tile (taps x ceil(Cin / 64)): 9 x 512 / 64 = 72, 1 x 2048 / 64 = 32
 
 struct __align__(8) PipeBars {
   uint64_t full[kMaxStages];
@@ -51,14 +52,29 @@ struct __align__(8) PipeBars {
   uint64_t res_full[2];     // TMA-loaded residual tile of each epilogue warpgroup (staged epilogue)
   uint32_t tmem_base;
   uint32_t pad;
+  uint32_t kb_tab[kMaxKBlocks];   // per k-block: weight K coordinate (15 b) | channel offset (12 b) << 15 | tap s << 27 | tap r << 29
 };
+
+// All K16 steps of one 64-channel k-block: K advances 32 B (+2 in the descriptor's address field) per step.
+template <int NK, bool kPair>
+__device__ __forceinline__ void issue_k16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate_first) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    if constexpr (kPair)
+      ptx::mma_f16_ss_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : accumulate_first);
+    else
+      ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : accumulate_first);
+  }
+}
 
 // kPair is a template parameter (not a run-time flag): a kernel that contains cta_group::2 instructions can only be
 // launched as a cluster of CTA pairs ("cluster misconfiguration" otherwise).
 // Body of one CTA working on problem `p` as CTA `cta` of `nctas`; shared by the single-problem kernels and the grouped
 // multi-problem kernel (conv_group.cu, kPair = false only).
-// kEpiTma selects the staged TMA-store epilogue at compile time (p.epi_tma must agree).
-template <bool kPair, bool kEpiTma>
+// kEpi selects the epilogue at compile time (p.epi_tma must agree): 0 direct row-per-thread stores, 1 staged TMA stores,
+// 2 warp-staged coalesced stores (epilogue.cuh).
+template <bool kPair, int kEpi>
 __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO,
                                                 const CUtensorMap* tmR, const ConvTcParams& p, const int cta,
                                                 const int nctas, uint8_t* smem_raw) {
@@ -110,6 +126,16 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     if constexpr (kPair) ptx::tmem_alloc_2cta(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
     else ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
   }
+  uint32_t* kb_tab = bars->kb_tab;
+  if (warp == 3) {   // k-block table: no divisions on the producers' issue path
+    for (int kb = lane; kb < p.nkb; kb += 32) {
+      const int tap = kb / p.cpt;
+      const int c0 = (kb - tap * p.cpt) * kKC;
+      const int r = tap / p.ksize;
+      const int sx = tap - r * p.ksize;
+      kb_tab[kb] = (uint32_t)(tap * p.Cin + c0) | ((uint32_t)c0 << 15) | ((uint32_t)sx << 27) | ((uint32_t)r << 29);
+    }
+  }
   if (warp >= 4) {
     for (int i = threadIdx.x - 128; i < p.Cout; i += 256) {   // constants: safe before pdl_wait
       s_scale[i] = p.scale[i];
@@ -124,134 +150,143 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
   const uint32_t tmem_base = bars->tmem_base;
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 32 + 17] = (long long)ptx::globaltimer();
 
+  // Issue-side costs measured on B200 (profiles/r01_exp_mma_issue_overhead.log): a tcgen05.mma takes ~48 clk of the
+  // issuing thread whatever N, a tcgen05.commit ~90, an mbarrier try_wait ~150 even when the phase is already complete,
+  // and every entry into an elect region ~40.  With one 64-channel k-block per stage that serial overhead (not the
+  // math, not shared-memory bandwidth) set the pace: ~570 clk per k-block for every N <= 192.  Hence: ONE elected thread
+  // runs each role's whole loop, the barrier state of the NEXT stage is probed (non-blocking test_wait) before the current stage's TMA / MMA
+  // instructions are issued (the try_wait latency overlaps them), and small-N convs put two k-blocks in a stage.
   if (warp < 2) {
     // ===================================================================== TMA producers (stage parity = warp)
-    long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    const int b_rows = p.n_tile / cs;   // pair: this CTA stages only its half of the weight tile
-    int L = 0;                            // running stage-load index over all tiles of this CTA
-    for (int st = cluster_id; st < total_super; st += num_clusters) {
-      const int nt = st / m_super;
-      const int mt = min((st - nt * m_super) * cs + (int)crank, p.m_tiles - 1);  // ghost CTAs redo the last tile
-      const int m0 = mt * kTileM;
-      const int img = m0 / p.OHW;
-      const int rem = m0 - img * p.OHW;
-      const int oh0 = rem / p.OW;
-      const int ow0 = rem - oh0 * p.OW;
-      const int bw = ow0 * p.stride - p.pad_w;
-      const int bh = oh0 * p.stride - p.pad_h;
-      const int n0 = nt * p.n_tile;
-      for (int ks = 0; ks < nstages_k; ++ks, ++L) {
-        if ((L & 1) != warp) continue;
-        const int stage = L % p.stages;
-        const uint32_t phase = (uint32_t)((L / p.stages) & 1);
-        const int kb0 = ks * p.bps;
-        const int nblk = min(p.bps, p.nkb - kb0);
-        long long tq0 = 0; if (p.dbg) tq0 = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
-        if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
-        const uint32_t full = ptx::smem_u32(&bars->full[stage]);
-        const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
-        const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
-        const uint32_t tx = (uint32_t)(nblk * (kTileM * kKC * 2 + b_rows * kKC * 2));
-        if (ptx::elect_one()) {
+    if (ptx::elect_one()) {
+      long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
+      const int b_rows = p.n_tile / cs;   // pair: this CTA stages only its half of the weight tile
+      int L = 0;                            // running stage-load index over all tiles of this CTA
+      int stage = warp;                     // stage / phase of the next load of THIS producer (advances by 2; stages is even)
+      uint32_t phase = 0;
+      bool ready = false;                   // result of the early try_wait on empty[stage]
+      for (int st = cluster_id; st < total_super; st += num_clusters) {
+        const int nt = st / m_super;
+        const int mt = min((st - nt * m_super) * cs + (int)crank, p.m_tiles - 1);  // ghost CTAs redo the last tile
+        const int m0 = mt * kTileM;
+        const int img = m0 / p.OHW;
+        const int rem = m0 - img * p.OHW;
+        const int oh0 = rem / p.OW;
+        const int ow0 = rem - oh0 * p.OW;
+        const int bw = ow0 * p.stride - p.pad_w;
+        const int bh = oh0 * p.stride - p.pad_h;
+        const int n0 = nt * p.n_tile;
+        for (int ks = 0; ks < nstages_k; ++ks, ++L) {
+          if ((L & 1) != warp) continue;
+          const int kb0 = ks * p.bps;
+          const int nblk = min(p.bps, p.nkb - kb0);
+          long long tq0 = 0; if (p.dbg) tq0 = clock64();
+          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
+          if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
+          const uint32_t full = ptx::smem_u32(&bars->full[stage]);
+          const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
+          const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
+          const uint32_t tx = (uint32_t)(nblk * (kTileM * kKC * 2 + b_rows * kKC * 2));
+          // this producer's next stage: ask for its barrier state now, look at the answer after the TMA issue
+          int nstage = stage + 2;
+          uint32_t nphase = phase;
+          if (nstage >= p.stages) { nstage -= p.stages; nphase ^= 1u; }
+          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->empty[nstage]), nphase ^ 1u);
           if constexpr (!kPair) {
             ptx::mbar_expect_tx(full, tx);
             for (int j = 0; j < nblk; ++j) {
-              const int kb = kb0 + j;
-              const int tap = kb / p.cpt;
-              const int c0 = (kb - tap * p.cpt) * kKC;
-              const int r = tap / p.ksize;
-              const int s = tap - r * p.ksize;
-              ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, full, c0, bw, bh, img,
-                                      (uint16_t)s, (uint16_t)r);
-              ptx::tma_load_2d(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, full, tap * p.Cin + c0, n0);
+              const uint32_t e = kb_tab[kb0 + j];       // (weight K coordinate | channel offset | tap s | tap r)
+              ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, full, (int)((e >> 15) & 0xfffu), bw, bh, img,
+                                      (uint16_t)((e >> 27) & 3u), (uint16_t)(e >> 29));
+              ptx::tma_load_2d(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, full, (int)(e & 0x7fffu), n0);
             }
           } else {
             const uint32_t lfull = ptx::mapa_cluster(full, 0);   // the leader's barrier collects both CTAs' bytes
             ptx::mbar_expect_tx_cluster(lfull, tx);
             for (int j = 0; j < nblk; ++j) {
-              const int kb = kb0 + j;
-              const int tap = kb / p.cpt;
-              const int c0 = (kb - tap * p.cpt) * kKC;
-              const int r = tap / p.ksize;
-              const int s = tap - r * p.ksize;
-              ptx::tma_load_im2col_4d_2cta(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, lfull, c0, bw, bh, img,
-                                           (uint16_t)s, (uint16_t)r);
-              ptx::tma_load_2d_2cta(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, lfull, tap * p.Cin + c0,
+              const uint32_t e = kb_tab[kb0 + j];
+              ptx::tma_load_im2col_4d_2cta(a_dst + (uint32_t)(j * p.a_blk_bytes), &tmA, lfull, (int)((e >> 15) & 0xfffu), bw, bh,
+                                           img, (uint16_t)((e >> 27) & 3u), (uint16_t)(e >> 29));
+              ptx::tma_load_2d_2cta(b_dst + (uint32_t)(j * p.b_blk_bytes), &tmB, lfull, (int)(e & 0x7fffu),
                                     n0 + (int)crank * b_rows);
             }
           }
+          stage = nstage; phase = nphase; ready = nready;
+          if (p.dbg) dbg_issue += clock64() - tq0;
         }
-        __syncwarp();
-        if (p.dbg) dbg_issue += clock64() - tq0;
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 32 + 0 + 11 * warp] = dbg_wait;
+        p.dbg[blockIdx.x * 32 + 1 + 11 * warp] = dbg_issue;
+        p.dbg[blockIdx.x * 32 + 2 + 11 * warp] = clock64() - dbg_t0;
       }
     }
-    if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 32 + 0 + 11 * warp] = dbg_wait;
-      p.dbg[blockIdx.x * 32 + 1 + 11 * warp] = dbg_issue;
-      p.dbg[blockIdx.x * 32 + 2 + 11 * warp] = clock64() - dbg_t0;
-    }
+    __syncwarp();
   } else if (warp == 2 && (!pair || crank == 0)) {
     // ===================================================================== MMA issuer (pair mode: leader CTA only)
-    const uint32_t idesc = ptx::umma_idesc_f16(pair ? 2 * kTileM : kTileM, p.n_tile);
-    const int ctail = p.Cin - (p.cpt - 1) * kKC;          // real channels in the last k-block of a tap
-    int L = 0;
-    int it = 0;
-    long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    for (int st = cluster_id; st < total_super; st += num_clusters, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      long long tq0 = 0; if (p.dbg) tq0 = clock64();
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
-      if (p.dbg) dbg_wtm += clock64() - tq0;
-      ptx::tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-      for (int ks = 0; ks < nstages_k; ++ks, ++L) {
-        const int stage = L % p.stages;
-        const uint32_t phase = (uint32_t)((L / p.stages) & 1);
-        const int kb0 = ks * p.bps;
-        const int nblk = min(p.bps, p.nkb - kb0);
-        if (p.dbg) tq0 = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
-        if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (L == 0 && lane == 0) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::umma_idesc_f16(pair ? 2 * kTileM : kTileM, p.n_tile);
+      const int ctail = p.Cin - (p.cpt - 1) * kKC;          // real channels in the last k-block of a tap
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ready = false;                   // result of the early try_wait on full[stage]
+      int it = 0;
+      bool first_stage = true;
+      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
+      for (int st = cluster_id; st < total_super; st += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        long long tq0 = 0; if (p.dbg) tq0 = clock64();
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        if (p.dbg) dbg_wtm += clock64() - tq0;
         ptx::tc_fence_after_sync();
-        const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
-        const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
-        if (ptx::elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+        int cblk = 0;                         // channel block of the stage's first k-block within its tap (kb % cpt, no division)
+        for (int ks = 0; ks < nstages_k; ++ks) {
+          const int kb0 = ks * p.bps;
+          const int nblk = min(p.bps, p.nkb - kb0);
+          if (p.dbg) tq0 = clock64();
+          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+          if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (first_stage) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
+          first_stage = false;
+          ptx::tc_fence_after_sync();
+          const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
+          const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
+          // the next stage's barrier state is requested before this stage's MMAs are issued
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
+          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->full[nstage]), nphase);
           for (int j = 0; j < nblk; ++j) {
-            const int kb = kb0 + j;
-            const int cblk = kb % p.cpt;
             const int nk = (cblk == p.cpt - 1 ? ctail : kKC) / 16;
+            cblk = cblk + 1 == p.cpt ? 0 : cblk + 1;
             const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)(j * p.a_blk_bytes), 128u, 1024u);
             const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), 128u, 1024u);
-            for (int k = 0; k < nk; ++k) {
-              // advancing K by 16 fp16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-              if constexpr (!kPair)
-                ptx::mma_f16_ss(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                (uint32_t)((ks | j | k) != 0));
-              else
-                ptx::mma_f16_ss_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                     (uint32_t)((ks | j | k) != 0));
+            const uint32_t first = (uint32_t)((kb0 + j) != 0);
+            switch (nk) {   // fully unrolled K16 steps: descriptors are base + compile-time offset
+              case 4: issue_k16<4, kPair>(d_tmem, adesc, bdesc, idesc, first); break;
+              case 3: issue_k16<3, kPair>(d_tmem, adesc, bdesc, idesc, first); break;
+              case 2: issue_k16<2, kPair>(d_tmem, adesc, bdesc, idesc, first); break;
+              default: issue_k16<1, kPair>(d_tmem, adesc, bdesc, idesc, first); break;
             }
           }
           // frees the smem slot (pair: in both CTAs) when the MMAs retire
           if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
           else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
+          stage = nstage; phase = nphase; ready = nready;
+          if (p.dbg) dbg_mma += clock64() - tq0;
         }
-        __syncwarp();
-        if (p.dbg) dbg_mma += clock64() - tq0;
-      }
-      if (ptx::elect_one()) {   // accumulator ready (pair: for both CTAs' epilogues)
+        // accumulator ready (pair: for both CTAs' epilogues)
         if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
         else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->tmem_full[acc]), mc_mask);
       }
-      __syncwarp();
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 32 + 19] = (long long)ptx::globaltimer();
+        p.dbg[blockIdx.x * 32 + 4] = dbg_wfull; p.dbg[blockIdx.x * 32 + 5] = dbg_wtm;
+        p.dbg[blockIdx.x * 32 + 6] = dbg_mma; p.dbg[blockIdx.x * 32 + 7] = clock64() - dbg_t0;
+      }
     }
-    if (p.dbg && lane == 0) {
-      p.dbg[blockIdx.x * 32 + 19] = (long long)ptx::globaltimer();
-      p.dbg[blockIdx.x * 32 + 4] = dbg_wfull; p.dbg[blockIdx.x * 32 + 5] = dbg_wtm;
-      p.dbg[blockIdx.x * 32 + 6] = dbg_mma; p.dbg[blockIdx.x * 32 + 7] = clock64() - dbg_t0;
-    }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================================================================== epilogue (two warpgroups, alternating tiles)
     const int g = (warp - 4) >> 2;        // warpgroup == accumulator buffer it drains
@@ -270,7 +305,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       const int mt = min(mt_raw, p.m_tiles - 1);
       const int m = mt * kTileM + row;
       const int n0 = nt * p.n_tile;
-      if constexpr (kEpiTma) {
+      if constexpr (kEpi == 1) {
         EpiTma e;
         e.tm_out = tmO; e.tm_res = tmR; e.dims4 = 0; e.c_row0 = mt * kTileM; e.c_w0 = e.c_h0 = e.c_img = 0;
         e.ch0 = n0; e.ncols = p.n_tile; e.has_res = p.residual != nullptr; e.relu = p.relu;
@@ -285,6 +320,23 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
         if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
         ptx::tc_fence_after_sync();
         epi_tma_tile(e, t_row, row, leader, res_phase);
+        if (p.dbg) dbg_work += clock64() - tq0;
+        ptx::tc_fence_before_sync();
+        if (!pair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
+        else if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[g]), 0);
+      } else if constexpr (kEpi == 2) {
+        EpiCoal e;
+        e.s_scale = s_scale; e.s_bias = s_bias; e.residual = p.residual; e.out = reinterpret_cast<__half*>(p.out);
+        e.row_off = (size_t)m * p.Cout + n0;
+        e.ch0 = n0; e.ncols = p.n_tile; e.relu = p.relu;
+        e.valid = m < p.M_total && mt_raw < p.m_tiles;
+        e.stage = epi_base + (uint32_t)(warp - 4) * (uint32_t)kCoalWarpBytes;
+        if (e.residual != nullptr) epi_coal_fetch_residual(e, 0, lane);   // in flight while the MMAs of this tile finish
+        long long tq0 = 0; if (p.dbg) tq0 = clock64();
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
+        if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
+        ptx::tc_fence_after_sync();
+        epi_coal_tile(e, t_row, lane);
         if (p.dbg) dbg_work += clock64() - tq0;
         ptx::tc_fence_before_sync();
         if (!pair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
@@ -317,7 +369,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       else if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[g]), 0);   // the leader's MMA warp waits for both CTAs
       }
     }
-    if (kEpiTma && leader) ptx::tma_store_wait_all();   // shared memory must outlive the bulk stores
+    if (kEpi == 1 && leader) ptx::tma_store_wait_all();   // shared memory must outlive the bulk stores
     if (p.dbg && threadIdx.x == 128) {
       p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
       p.dbg[blockIdx.x * 32 + 10] = clock64() - dbg_t0;

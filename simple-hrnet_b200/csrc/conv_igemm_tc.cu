@@ -6,20 +6,26 @@
 
 namespace hrnet {
 
-template <bool kPair, bool kEpiTma>
+template <bool kPair, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                      const ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  conv_igemm_body<kPair, kEpiTma>(tmA, tmB, &tmO, &tmR, p, (int)blockIdx.x, (int)gridDim.x, smem_raw);
+  conv_igemm_body<kPair, kEpi>(tmA, tmB, &tmO, &tmR, p, (int)blockIdx.x, (int)gridDim.x, smem_raw);
 }
 
+template <bool kPair, int kEpi>
+static cudaError_t set_attr(int max_smem) {
+  return cudaFuncSetAttribute(conv_igemm_tc_kernel<kPair, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
 cudaError_t conv_tc_set_attributes(int max_smem) {
-  cudaError_t e = cudaFuncSetAttribute(conv_igemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_igemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaError_t e = set_attr<false, 0>(max_smem);
+  if (e == cudaSuccess) e = set_attr<false, 1>(max_smem);
+  if (e == cudaSuccess) e = set_attr<false, 2>(max_smem);
+  if (e == cudaSuccess) e = set_attr<true, 0>(max_smem);
+  if (e == cudaSuccess) e = set_attr<true, 1>(max_smem);
+  if (e == cudaSuccess) e = set_attr<true, 2>(max_smem);
   return e;
 }
 
@@ -42,7 +48,7 @@ int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms) {
       at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, conv_igemm_tc_kernel<true, false>, &cfg) == cudaSuccess && nc > 0) cached[cs] = nc;
+      if (cudaOccupancyMaxActiveClusters(&nc, conv_igemm_tc_kernel<true, 0>, &cfg) == cudaSuccess && nc > 0) cached[cs] = nc;
       else { cudaGetLastError(); cached[cs] = num_sms / cs; }
     }
     max_clusters = cached[cs];
@@ -59,8 +65,8 @@ static bool pdl_enabled() {
 cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOR, const ConvTcParams& p,
                            int smem_bytes, int grid, cudaStream_t st) {
   // without the staged epilogue the two extra maps are never dereferenced: pass any valid descriptor
-  const CUtensorMap& tmO = p.epi_tma ? tmOR[0] : tmA;
-  const CUtensorMap& tmR = p.epi_tma ? tmOR[1] : tmA;
+  const CUtensorMap& tmO = p.epi_tma == 1 ? tmOR[0] : tmA;
+  const CUtensorMap& tmR = p.epi_tma == 1 ? tmOR[1] : tmA;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
@@ -80,11 +86,13 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   }
   cfg.attrs = at; cfg.numAttrs = (unsigned)na;
   if (p.cs > 1) {
-    if (p.epi_tma) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true, true>, tmA, tmB, tmO, tmR, p);
-    return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true, false>, tmA, tmB, tmO, tmR, p);
+    if (p.epi_tma == 1) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true, 1>, tmA, tmB, tmO, tmR, p);
+    if (p.epi_tma == 2) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true, 2>, tmA, tmB, tmO, tmR, p);
+    return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<true, 0>, tmA, tmB, tmO, tmR, p);
   }
-  if (p.epi_tma) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, true>, tmA, tmB, tmO, tmR, p);
-  return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, false>, tmA, tmB, tmO, tmR, p);
+  if (p.epi_tma == 1) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, 1>, tmA, tmB, tmO, tmR, p);
+  if (p.epi_tma == 2) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, 2>, tmA, tmB, tmO, tmR, p);
+  return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, 0>, tmA, tmB, tmO, tmR, p);
 }
 
 }  // namespace hrnet

@@ -219,4 +219,133 @@ __device__ __forceinline__ void epi_tma_tile(const EpiTma& e, uint32_t t_row, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-staged coalesced epilogue (fp16 output, no sub-pixel remap).
+//
+// With one thread per output row every 16-byte global access of a warp touches 32 different cache lines; measured on
+// the 48-channel halo-patch conv that costs ~1000 clk of load/store-unit time per tile for the stores and ~500 for the
+// residual, more than the tile's MMAs in CTA-pair mode (profiles/r01_exp_patch_pair_nostore.log).  Here each epilogue
+// warp owns a private [32 rows][64 channels + 16 B pad] staging tile in shared memory (pitch 144 B: both the row-per-
+// thread and the coalesced access pattern are bank-conflict free) and only __syncwarp() is needed:
+//   residual: cp.async 16-byte copies in coalesced order (consecutive lanes = consecutive bytes of a row) -> each
+//             thread reads its own row;
+//   output  : each thread writes its row, then the warp stores the tile in coalesced order.
+// A warp instruction then touches 32 / (chunks per row) rows of 16 * (chunks per row) contiguous bytes: 4-6 lines.
+
+struct EpiCoal {
+  const float* s_scale;
+  const float* s_bias;
+  const __half* residual;   // global NHWC fp16 or nullptr
+  __half* out;              // global NHWC fp16
+  size_t row_off;           // element offset of (this thread's pixel, first channel of this tile)
+  int ch0, ncols;           // absolute first channel / channels of this tile (multiple of 16)
+  int relu;
+  bool valid;               // this thread's row maps to a real output pixel
+  uint32_t stage;           // shared-memory address of this warp's staging tile
+};
+
+// residual chunk [c64, c64 + nc) of the warp's 32 rows -> staging (asynchronous; complete with cp_async_wait_all)
+__device__ __forceinline__ void epi_coal_fetch_residual(const EpiCoal& e, int c64, int lane) {
+  const int nc = min(64, e.ncols - c64);
+  const int cpr = nc >> 3;                               // 16-byte pieces per row: 2, 4, 6 or 8
+  const uint32_t inv = (65536u + (uint32_t)cpr - 1u) / (uint32_t)cpr;
+  const uint32_t vmask = __ballot_sync(0xffffffffu, e.valid);
+  const unsigned long long off = (unsigned long long)e.row_off;
+  for (int i = 0; i < cpr; ++i) {
+    const uint32_t idx = (uint32_t)(i * 32 + lane);
+    const uint32_t r = (idx * inv) >> 16;
+    const uint32_t k = idx - r * (uint32_t)cpr;
+    const unsigned long long roff = __shfl_sync(0xffffffffu, off, (int)r);
+    if ((vmask >> r) & 1u)
+      ptx::cp_async16(e.stage + r * (uint32_t)kCoalPitch + (k << 4), e.residual + roff + (size_t)(c64 + (int)(k << 3)));
+  }
+  ptx::cp_async_commit();
+}
+
+// t_row = TMEM address of (this warp's lane quarter, first column of the accumulator).  The residual of chunk 0 must
+// have been requested (epi_coal_fetch_residual(e, 0, lane)) before the wait on the accumulator barrier.
+__device__ __forceinline__ void epi_coal_tile(const EpiCoal& e, uint32_t t_row, int lane) {
+  const uint32_t my = e.stage + (uint32_t)lane * (uint32_t)kCoalPitch;
+  const uint32_t vmask = __ballot_sync(0xffffffffu, e.valid);
+  const unsigned long long off = (unsigned long long)e.row_off;
+  const bool has_res = e.residual != nullptr;
+  for (int c64 = 0; c64 < e.ncols; c64 += 64) {
+    const int nc = min(64, e.ncols - c64);     // warp-uniform
+    const int cpr = nc >> 3;
+    uint4 cur[8];
+    if (has_res) {
+      ptx::cp_async_wait_all();
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < cpr) cur[k] = ptx::lds128(my + (uint32_t)(k << 4));
+      __syncwarp();                            // staging tile free for the outputs
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c64 + 32 * h;
+      if (32 * h < nc) {                       // warp-uniform
+        uint32_t v0[16], v1[16];
+        const bool two = 32 * h + 16 < nc;
+        ptx::tmem_ld16(t_row + (uint32_t)c, v0);
+        if (two) ptx::tmem_ld16(t_row + (uint32_t)(c + 16), v1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && !two) break;
+          const uint32_t* v = half ? v1 : v0;
+          const int cc = c + 16 * half;
+          const float4* sc = reinterpret_cast<const float4*>(e.s_scale + e.ch0 + cc);
+          const float4* bi = reinterpret_cast<const float4*>(e.s_bias + e.ch0 + cc);
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 s4 = sc[i], b4 = bi[i];
+            y[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), s4.x, b4.x);
+            y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), s4.y, b4.y);
+            y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), s4.z, b4.z);
+            y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), s4.w, b4.w);
+          }
+          if (has_res) {
+            const __half2* h0 = reinterpret_cast<const __half2*>(&cur[4 * h + 2 * half]);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&cur[4 * h + 2 * half + 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
+              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
+              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
+            }
+          }
+          if (e.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          uint4 o[2];
+          __half2* oh2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) oh2[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+          ptx::sts128(my + (uint32_t)((4 * h + 2 * half) << 4), o[0]);
+          ptx::sts128(my + (uint32_t)((4 * h + 2 * half + 1) << 4), o[1]);
+        }
+      }
+    }
+    __syncwarp();
+    {   // coalesced store of the warp's 32 x nc tile
+      const uint32_t inv = (65536u + (uint32_t)cpr - 1u) / (uint32_t)cpr;
+      for (int i = 0; i < cpr; ++i) {
+        const uint32_t idx = (uint32_t)(i * 32 + lane);
+        const uint32_t r = (idx * inv) >> 16;
+        const uint32_t k = idx - r * (uint32_t)cpr;
+        const unsigned long long roff = __shfl_sync(0xffffffffu, off, (int)r);
+        if ((vmask >> r) & 1u) {
+          const uint4 v = ptx::lds128(e.stage + r * (uint32_t)kCoalPitch + (k << 4));
+          *reinterpret_cast<uint4*>(e.out + roff + (size_t)(c64 + (int)(k << 3))) = v;
+        }
+      }
+    }
+    __syncwarp();                              // staging tile free again
+    if (has_res && c64 + 64 < e.ncols) epi_coal_fetch_residual(e, c64 + 64, lane);
+  }
+}
+
 }  // namespace hrnet

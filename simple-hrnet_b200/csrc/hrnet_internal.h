@@ -49,9 +49,14 @@ struct ConvTcCfg {
   int smem_bytes = 0;
   int tmem_cols = 0;
   int cs = 1;        // 2: CTA-pair mode (cta_group::2)
-  int epi_bytes = 0; // shared memory of the TMA-store epilogue staging tiles (0: direct stores)
+  int epi = 0;       // epilogue: 0 direct stores, 1 staged TMA stores, 2 warp-staged coalesced stores
+  int epi_bytes = 0; // shared memory of the epilogue staging tiles
 };
 
+
+// warp-staged coalesced epilogue (epilogue.cuh): staging tile of one epilogue warp
+constexpr int kCoalPitch = 144;                       // bytes per staged row (64 fp16 channels + 16 B pad)
+constexpr int kCoalWarpBytes = 32 * kCoalPitch;       // 4608 B per epilogue warp
 
 // device-side parameter block for the tcgen05 implicit-GEMM conv
 struct ConvTcParams {
@@ -66,7 +71,7 @@ struct ConvTcParams {
   int relu, out_f32;
   int tmem_cols;
   int a_blk_bytes, b_blk_bytes;
-  int epi_tma, epi_bytes;   // staged epilogue with TMA stores (epilogue.cuh): staging tiles follow the pipeline stages
+  int epi_tma, epi_bytes;   // epilogue (epilogue.cuh): 0 direct, 1 staged TMA stores, 2 warp-staged coalesced; staging follows the stages
   const float* scale;
   const float* bias;
   const __half* residual;
@@ -89,8 +94,10 @@ struct ConvPatchParams {
   int b_stream;                // 1: the 9-tap weight block of a chunk travels with its patch slot (weights too big to stay)
   int a_slot_bytes;            // bytes of the patch part of a slot (weights of a streamed chunk follow it)
   int slot_bytes, nslots;      // ring of patch slots (one channel chunk of one tile each)
+  int nacc, nacc_log2;         // TMEM accumulator buffers (2 or 4)
+  int cs;                      // 2: CTA-pair mode (cta_group::2), each CTA keeps Cout / 2 weight rows; else 1
   int relu, out_f32, tmem_cols;
-  int epi_tma, epi_bytes;      // staged epilogue with TMA stores: staging tiles follow the patch slots
+  int epi_tma, epi_bytes;      // epilogue: 0 direct, 1 staged TMA stores, 2 warp-staged coalesced; staging follows the patch slots
   const float* scale;
   const float* bias;
   const __half* residual;
@@ -186,5 +193,6 @@ int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms);
 cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, const CUtensorMap* tmOR,
                               const ConvPatchParams& p, int smem_bytes, int grid, cudaStream_t st);
 cudaError_t conv_patch_set_attributes(int max_smem);
+int conv_patch_grid(const ConvPatchParams& p, int num_sms);
 
 }  // namespace hrnet

@@ -162,7 +162,11 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
     nt = op.cout / d;
   }
   c.n_tile = nt;
-  c.bps = 1;
+  // k-blocks per pipeline stage: every stage costs the issuing threads a barrier wait, an expect_tx and a commit
+  // (~300 clk, conv_igemm_body.cuh); with narrow tiles that is more than the stage's MMAs, so two k-blocks share a
+  // stage when four such stages still fit (HRNET_B200_BPS overrides).
+  c.bps = (nt <= 64 && op.k * op.k * ((op.cin + 63) / 64) >= 4) ? 2 : 1;
+  if (const char* e = getenv("HRNET_B200_BPS")) { const int v = atoi(e); if (v == 1 || v == 2) c.bps = v; }
   // CTA-pair mode (tcgen05 cta_group::2): each CTA stages half of the weight tile.  Measured on B200 it makes the
   // large-N kernels faster in isolation (stage-4 C=192/384 convs 46 -> 42.7 us, 2.3x fewer clk per GEMM row) but the
   // whole W48/64 forward slower (9.76 vs 9.46 ms: pair clusters co-schedule worse with the other branches' kernels,
@@ -179,8 +183,8 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   const int a_blk = (int)align_up((size_t)128 * c.kc * 2, 1024);
   const int b_blk = (int)align_up((size_t)(nt / c.cs) * c.kc * 2, 1024);
   const int stage = c.bps * (a_blk + b_blk);
-  const int fixed = 1024 + 2 * op.cout * 4 + 256;
-  const int budget = 200 * 1024;
+  const int fixed = 1024 + 2 * op.cout * 4 + 1024;   // alignment slack, BN scale / bias, barriers + k-block table
+  const int budget = 208 * 1024;
   const int nkb = op.k * op.k * ((op.cin + c.kc - 1) / c.kc);
   const int kstages = (nkb + c.bps - 1) / c.bps;
   c.stages = std::max(2, std::min({8, (budget - fixed) / stage, std::max(2, kstages * 2)}));
@@ -205,6 +209,16 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
   if ((double)(H * W) / (double)(tw * kPatchTW * th * kPatchTH) < 0.85) return false;
   ConvPatchParams p{};
   p.H = H; p.W = W; p.Cin = op.cin; p.Cout = op.cout; p.tiles_w = tw; p.tiles_h = th;
+  // CTA-pair mode (conv3x3_patch_body.cuh): HRNET_B200_PATCH_PAIR=<min Cout> enables it for convs with at least that
+  // many (and at most HRNET_B200_PATCH_PAIR_MAX) output channels; each CTA then keeps Cout / 2 weight rows.
+  p.cs = 1;
+  if (!(flags & HRNET_FLAG_GROUP)) {
+    int pair_min = 0, pair_max = 1 << 30;
+    if (const char* e = getenv("HRNET_B200_PATCH_PAIR")) pair_min = atoi(e);
+    if (const char* m = getenv("HRNET_B200_PATCH_PAIR_MAX")) pair_max = atoi(m);
+    if (pair_min > 0 && op.cout >= pair_min && op.cout <= pair_max && op.cout % 16 == 0) p.cs = 2;
+  }
+  const int b_rows = op.cout / p.cs;
   int c = 0, n = 0;
   size_t boff = 0;
   while (c < op.cin) {
@@ -212,7 +226,7 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
     if (n == 4) return false;
     const int bkc = real > 32 ? 64 : (real > 16 ? 32 : 16);
     p.c0[n] = c; p.kreal[n] = real; p.bkc[n] = bkc; p.mapi[n] = bkc == 64 ? 0 : (bkc == 32 ? 1 : 2);
-    p.bblk[n] = (int)align_up((size_t)op.cout * bkc * 2, 1024);
+    p.bblk[n] = (int)align_up((size_t)b_rows * bkc * 2, 1024);
     p.boff[n] = (int)boff;
     boff += (size_t)9 * p.bblk[n];
     c += 64; ++n;
@@ -224,6 +238,7 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
   p.b_bytes = (int)boff;
   p.slot_bytes = p.a_slot_bytes;
   int avail = kMaxDynSmem - fixed - p.b_bytes;
+  if (avail < 2 * p.slot_bytes && p.cs == 2) return false;   // (not reached for the HRNet shapes)
   if (avail < 2 * p.slot_bytes) {
     // weights too big to stay resident: stream each chunk's 9-tap block with its patch
     int maxblk = 0;
@@ -235,8 +250,12 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
     if (avail < 2 * p.slot_bytes) return false;
   }
   p.nslots = std::min(8, avail / p.slot_bytes) & ~1;   // two producer warps alternate slots
+  // accumulator buffers: 4 when they fit the 512 TMEM columns (HRNET_B200_PATCH_NACC=2 forces double buffering)
+  p.nacc = 4 * op.cout <= 512 ? 4 : 2;
+  if (const char* e = getenv("HRNET_B200_PATCH_NACC")) { if (atoi(e) == 2) p.nacc = 2; }
+  p.nacc_log2 = p.nacc == 4 ? 2 : 1;
   int cols = 32;
-  while (cols < 2 * op.cout) cols *= 2;
+  while (cols < p.nacc * op.cout) cols *= 2;
   p.tmem_cols = cols;
   p.relu = op.relu;
   op.pp = p;
@@ -245,41 +264,50 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
   return true;
 }
 
-// Staged epilogue with TMA stores (epilogue.cuh): fp16 outputs only, not for the sub-pixel phases of a transposed
-// conv.  HRNET_B200_EPI_TMA = 0: never, 1: tiles at least 128 channels wide (where the thread-per-row stores
-// bound the kernel), 2 (default): every eligible conv (W48/64 forward 10.19 / 9.87 / 9.25 ms for 0 / 1 / 2).  The staging tiles are carved out of the pipeline's shared memory.
-int epi_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("HRNET_B200_EPI_TMA");
-    v = e ? atoi(e) : 3;
-  }
-  return v;
+// Epilogue selection (epilogue.cuh), fp16 outputs only and not for the sub-pixel phases of a transposed conv:
+//   1 staged TMA stores        : tiles at least 256 channels wide (layer1 conv3 / downsample: 136 -> 104 us)
+//   2 warp-staged coalesced    : everything else, when the 36 KB of staging fit next to the pipeline
+//   0 direct row-per-thread    : fp32 outputs, sub-pixel phases, or no shared memory left (C = 96 halo-patch conv)
+// HRNET_B200_EPI = auto (default) | direct | tma (TMA wherever eligible) | coal (coalesced wherever it fits); read at
+// plan time.  The staging tiles are carved out of the pipeline's shared memory.
+int epi_policy() {
+  const char* e = getenv("HRNET_B200_EPI");
+  if (!e || !strcmp(e, "auto")) return 0;
+  if (!strcmp(e, "direct")) return 1;
+  if (!strcmp(e, "tma")) return 2;
+  if (!strcmp(e, "coal")) return 3;
+  return 0;
 }
 void choose_epi(Op& op, bool out_f32, bool sub, bool has_res) {
-  const int mode = epi_mode();
-  if (!op.use_tc || mode == 0 || out_f32 || sub) return;
-  const int reserve = has_res ? 65536 : 32768;   // per warpgroup: one output tile (+ one residual tile) of 128 x 64 fp16
-  if (op.use_patch) {
-    ConvPatchParams& p = op.pp;
-    if ((mode == 1 && p.Cout < 128) || (mode == 3 && p.Cout < 256)) return;
-    const int fixed = 1024 + 2 * op.cout * 4 + 512;
-    const int avail = kMaxDynSmem - fixed - p.b_bytes - reserve;
-    const int ns = std::min(8, avail / p.slot_bytes) & ~1;
-    if (ns < 2) return;
-    p.nslots = std::min(p.nslots, ns);
-    p.epi_tma = 1; p.epi_bytes = reserve;
-    op.patch_smem = fixed + p.b_bytes + p.nslots * p.slot_bytes + reserve;
-  } else {
-    ConvTcCfg& c = op.tc;
-    if ((mode == 1 && c.n_tile < 128) || (mode == 3 && c.n_tile < 256)) return;
-    if (op.cout / c.n_tile > 1 && c.n_tile % 64) return;   // a partial last 64-channel chunk would spill into the next N-tile
-    const int fixed = 1024 + 2 * op.cout * 4 + 256;
-    const int stage = (c.smem_bytes - fixed) / c.stages;
-    const int ns = std::min(c.stages, ((kMaxDynSmem - fixed - reserve) / stage) & ~1);
-    if (ns < std::min(c.stages, 4)) return;
-    c.stages = ns; c.epi_bytes = reserve;
-    c.smem_bytes = fixed + ns * stage + reserve;
+  const int policy = epi_policy();
+  if (!op.use_tc || policy == 1 || out_f32 || sub) return;
+  const int width = op.use_patch ? op.pp.Cout : op.tc.n_tile;
+  const bool want_tma = policy == 2 || (policy == 0 && width >= 256);
+  for (int kind = want_tma ? 1 : 2; kind <= 2; ++kind) {   // TMA first if wanted, else / then coalesced
+    if (kind == 2 && policy == 2) break;
+    const int reserve = kind == 1 ? (has_res ? 65536 : 32768)   // per warpgroup: output (+ residual) tile of 128 x 64 fp16
+                                  : 8 * kCoalWarpBytes;        // per epilogue warp: 32 rows x 144 B
+    if (op.use_patch) {
+      ConvPatchParams& p = op.pp;
+      const int fixed = 1024 + 2 * op.cout * 4 + 512;
+      const int avail = kMaxDynSmem - fixed - p.b_bytes - reserve;
+      const int ns = std::min(8, avail / p.slot_bytes) & ~1;
+      if (ns < 2 || (ns < 4 && p.nchunks > 1 && !p.b_stream)) continue;   // keep two tiles in flight
+      p.nslots = std::min(p.nslots, ns);
+      p.epi_tma = kind; p.epi_bytes = reserve;
+      op.patch_smem = fixed + p.b_bytes + p.nslots * p.slot_bytes + reserve;
+      return;
+    } else {
+      ConvTcCfg& c = op.tc;
+      if (kind == 1 && op.cout / c.n_tile > 1 && c.n_tile % 64) continue;   // a partial last 64-channel chunk would spill into the next N-tile
+      const int fixed = 1024 + 2 * op.cout * 4 + 1024;   // alignment slack, BN scale / bias, barriers + k-block table
+      const int stage = (c.smem_bytes - fixed) / c.stages;
+      const int ns = std::min(c.stages, ((kMaxDynSmem - fixed - reserve) / stage) & ~1);
+      if (ns < std::min(c.stages, 4)) continue;
+      c.stages = ns; c.epi = kind; c.epi_bytes = reserve;
+      c.smem_bytes = fixed + ns * stage + reserve;
+      return;
+    }
   }
 }
 
@@ -708,11 +736,11 @@ int encode_epi_maps(Op& op, const void* out, const void* residual, int N, int OH
   const void* res = residual ? residual : out;
   int rc;
   if (op.use_patch) {
-    if (!op.pp.epi_tma) return 0;
+    if (op.pp.epi_tma != 1) return 0;
     rc = encode_out4d(&op.tmOR[0], out, N, OH, OW, op.cout);
     if (!rc) rc = encode_out4d(&op.tmOR[1], res, N, OH, OW, op.cout);
   } else {
-    if (!op.tc.epi_bytes) return 0;
+    if (op.tc.epi != 1) return 0;
     rc = encode_out2d(&op.tmOR[0], out, (size_t)N * OH * OW, op.cout);
     if (!rc) rc = encode_out2d(&op.tmOR[1], res, (size_t)N * OH * OW, op.cout);
   }
@@ -731,7 +759,7 @@ int encode_patch_maps(Op& op, const void* act, const void* w, int N) {
   int first = -1;
   for (int i = 0; i < 3; ++i) {
     if (!have[i]) continue;
-    rc = encode_weights(&op.tmPB[i], w, p.Cout, 9 * p.Cin, kcs[i], p.Cout);
+    rc = encode_weights(&op.tmPB[i], w, p.Cout, 9 * p.Cin, kcs[i], p.Cout / p.cs);
     if (rc) return rc;
     if (first < 0) first = i;
   }
@@ -843,7 +871,8 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
     o << "],\"tc\":{\"kc\":" << op.tc.kc << ",\"bps\":" << op.tc.bps << ",\"n_tile\":" << op.tc.n_tile
       << ",\"cs\":" << op.tc.cs << ",\"stages\":" << op.tc.stages << ",\"smem\":" << op.tc.smem_bytes << ",\"tmem_cols\":" << op.tc.tmem_cols
-      << ",\"epi\":" << (op.use_patch ? op.pp.epi_bytes : op.tc.epi_bytes) << "}}";
+      << ",\"epi\":" << (op.use_patch ? op.pp.epi_tma : op.tc.epi)
+      << ",\"patch_cs\":" << (op.use_patch ? op.pp.cs : 0) << ",\"patch_slots\":" << (op.use_patch ? op.pp.nslots : 0) << "}}";
   }
   o << "]}";
   const std::string s = o.str();
@@ -968,7 +997,7 @@ ConvTcParams fill_tc_params(HrnetPlan* P, const Op& op, int n) {
   p.bias = (const float*)(P->wbase + pi.bias_offset);
   p.residual = op.res >= 0 ? (const __half*)(P->abase + P->tensors[op.res].offset) : nullptr;
   p.out = P->abase + to.offset;
-  p.epi_tma = op.tc.epi_bytes ? 1 : 0; p.epi_bytes = op.tc.epi_bytes;
+  p.epi_tma = op.tc.epi; p.epi_bytes = op.tc.epi_bytes;
   return p;
 }
 
@@ -1090,7 +1119,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.out = tptr(op.out);
         if (p.total_tiles == 0) return 0;
         const int cap = std::max(1, (int)std::lround(op.sm_frac * P->num_sms));
-        CK(launch_conv_patch(op.tmPA, op.tmPB, op.tmOR, p, op.patch_smem, std::min(p.total_tiles, cap), st));
+        CK(launch_conv_patch(op.tmPA, op.tmPB, op.tmOR, p, op.patch_smem, std::min(std::max(p.cs, cap / p.cs * p.cs), conv_patch_grid(p, P->num_sms)), st));
       } else if (op.use_tc) {
         ConvTcParams p{};
         p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
@@ -1107,7 +1136,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.bias = (const float*)(P->wbase + pi.bias_offset);
         p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
         p.out = tptr(op.out);
-        p.epi_tma = op.tc.epi_bytes ? 1 : 0; p.epi_bytes = op.tc.epi_bytes;
+        p.epi_tma = op.tc.epi; p.epi_bytes = op.tc.epi_bytes;
         const int tiles = p.m_tiles * p.n_tiles;
         if (tiles == 0) return 0;
         const int cap = std::max(p.cs, (int)std::lround(op.sm_frac * P->num_sms) / p.cs * p.cs);
@@ -1423,9 +1452,11 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.N = n; p.total_tiles = n * p.tiles_w * p.tiles_h; p.relu = relu; p.out_f32 = out_f32;
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
     if (p.total_tiles == 0) return HRNET_OK;
+    if (getenv("HRNET_B200_DBG_NOSTORE")) p.H = 0;   // experiments: every output row invalid -> epilogue without global traffic
     if (const char* e = getenv("HRNET_B200_GRID_CAP")) sms = std::max(1, std::min(sms, atoi(e)));   // experiments
-    DbgTimers dt; dt.begin(std::min(p.total_tiles, sms)); p.dbg = dt.dev;
-    CK(launch_conv_patch(op.tmPA, op.tmPB, op.tmOR, p, op.patch_smem, std::min(p.total_tiles, sms), st));
+    const int pgrid = conv_patch_grid(p, sms);
+    DbgTimers dt; dt.begin(pgrid); p.dbg = dt.dev;
+    CK(launch_conv_patch(op.tmPA, op.tmPB, op.tmOR, p, op.patch_smem, pgrid, st));
     dt.end(st, "patch", p.total_tiles);
     return HRNET_OK;
   }
@@ -1456,7 +1487,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
     p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
-    p.epi_tma = op.tc.epi_bytes ? 1 : 0; p.epi_bytes = op.tc.epi_bytes;
+    p.epi_tma = op.tc.epi; p.epi_bytes = op.tc.epi_bytes;
     const int tiles = p.m_tiles * p.n_tiles;
     if (tiles == 0) return HRNET_OK;
     DbgTimers dt; dt.begin(conv_tc_grid(p, op.tc.smem_bytes, sms)); p.dbg = dt.dev;

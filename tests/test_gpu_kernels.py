@@ -90,6 +90,22 @@ def test_conv_tc_pair_mode_matches_cpu(shape, monkeypatch):
     assert err <= G.conv_tolerance(case), f"max abs err {err}"
 
 
+@pytest.mark.parametrize("shape", [(2, 96, 72, 48, 48), (3, 48, 36, 96, 96), (1, 16, 8, 64, 64), (5, 48, 24, 48, 96),
+                                   (1, 32, 16, 128, 128)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("epi", ["direct", "tma", "coal"])
+def test_conv_patch_pair_mode_matches_cpu(shape, epi, monkeypatch):
+    """Halo-patch kernel in CTA-pair mode (opt-in via HRNET_B200_PATCH_PAIR=<min Cout>): M=256 MMAs over two tiles, half of
+    the resident weight rows per CTA, odd tile counts (ghost CTA: (1,16,8) has one tile, (5,48,24) has 45), with the
+    direct, the TMA-store and the warp-staged coalesced epilogue."""
+    monkeypatch.setenv("HRNET_B200_PATCH_PAIR", "16")
+    monkeypatch.setenv("HRNET_B200_EPI", epi)
+    n, h, w, cin, cout = shape
+    case = G.conv_case(n, h, w, cin, cout, 3, 1, relu=True, residual=(cin == cout), out_f32=False, seed=9)
+    out = G.run_conv(case, use_tc=2)
+    err = (out - case["ref"]).abs().max().item()
+    assert err <= G.conv_tolerance(case), f"max abs err {err}"
+
+
 @pytest.mark.parametrize("shape", [(2, 24, 18, 192, 48, 1, 1), (2, 48, 36, 96, 192, 3, 2)], ids=str)
 def test_conv_tc_f32_output_no_relu(shape):
     case = G.conv_case(*shape, relu=False, residual=False, out_f32=True, seed=2)

@@ -8,6 +8,8 @@ d = torch.device("cuda")
 shapes = [(64, 96, 72, 64, 256, 1, 1, 1, 1), (64, 96, 72, 256, 64, 1, 1, 0, 1), (64, 96, 72, 48, 48, 3, 2, 0, 1),
           (64, 96, 72, 48, 96, 3, 2, 0, 1), (64, 48, 36, 96, 48, 1, 1, 0, 1), (64, 192, 144, 64, 64, 3, 2, 0, 1),
           (64, 96, 72, 256, 48, 3, 1, 0, 2)]
+if len(sys.argv) > 1:   # shapes as n,h,w,cin,cout,k,stride,residual,kernel ...
+    shapes = [tuple(int(v) for v in a.split(',')) for a in sys.argv[1:]]
 for (n, h, w, ci, co, k, s, res, kern) in shapes:
     x = (torch.randn(n, h, w, ci, device=d) * 0.5).to(torch.float16)
     wt = (torch.randn(co, k, k, ci, device=d) / (k * k * ci) ** 0.5).to(torch.float16)
