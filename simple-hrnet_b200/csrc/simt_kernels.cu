@@ -188,11 +188,7 @@ cudaError_t launch_maxpool(const __half* in, __half* out, int N, int IH, int IW,
 // ------------------------------------------------------------------------------------------------ fuse sum
 // out[n,h,w,c] = act( sum_j src_j[n, h >> shift_j, w >> shift_j, c] ), fp32 sum in ascending j like hrnet.py:61-66.
 // one thread = 8 channels (16 B fp16 / 32 B fp32 per source)
-__global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseParams p) {
-  const int CV = p.C / 8;
-  const long total = (long)p.N * p.H * p.W * CV;
-  const long i = (long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= total) return;
+__device__ __forceinline__ void fuse_sum_one(const FuseParams& p, long i, int CV) {
   const int cv = (int)(i % CV);
   const long pix = i / CV;
   const int n = (int)(pix / (p.H * p.W));
@@ -237,6 +233,14 @@ __global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseParams p) {
   *reinterpret_cast<uint4*>(p.out + (size_t)pix * p.C + (size_t)cv * 8) = o;
 }
 
+__global__ void __launch_bounds__(256) fuse_sum_kernel(const FuseParams p) {
+  const int CV = p.C / 8;
+  const long total = (long)p.N * p.H * p.W * CV;
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  fuse_sum_one(p, i, CV);   // (two elements per thread measured no faster: 34.9 vs 32.5 us for the 96x72x48 sum)
+}
+
 cudaError_t launch_fuse(const FuseParams& p, cudaStream_t st) {
   const long total = (long)p.N * p.H * p.W * (p.C / 8);
   if (total == 0) return cudaSuccess;
@@ -271,9 +275,13 @@ head_conv1x1_kernel(const __half* __restrict__ in, const float* __restrict__ w, 
     for (int k = 0; k < 4; ++k) { float2 f = __half22float2(hh[k]); x[2 * k] = f.x; x[2 * k + 1] = f.y; }
 #pragma unroll
     for (int j = 0; j < kHeadMaxJ; ++j) {
-      if (j < J) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[j] = fmaf(x[k], shw[j * Cin + c + k], acc[j]);
+      if (j < J) {   // two 16-byte broadcast reads per joint instead of eight scalar ones (the loop was LDS-bound)
+        const float4 w0 = *reinterpret_cast<const float4*>(shw + j * Cin + c);
+        const float4 w1 = *reinterpret_cast<const float4*>(shw + j * Cin + c + 4);
+        float a = acc[j];
+        a = fmaf(x[0], w0.x, a); a = fmaf(x[1], w0.y, a); a = fmaf(x[2], w0.z, a); a = fmaf(x[3], w0.w, a);
+        a = fmaf(x[4], w1.x, a); a = fmaf(x[5], w1.y, a); a = fmaf(x[6], w1.z, a); a = fmaf(x[7], w1.w, a);
+        acc[j] = a;
       }
     }
   }

@@ -9,7 +9,11 @@
 // laid out as two K-major SWIZZLE_128B k-blocks: block 0 = [hi | lo] x [W_hi | W_hi] (K = 64), block 1 = [hi] x [W_lo]
 // (K = 32) -> 6 tcgen05.mma of M=128, N=64, K=16, fp32 accumulate in TMEM.  The operands are written to shared
 // memory by ordinary stores (generic proxy), so a fence.proxy.async precedes the MMAs.
-// One tile per CTA, ~50 KB shared memory and 64 TMEM columns each: 4 CTAs per SM hide the load latency.
+// Persistent CTAs (4 per SM, ~50 KB shared memory and 64 TMEM columns each, so the others' loads hide one's latency):
+// barrier / TMEM setup and the hi / lo split of the weights happen once per CTA, then it loops over its tiles
+// (one tile per CTA cost 176 us at N=64: 13824 CTA prologues; profiles/r01_op_roofline_v9.txt).
+#include <algorithm>
+
 #include "hrnet_internal.h"
 #include "ptx.cuh"
 
@@ -61,53 +65,7 @@ stem_conv3x3s2_tc_kernel(const void* __restrict__ in_any, const float* __restric
 
   const int OH = H / 2, OW = W / 2;
   const long total = (long)N * OH * OW;
-  const long pix = (long)blockIdx.x * 128 + tid;
-  const bool valid = pix < total;
 
-  // ---- A rows: one output pixel per thread
-  {
-    float x[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = 0.f;
-    if (valid) {
-      const int n = (int)(pix / (OH * OW));
-      const int rem = (int)(pix - (long)n * OH * OW);
-      const int oh = rem / OW, ow = rem - oh * OW;
-      const float* ip = in + (size_t)n * 3 * H * W;
-      const uint8_t* ip8 = in8 + (size_t)n * H * W * 3;
-      const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};   // RGB, SimpleHRNet.py:152
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int ih = oh * 2 - 1 + r;
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int iw = ow * 2 - 1 + s;
-          const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-#pragma unroll
-          for (int ci = 0; ci < 3; ++ci) {
-            float v = 0.f;    // zero padding applies to the normalised tensor
-            if (ok) {
-              if constexpr (kU8) {
-                const float u = (float)__ldg(ip8 + ((size_t)ih * W + iw) * 3 + (2 - ci));   // BGR -> RGB
-                v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), mean[ci]), stdv[ci]);
-              } else {
-                v = __ldg(ip + ((size_t)ci * H + ih) * W + iw);
-              }
-            }
-            x[(r * 3 + s) * 3 + ci] = v;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 hi, lo;
-      split_pack8(x + 8 * c, hi, lo);
-      st_chunk(A0, tid, c, hi);
-      st_chunk(A0, tid, 4 + c, lo);
-      st_chunk(A1, tid, c, hi);
-    }
-  }
   // ---- B rows: one output channel per thread (weights [co][r][s][ci] fp32 -> K index (r*3+s)*3+ci)
   if (tid < 64) {
     float x[32];
@@ -122,53 +80,107 @@ stem_conv3x3s2_tc_kernel(const void* __restrict__ in_any, const float* __restric
       st_chunk(B1, tid, c, lo);
     }
   }
-  ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core (async proxy)
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem = *tslot;
-
-  if (warp == 0) {
-    if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::umma_idesc_f16(128, 64);
-      const uint64_t a0 = ptx::umma_desc_kmajor(sbase, 128u, 1024u);
-      const uint64_t a1 = ptx::umma_desc_kmajor(sbase + 16384u, 128u, 1024u);
-      const uint64_t b0 = ptx::umma_desc_kmajor(sbase + 32768u, 128u, 1024u);
-      const uint64_t b1 = ptx::umma_desc_kmajor(sbase + 40960u, 128u, 1024u);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem, a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
-#pragma unroll
-      for (int k = 0; k < 2; ++k) ptx::mma_f16_ss(tmem, a1 + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, 1u);
-      ptx::mma_commit(ptx::smem_u32(bar));
+  uint32_t phase = 0;
+  const long ntiles = (total + 127) / 128;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long pix = tile * 128 + tid;
+    const bool valid = pix < total;
+    // ---- A rows: one output pixel per thread
+    {
+      float x[32];
+  #pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = 0.f;
+      if (valid) {
+        const int n = (int)(pix / (OH * OW));
+        const int rem = (int)(pix - (long)n * OH * OW);
+        const int oh = rem / OW, ow = rem - oh * OW;
+        const float* ip = in + (size_t)n * 3 * H * W;
+        const uint8_t* ip8 = in8 + (size_t)n * H * W * 3;
+        const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};   // RGB, SimpleHRNet.py:152
+  #pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int ih = oh * 2 - 1 + r;
+  #pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int iw = ow * 2 - 1 + s;
+            const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+  #pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+              float v = 0.f;    // zero padding applies to the normalised tensor
+              if (ok) {
+                if constexpr (kU8) {
+                  const float u = (float)__ldg(ip8 + ((size_t)ih * W + iw) * 3 + (2 - ci));   // BGR -> RGB
+                  v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), mean[ci]), stdv[ci]);
+                } else {
+                  v = __ldg(ip + ((size_t)ci * H + ih) * W + iw);
+                }
+              }
+              x[(r * 3 + s) * 3 + ci] = v;
+            }
+          }
+        }
+      }
+  #pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 hi, lo;
+        split_pack8(x + 8 * c, hi, lo);
+        st_chunk(A0, tid, c, hi);
+        st_chunk(A0, tid, 4 + c, lo);
+        st_chunk(A1, tid, c, hi);
+      }
     }
-    __syncwarp();
-  }
-  ptx::mbar_wait(ptx::smem_u32(bar), 0);
-  ptx::tc_fence_after_sync();
-
-  // ---- epilogue: thread = accumulator row = output pixel; 64 channels = 128 contiguous bytes
-  const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
-  uint4 o[8];
-  __half2* oh2 = reinterpret_cast<__half2*>(o);
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint32_t v0[16], v1[16];
-    ptx::tmem_ld16(t_row + (uint32_t)(32 * h), v0);
-    ptx::tmem_ld16(t_row + (uint32_t)(32 * h + 16), v1);
-    ptx::tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = 32 * h + 2 * i;
-      oh2[16 * h + i] = __floats2half2_rn(fmaxf(fmaf(__uint_as_float(v0[2 * i]), s_scale[c], s_bias[c]), 0.f),
-                                         fmaxf(fmaf(__uint_as_float(v0[2 * i + 1]), s_scale[c + 1], s_bias[c + 1]), 0.f));
-      oh2[16 * h + 8 + i] = __floats2half2_rn(fmaxf(fmaf(__uint_as_float(v1[2 * i]), s_scale[c + 16], s_bias[c + 16]), 0.f),
-                                             fmaxf(fmaf(__uint_as_float(v1[2 * i + 1]), s_scale[c + 17], s_bias[c + 17]), 0.f));
+    ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core (async proxy)
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    if (warp == 0) {
+      if (ptx::elect_one()) {
+        const uint32_t idesc = ptx::umma_idesc_f16(128, 64);
+        const uint64_t a0 = ptx::umma_desc_kmajor(sbase, 128u, 1024u);
+        const uint64_t a1 = ptx::umma_desc_kmajor(sbase + 16384u, 128u, 1024u);
+        const uint64_t b0 = ptx::umma_desc_kmajor(sbase + 32768u, 128u, 1024u);
+        const uint64_t b1 = ptx::umma_desc_kmajor(sbase + 40960u, 128u, 1024u);
+  #pragma unroll
+        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem, a0 + (uint64_t)(2 * k), b0 + (uint64_t)(2 * k), idesc, (uint32_t)(k != 0));
+  #pragma unroll
+        for (int k = 0; k < 2; ++k) ptx::mma_f16_ss(tmem, a1 + (uint64_t)(2 * k), b1 + (uint64_t)(2 * k), idesc, 1u);
+        ptx::mma_commit(ptx::smem_u32(bar));
+      }
+      __syncwarp();
     }
-  }
-  if (valid) {
-    uint4* op = reinterpret_cast<uint4*>(out + (size_t)pix * 64);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) op[i] = o[i];
+    ptx::mbar_wait(ptx::smem_u32(bar), phase);
+    phase ^= 1u;
+    ptx::tc_fence_after_sync();
+
+    // ---- epilogue: thread = accumulator row = output pixel; 64 channels = 128 contiguous bytes
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    uint4 o[8];
+    __half2* oh2 = reinterpret_cast<__half2*>(o);
+  #pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t v0[16], v1[16];
+      ptx::tmem_ld16(t_row + (uint32_t)(32 * h), v0);
+      ptx::tmem_ld16(t_row + (uint32_t)(32 * h + 16), v1);
+      ptx::tmem_ld_wait();
+  #pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = 32 * h + 2 * i;
+        oh2[16 * h + i] = __floats2half2_rn(fmaxf(fmaf(__uint_as_float(v0[2 * i]), s_scale[c], s_bias[c]), 0.f),
+                                           fmaxf(fmaf(__uint_as_float(v0[2 * i + 1]), s_scale[c + 1], s_bias[c + 1]), 0.f));
+        oh2[16 * h + 8 + i] = __floats2half2_rn(fmaxf(fmaf(__uint_as_float(v1[2 * i]), s_scale[c + 16], s_bias[c + 16]), 0.f),
+                                               fmaxf(fmaf(__uint_as_float(v1[2 * i + 1]), s_scale[c + 17], s_bias[c + 17]), 0.f));
+      }
+    }
+    if (valid) {
+      uint4* op = reinterpret_cast<uint4*>(out + (size_t)pix * 64);
+  #pragma unroll
+      for (int i = 0; i < 8; ++i) op[i] = o[i];
+    }
+    ptx::tc_fence_before_sync();   // this tile's TMEM reads are ordered before the next tile's MMAs by the __syncthreads above
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -188,7 +200,12 @@ static cudaError_t launch_stem_tc_any(const void* in, bool u8, const float* w, c
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  const unsigned grid = (unsigned)((total + 127) / 128);
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return cudaGetLastError();
+  }
+  const unsigned grid = (unsigned)std::min<long>((total + 127) / 128, (long)sms * 4);
   if (u8) stem_conv3x3s2_tc_kernel<true><<<grid, 128, smem, st>>>(in, w, scale, bias, out, N, H, W);
   else stem_conv3x3s2_tc_kernel<false><<<grid, 128, smem, st>>>(in, w, scale, bias, out, N, H, W);
   return cudaGetLastError();
