@@ -298,7 +298,7 @@ def main():
                 else:
                     cls = "stem conv2 + transitions"
             else:
-                cls = {0: "stem conv1 (SIMT)", 2: "exchange-unit sum", 3: "head 1x1", 4: "argmax decode"}[op["kind"]]
+                cls = {0: "stem conv1 (hi/lo-split tcgen05)", 2: "exchange-unit sum", 3: "head 1x1", 4: "argmax decode"}[op["kind"]]
             cls_t[cls] = cls_t.get(cls, 0.0) + us
             cls_f[cls] = cls_f.get(cls, 0.0) + flop
             cls_n[cls] = cls_n.get(cls, 0) + 1
