@@ -117,6 +117,12 @@ int hrnet_forward_u8(HrnetPlan* plan, const uint8_t* images_nhwc_bgr_u8, int n, 
                      int32_t* argmax_idx, const float* boxes, void* stream);
 int hrnet_forward_host_u8(HrnetPlan* plan, const uint8_t* images_nhwc_bgr_u8_host, int n, float* heatmaps_host,
                           float* joints_host, int32_t* argmax_idx_host, const float* boxes_host, void* stream);
+/* Same, but only ENQUEUES the copies and the forward on `stream` and returns: the host buffers must be pinned and stay
+ * untouched until the caller synchronises `stream`.  With two plans bound to the same weight buffer (own workspaces) on
+ * two streams this double-buffers a serving loop: batch i+1 is copied to the device while batch i computes (replaces the
+ * reference's synchronous images.to(device) -> model -> .cpu() sequence, SimpleHRNet.py:282-296). */
+int hrnet_forward_host_u8_async(HrnetPlan* plan, const uint8_t* images_nhwc_bgr_u8_host, int n, float* heatmaps_host,
+                                float* joints_host, int32_t* argmax_idx_host, const float* boxes_host, void* stream);
 
 /* Per-op device time: runs the plan's ops one after the other on `stream` (no graph, no branch concurrency) with a
  * CUDA event pair around every launch; usec_per_op[i] = median over `iters` passes for op i of hrnet_plan_describe.

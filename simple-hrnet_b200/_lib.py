@@ -44,6 +44,7 @@ SYMBOLS = {
     "hrnet_forward_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hrnet_forward_u8": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hrnet_forward_host_u8": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hrnet_forward_host_u8_async": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hrnet_plan_launch_count": (_i, [_vp]),
     "hrnet_profile_ops": (_i, [_vp, _vp, _i, ctypes.POINTER(ctypes.c_float), _i, _vp]),
     "hrnet_conv_bn_act": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -1281,8 +1281,8 @@ int hrnet_forward_u8(HrnetPlan* P, const uint8_t* images_nhwc_bgr, int n, float*
   return rc;
 }
 
-int hrnet_forward_host_u8(HrnetPlan* P, const uint8_t* images_h, int n, float* heatmaps_h, float* joints_h,
-                          int32_t* idx_h, const float* boxes_h, void* stream) {
+static int forward_host_u8_impl(HrnetPlan* P, const uint8_t* images_h, int n, float* heatmaps_h, float* joints_h,
+                                int32_t* idx_h, const float* boxes_h, void* stream, bool sync) {
   if (!P) return fail(HRNET_E_INVALID, "null plan");
   if (!P->bound) return fail(HRNET_E_STATE, "hrnet_plan_bind must be called before hrnet_forward_host_u8");
   if (n < 0 || n > P->desc.max_batch) return fail(HRNET_E_INVALID, "n out of range [0, max_batch]");
@@ -1303,8 +1303,18 @@ int hrnet_forward_host_u8(HrnetPlan* P, const uint8_t* images_h, int n, float* h
   if (heatmaps_h)
     CK(cudaMemcpyAsync(heatmaps_h, P->abase + P->tensors[P->t_heatmaps].offset, (size_t)n * J * P->Hh * P->Wh * 4,
                        cudaMemcpyDeviceToHost, s0));
-  CK(cudaStreamSynchronize(s0));
+  if (sync) CK(cudaStreamSynchronize(s0));
   return HRNET_OK;
+}
+
+int hrnet_forward_host_u8(HrnetPlan* P, const uint8_t* images_h, int n, float* heatmaps_h, float* joints_h,
+                          int32_t* idx_h, const float* boxes_h, void* stream) {
+  return forward_host_u8_impl(P, images_h, n, heatmaps_h, joints_h, idx_h, boxes_h, stream, true);
+}
+
+int hrnet_forward_host_u8_async(HrnetPlan* P, const uint8_t* images_h, int n, float* heatmaps_h, float* joints_h,
+                                int32_t* idx_h, const float* boxes_h, void* stream) {
+  return forward_host_u8_impl(P, images_h, n, heatmaps_h, joints_h, idx_h, boxes_h, stream, false);
 }
 
 int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, int iters, void* stream) {

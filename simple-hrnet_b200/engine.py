@@ -102,6 +102,7 @@ class Plan:
         self.c, self.J = int(c), int(nof_joints)
         self.H, self.W = int(resolution[0]), int(resolution[1])
         self.max_batch = int(max_batch)
+        self.flags = int(flags)
         self._plan = ctypes.c_void_p()
         desc = HrnetDesc(self.arch, self.c, self.J, self.H, self.W, self.max_batch, int(flags))
         check(self.lib.hrnet_plan_create(ctypes.byref(desc), ctypes.byref(self._plan)), self.lib)
@@ -163,6 +164,20 @@ class B200Engine(Plan):
             check(self.lib.hrnet_plan_bind(self._plan, self._weights.data_ptr(), self.weight_bytes,
                                            self._workspace.data_ptr(), self.act_bytes), self.lib)
         return self
+
+    def clone_shared(self):
+        """A second engine of the same plan bound to the SAME device weights with its own workspace (for double
+        buffering: `HostPipeline`)."""
+        if self._weights is None:
+            raise HrnetError("load_state_dict must be called before clone_shared")
+        other = B200Engine("hrnet" if self.arch == _lib.ARCH_HRNET else "poseresnet", self.c, self.J, (self.H, self.W),
+                           self.max_batch, self.device, flags=self.flags)
+        with torch.cuda.device(self.device):
+            other._weights = self._weights
+            other._workspace = torch.zeros(other.act_bytes, dtype=torch.uint8, device=self.device)
+            check(other.lib.hrnet_plan_bind(other._plan, other._weights.data_ptr(), other.weight_bytes,
+                                            other._workspace.data_ptr(), other.act_bytes), other.lib)
+        return other
 
     # -- execution --------------------------------------------------------------------------
     def _check_input(self, images):
@@ -283,3 +298,81 @@ class B200Engine(Plan):
 
     def to(self, *_a, **_k):
         return self
+
+
+class HostPipeline:
+    """Double-buffered end-to-end runner for a stream of uint8 crop batches held in HOST memory.
+
+    The reference moves a batch to the device, runs the model and copies the result back one after the other
+    (SimpleHRNet.py:282-296).  Here `depth` engines share one set of device weights; batch i+1 is copied to the device
+    on its own stream while batch i computes, and the joints of batch i come back while batch i+1 computes.
+
+        pipe = HostPipeline(engine)                  # engine: a loaded B200Engine
+        for joints in pipe.run(batches):             # batches: iterable of uint8 [n,H,W,3] BGR arrays (numpy / torch, CPU)
+            ...                                       # joints: numpy [n,J,3] (y, x, confidence), in submission order
+
+    Inputs are staged through the pipeline's own pinned buffers unless they already are pinned torch tensors.
+    """
+
+    def __init__(self, engine, depth=2):
+        self.engines = [engine] + [engine.clone_shared() for _ in range(depth - 1)]
+        self.device = engine.device
+        e = engine
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(self.device) for _ in self.engines]
+        self._in = [torch.empty(e.max_batch, e.H, e.W, 3, dtype=torch.uint8).pin_memory() for _ in self.engines]
+        self._joints = [torch.empty(e.max_batch, e.J, 3, dtype=torch.float32).pin_memory() for _ in self.engines]
+        self._idx = [torch.empty(e.max_batch, e.J, dtype=torch.int32).pin_memory() for _ in self.engines]
+        self._boxes = [torch.empty(e.max_batch, 4, dtype=torch.float32).pin_memory() for _ in self.engines]
+        self._pending = [None] * len(self.engines)   # batch size in flight per slot
+        self._next = 0
+
+    def submit(self, images_u8, boxes=None):
+        """Enqueue one batch; returns the slot index.  Blocks only if that slot's previous batch is still in flight
+        and has not been collected (collect it first with `collect`)."""
+        slot = self._next
+        if self._pending[slot] is not None:
+            raise HrnetError("HostPipeline slot still holds an uncollected batch: call collect() first")
+        eng = self.engines[slot]
+        x = torch.as_tensor(images_u8)
+        if x.dtype != torch.uint8 or x.dim() != 4 or tuple(x.shape[1:]) != (eng.H, eng.W, 3):
+            raise ValueError(f"expected uint8 [n,{eng.H},{eng.W},3], got {x.dtype} {tuple(x.shape)}")
+        n = x.shape[0]
+        if n > eng.max_batch:
+            raise ValueError(f"batch {n} > max_batch {eng.max_batch}")
+        if not (x.is_pinned() and x.is_contiguous()):
+            self._in[slot][:n].copy_(x)
+            x = self._in[slot][:n]
+        bx = None
+        if boxes is not None:
+            self._boxes[slot][:n].copy_(torch.as_tensor(boxes, dtype=torch.float32))
+            bx = self._boxes[slot]
+        with torch.cuda.device(self.device):
+            check(eng.lib.hrnet_forward_host_u8_async(eng._plan, x.data_ptr(), n, None, self._joints[slot].data_ptr(),
+                                                      self._idx[slot].data_ptr(), bx.data_ptr() if bx is not None else None,
+                                                      self.streams[slot].cuda_stream), eng.lib)
+        self._pending[slot] = (n, x)       # keep the input alive until the copy has run
+        self._next = (slot + 1) % len(self.engines)
+        return slot
+
+    def collect(self, slot):
+        """Wait for the batch in `slot`; returns (joints [n,J,3] numpy copy, argmax idx [n,J] numpy copy)."""
+        if self._pending[slot] is None:
+            raise HrnetError("HostPipeline slot is empty")
+        n, _ = self._pending[slot]
+        self.streams[slot].synchronize()
+        self._pending[slot] = None
+        return self._joints[slot][:n].numpy().copy(), self._idx[slot][:n].numpy().copy()
+
+    def run(self, batches, boxes=None):
+        """Generator over an iterable of batches: yields joints per batch, in order, keeping `depth` batches in flight."""
+        order = []
+        for i, b in enumerate(batches):
+            slot = self._next
+            if self._pending[slot] is not None:
+                order.remove(slot)
+                yield self.collect(slot)[0]
+            self.submit(b, None if boxes is None else boxes[i])
+            order.append(slot)
+        for slot in list(order):
+            yield self.collect(slot)[0]

@@ -138,6 +138,29 @@ def test_forward_host_equals_device_path():
         e.forward_decode(torch.zeros(9, 3, 256, 192).cuda())
 
 
+def test_host_pipeline_matches_blocking_calls():
+    """HostPipeline (hrnet_forward_host_u8_async on two engines sharing one weight buffer) returns, in order, exactly
+    what one blocking hrnet_forward_host_u8 call per batch returns -- ragged batch sizes, pinned and pageable inputs."""
+    from simple_hrnet_b200 import HostPipeline
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=4, bn="random")
+    e = _engine("hrnet", 32, (64, 64), 6, sd)
+    g = torch.Generator().manual_seed(11)
+    sizes = [6, 3, 1, 6, 5, 2, 6]
+    batches = [torch.randint(0, 256, (n, 64, 64, 3), generator=g, dtype=torch.uint8) for n in sizes]
+    batches = [b.pin_memory() if i % 2 else b for i, b in enumerate(batches)]
+    want = [e.forward_host_u8(b.numpy())[0] for b in batches]
+    pipe = HostPipeline(e, depth=2)
+    got = list(pipe.run(batches))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    # a second pass through the same pipeline object, numpy inputs
+    got2 = list(pipe.run([b.numpy() for b in batches[:3]]))
+    assert all(np.array_equal(a, b) for a, b in zip(got2, want[:3]))
+    with pytest.raises(ValueError):
+        pipe.submit(np.zeros((7, 64, 64, 3), dtype=np.uint8))
+
+
 def test_simplehrnet_predict_api(golden_dir):
     """BASELINE config 1 through the public API: same call, same return structure as the reference."""
     g = np.load(os.path.join(golden_dir, "w32_256x192_predict.npz"))
