@@ -38,7 +38,7 @@ struct __align__(8) PatchBars {
   uint64_t a_empty[kPMaxSlots];
   uint64_t tmem_full[4];    // up to 4 accumulator buffers (p.nacc): the MMAs may run that many tiles ahead of the epilogue
   uint64_t tmem_empty[4];
-  uint64_t res_full[2];     // TMA-loaded residual tile of each epilogue warpgroup (staged epilogue)
+  uint64_t wres_full[8];    // TMA-loaded residual tile of each epilogue warp (per-warp TMA epilogue)
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -46,7 +46,7 @@ struct __align__(8) PatchBars {
 struct PatchMaps {
   CUtensorMap a;      // activations, box {64, 10, 18, 1}, SWIZZLE_128B
   CUtensorMap b[3];   // weights, box {64 | 32 | 16, Cout}
-  CUtensorMap o, r;   // staged epilogue: output / residual, box {64, 8, 16, 1}, SWIZZLE_128B
+  CUtensorMap o, r;   // per-warp TMA epilogue: output / residual, box {64, 8, 4, 1}, SWIZZLE_128B
 };
 
 // All MMAs of one channel chunk: tap (r, s) = the same patch viewed from pixel row r * 10 + s (8-row core groups are one
@@ -121,7 +121,7 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128u * (uint32_t)cs);   // pair: both CTAs' epilogues
     }
-    for (int i = 0; i < 2; ++i) ptx::mbar_init(ptx::smem_u32(&bars->res_full[i]), 1);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(ptx::smem_u32(&bars->wres_full[i]), 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -283,7 +283,6 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
     const int dh = row >> 3, dw = row & 7;
     ptx::pdl_wait();                      // residual reads / output writes need the previous kernel
     long long dbg_wacc = 0, dbg_work = 0, dbg_t0 = p.dbg ? clock64() : 0;
-    const bool leader = (q == 0) && (lane == 0);
     uint32_t res_phase = 0;
     int it = 0;
     for (int pi = cluster_id; pi < total_pairs; pi += num_clusters, ++it) {
@@ -298,20 +297,23 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
       const int th = rem / p.tiles_w;
       const int tw = rem - th * p.tiles_w;
       if constexpr (kEpi == 1) {
-        EpiTma e;
-        e.tm_out = &maps.o; e.tm_res = &maps.r; e.dims4 = 1; e.c_row0 = 0;
-        e.c_w0 = tw * kPatchTW; e.c_h0 = th * kPatchTH; e.c_img = img;
-        e.ch0 = 0; e.ncols = p.Cout; e.has_res = p.residual != nullptr; e.relu = p.relu; e.store = !ghost;
+        EpiWarpTma e;
+        e.tm_out = &maps.o; e.tm_res = &maps.r;
+        e.c_w0 = tw * kPatchTW; e.c_h0 = th * kPatchTH + 4 * q; e.c_img = img;   // this warp's 32 rows = 4 tile rows
+        e.ncols = p.Cout; e.has_res = p.residual != nullptr; e.relu = p.relu; e.store = !ghost;
         e.s_scale = s_scale; e.s_bias = s_bias;
-        e.stage_out = epi_base + (uint32_t)g * (uint32_t)(p.epi_bytes >> 1);
-        e.stage_res = e.stage_out + 16384u;
-        e.res_bar = ptx::smem_u32(&bars->res_full[g]); e.bar_id = 1 + g;
-        if (e.has_res && leader) epi_tma_issue_residual(e, 0);   // in flight while the MMAs of this tile finish
+        e.stage_out = epi_base + (uint32_t)(warp - 4) * (uint32_t)(p.epi_bytes >> 3);
+        e.stage_res = e.stage_out + 4096u;
+        e.res_bar = ptx::smem_u32(&bars->wres_full[warp - 4]);
+        if (e.has_res) {   // in flight while the MMAs of this tile finish
+          if (ptx::elect_one()) epi_wtma_issue_residual(e, 0);
+          __syncwarp();
+        }
         long long tq0 = 0; if (p.dbg) tq0 = clock64();
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
         if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
         ptx::tc_fence_after_sync();
-        epi_tma_tile(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout), row, leader, res_phase);
+        epi_wtma_tile(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout), lane, res_phase);
         if (p.dbg) dbg_work += clock64() - tq0;
         ptx::tc_fence_before_sync();
         if (!kPair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
@@ -354,7 +356,10 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
       else if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::smem_u32(&bars->tmem_empty[acc]), 0);
       }
     }
-    if (kEpi == 1 && leader) ptx::tma_store_wait_all();   // shared memory must outlive the bulk stores
+    if constexpr (kEpi == 1) {   // shared memory must outlive the bulk stores (same elected lane that committed them)
+      if (ptx::elect_one()) ptx::tma_store_wait_all();
+      __syncwarp();
+    }
     if (p.dbg && threadIdx.x == 128) {
       p.dbg[blockIdx.x * 32 + 8] = dbg_wacc; p.dbg[blockIdx.x * 32 + 9] = dbg_work;
       p.dbg[blockIdx.x * 32 + 10] = clock64() - dbg_t0;

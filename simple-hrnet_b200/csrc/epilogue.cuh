@@ -220,6 +220,110 @@ __device__ __forceinline__ void epi_tma_tile(const EpiTma& e, uint32_t t_row, in
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Per-warp TMA epilogue of the halo-patch kernel (fp16 output).  Same idea as above at warp granularity: every epilogue
+// warp owns a 4 KB output and a 4 KB residual tile ([32 rows][64 channels], SWIZZLE_128B) and its own mbarrier, its 32
+// accumulator rows are 4 rows x 8 pixels of the 8 x 16 output tile = one TMA box {64, 8, 4, 1}.  Only __syncwarp() and
+// one elected lane's TMA instructions are needed -- no 128-thread barriers -- and the load/store unit sees 12 shared-
+// memory accesses per thread instead of 12 scattered global ones (the thread-per-row stores cost ~1000 clk per tile,
+// the residual loads ~500: more than a CTA pair's MMAs for the tile, profiles/r01_exp_patch_pair_nostore.log).
+// elect.sync picks the same lane for the same mask every time, so the lane that commits a bulk group also waits on it.
+struct EpiWarpTma {
+  const void* tm_out;        // 4-D {C, W, H, N}, box {64, 8, 4, 1}
+  const void* tm_res;
+  int c_w0, c_h0, c_img;     // tile origin of THIS warp's 4 rows
+  int ncols, has_res, relu;
+  bool store;                // false for ghost tiles (CTA-pair mode)
+  const float* s_scale;
+  const float* s_bias;
+  uint32_t stage_out, stage_res;   // 1024 B aligned shared-memory addresses of this warp's tiles
+  uint32_t res_bar;
+};
+
+__device__ __forceinline__ void epi_wtma_issue_residual(const EpiWarpTma& e, int c64) {   // call from one elected lane
+  ptx::mbar_expect_tx(e.res_bar, 32u * 128u);
+  ptx::tma_load_4d(e.stage_res, e.tm_res, e.res_bar, c64, e.c_w0, e.c_h0, e.c_img);
+}
+
+// The residual of chunk 0 must have been requested before the wait on the accumulator barrier.
+__device__ __forceinline__ void epi_wtma_tile(const EpiWarpTma& e, uint32_t t_row, int lane, uint32_t& res_phase) {
+  const uint32_t my_out = e.stage_out + (uint32_t)lane * 128u;
+  const uint32_t my_res = e.stage_res + (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  for (int c64 = 0; c64 < e.ncols; c64 += 64) {
+    const int nc = min(64, e.ncols - c64);     // warp-uniform
+    uint4 cur[8];
+    if (e.has_res) {
+      ptx::mbar_wait(e.res_bar, res_phase);
+      res_phase ^= 1u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (8 * k < nc) cur[k] = ptx::lds128(my_res + (((uint32_t)k ^ sw) << 4));
+    }
+    if (ptx::elect_one()) ptx::tma_store_wait_read();   // the previous store no longer reads stage_out
+    __syncwarp();                                        // ... and every lane has read its residual row
+    if (e.has_res && c64 + 64 < e.ncols) {
+      if (ptx::elect_one()) epi_wtma_issue_residual(e, c64 + 64);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c64 + 32 * h;
+      if (32 * h < nc) {                         // warp-uniform
+        uint32_t v0[16], v1[16];
+        const bool two = 32 * h + 16 < nc;
+        ptx::tmem_ld16(t_row + (uint32_t)c, v0);
+        if (two) ptx::tmem_ld16(t_row + (uint32_t)(c + 16), v1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && !two) break;
+          const uint32_t* v = half ? v1 : v0;
+          const int cc = c + 16 * half;
+          const float4* sc = reinterpret_cast<const float4*>(e.s_scale + cc);
+          const float4* bi = reinterpret_cast<const float4*>(e.s_bias + cc);
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 s4 = sc[i], b4 = bi[i];
+            y[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), s4.x, b4.x);
+            y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), s4.y, b4.y);
+            y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), s4.z, b4.z);
+            y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), s4.w, b4.w);
+          }
+          if (e.has_res) {
+            const __half2* h0 = reinterpret_cast<const __half2*>(&cur[4 * h + 2 * half]);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&cur[4 * h + 2 * half + 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
+              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
+              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
+            }
+          }
+          if (e.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+          }
+          uint4 o[2];
+          __half2* oh2 = reinterpret_cast<__half2*>(o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) oh2[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+          ptx::sts128(my_out + ((((uint32_t)(4 * h + 2 * half)) ^ sw) << 4), o[0]);
+          ptx::sts128(my_out + ((((uint32_t)(4 * h + 2 * half + 1)) ^ sw) << 4), o[1]);
+        }
+      }
+    }
+    ptx::fence_proxy_async_smem();               // generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (e.store && ptx::elect_one()) {
+      ptx::tma_store_4d(e.tm_out, e.stage_out, c64, e.c_w0, e.c_h0, e.c_img);
+      ptx::tma_store_commit();
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Warp-staged coalesced epilogue (fp16 output, no sub-pixel remap).
 //
 // With one thread per output row every 16-byte global access of a warp touches 32 different cache lines; measured on

@@ -276,17 +276,22 @@ int epi_policy() {
   if (!strcmp(e, "direct")) return 1;
   if (!strcmp(e, "tma")) return 2;
   if (!strcmp(e, "coal")) return 3;
+  if (!strcmp(e, "tma_patch")) return 4;    // experiments: TMA epilogue on every halo-patch conv, auto elsewhere
+  if (!strcmp(e, "tma_igemm")) return 5;    // experiments: TMA epilogue on every im2col conv, auto elsewhere
   return 0;
 }
 void choose_epi(Op& op, bool out_f32, bool sub, bool has_res) {
   const int policy = epi_policy();
   if (!op.use_tc || policy == 1 || out_f32 || sub) return;
   const int width = op.use_patch ? op.pp.Cout : op.tc.n_tile;
-  const bool want_tma = policy == 2 || (policy == 0 && width >= 256);
+  // CTA-pair halo-patch convs need the cheap per-warp TMA epilogue to keep up with the halved MMA time
+  const bool want_tma = policy == 2 || (policy == 4 && op.use_patch) || (policy == 5 && !op.use_patch) || width >= 256 ||
+                        (op.use_patch && op.pp.cs == 2);
   for (int kind = want_tma ? 1 : 2; kind <= 2; ++kind) {   // TMA first if wanted, else / then coalesced
-    if (kind == 2 && policy == 2) break;
-    const int reserve = kind == 1 ? (has_res ? 65536 : 32768)   // per warpgroup: output (+ residual) tile of 128 x 64 fp16
-                                  : 8 * kCoalWarpBytes;        // per epilogue warp: 32 rows x 144 B
+    if (kind == 2 && policy != 3) break;   // the coalesced epilogue is opt-in only
+    // kind 1: im2col kernel: per warpgroup an output (+ residual) tile of 128 x 64 fp16; halo-patch kernel: per warp
+    //         an output + a residual tile of 32 x 64 fp16;  kind 2: per epilogue warp 32 rows x 144 B
+    const int reserve = kind == 1 ? (op.use_patch ? 8 * 8192 : (has_res ? 65536 : 32768)) : 8 * kCoalWarpBytes;
     if (op.use_patch) {
       ConvPatchParams& p = op.pp;
       const int fixed = 1024 + 2 * op.cout * 4 + 512;
@@ -719,11 +724,11 @@ int encode_out2d(CUtensorMap* tm, const void* ptr, size_t rows, int C) {
   if (r != CUDA_SUCCESS) return fail(HRNET_E_CUDA, "cuTensorMapEncodeTiled(out 2d) failed: " + std::to_string((int)r));
   return 0;
 }
-// ... and for the halo-patch kernel: 4-D {C, W, H, N}, box = one 8 x 16 output tile of 64 channels
+// ... and for the halo-patch kernel: 4-D {C, W, H, N}, box = the 8 x 4 pixels (32 accumulator rows) of one epilogue warp
 int encode_out4d(CUtensorMap* tm, const void* ptr, int N, int H, int W, int C) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)kPatchTW, (cuuint32_t)kPatchTH, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)kPatchTW, (cuuint32_t)(kPatchTH / 4), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
