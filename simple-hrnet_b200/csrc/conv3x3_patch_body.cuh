@@ -170,17 +170,23 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
       __syncwarp();
     }
     ptx::pdl_wait();                      // weights are constants; activations need the previous kernel
-    int L = 0;                            // running slot-load index over all (tile, chunk) of this CTA
-    for (int pi = cluster_id; pi < total_pairs; pi += num_clusters) {
+    // One issuer (p.mma_warps == 1): the two producers alternate the slot loads of every tile over the whole ring.
+    // Two issuers: producer w, issuer w and epilogue warpgroup w form an independent pipeline over the tiles of parity
+    // w with its own half of the slot ring (a barrier is then only ever waited on by one issuer, in consecutive phases).
+    const int nw = p.mma_warps == 2 ? 2 : 1;
+    const int ring = nw == 2 ? p.nslots / 2 : p.nslots;
+    const int sbase = nw == 2 ? warp * ring : 0;
+    int L = 0;                            // running slot-load index over the (tile, chunk) pairs of this ring
+    for (int pi = cluster_id + (nw == 2 ? warp * num_clusters : 0); pi < total_pairs; pi += nw * num_clusters) {
       const int tile = min(pi * cs + (int)crank, p.total_tiles - 1);   // a ghost CTA redoes the last tile
       const int img = tile / tiles_per_img;
       const int rem = tile - img * tiles_per_img;
       const int th = rem / p.tiles_w;
       const int tw = rem - th * p.tiles_w;
       for (int j = 0; j < p.nchunks; ++j, ++L) {
-        if ((L & 1) != warp) continue;
-        const int slot = L % p.nslots;
-        const uint32_t phase = (uint32_t)((L / p.nslots) & 1);
+        if (nw == 1 && (L & 1) != warp) continue;
+        const int slot = sbase + L % ring;
+        const uint32_t phase = (uint32_t)((L / ring) & 1);
         long long tq0 = 0; if (p.dbg) tq0 = clock64();
         ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[slot]), phase ^ 1u);
         if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
@@ -212,40 +218,50 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
       p.dbg[blockIdx.x * 32 + 1 + 11 * warp] = dbg_issue;
       p.dbg[blockIdx.x * 32 + 2 + 11 * warp] = clock64() - dbg_t0;
     }
-  } else if (warp == 2 && (!kPair || crank == 0)) {
-    // ===================================================================== MMA issuer (pair mode: leader CTA only)
+  } else if ((warp == 2 || (warp == 3 && p.mma_warps == 2)) && (!kPair || crank == 0)) {
+    // ===================================================================== MMA issuer(s) (pair mode: leader CTA only)
     // One elected thread runs the whole loop; the next slot's barrier is probed before the current chunk's MMAs are
     // issued so that its ~150 clk latency overlaps them (conv_igemm_body.cuh, profiles/r01_exp_mma_issue_overhead.log).
+    // p.mma_warps == 2: warps 2 and 3 issue the MMAs of alternate tiles (tile parity = issuer = epilogue warpgroup =
+    // accumulator parity), i.e. two independent MMA -> epilogue pipelines fed by the same producers.  A narrow-N MMA
+    // occupies its issuing thread (~48 clk) longer than the tensor pipe (N = 48: 44 clk), and every tile adds ~800 clk
+    // of serial barrier / commit latency to a single issuer; with two issuers those gaps are filled by the other tile.
+    const int mw = warp - 2;
+    const int nw = p.mma_warps == 2 ? 2 : 1;
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::umma_idesc_f16(kPair ? 256 : 128, p.Cout);
       if (!p.b_stream) ptx::mbar_wait(ptx::smem_u32(&bars->b_full), 0);
-      int slot = 0;
+      // two issuers: this one owns the tiles of parity mw and the slot ring [sbase, sbase + ring) (see the producers)
+      const int ring = nw == 2 ? p.nslots / 2 : p.nslots;
+      const int sbase = nw == 2 ? mw * ring : 0;
+      int slot = 0;                       // ring-local
       uint32_t phase = 0;
       bool ready = false;                 // result of the early probe of a_full[slot]
       bool first_chunk = true;
-      int it = 0;
-      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
-      for (int pi = cluster_id; pi < total_pairs; pi += num_clusters, ++it) {
+      int it = mw;
+      const bool dbg_on = p.dbg != nullptr && mw == 0;
+      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = dbg_on ? clock64() : 0;
+      for (int pi = cluster_id + mw * num_clusters; pi < total_pairs; pi += nw * num_clusters, it += nw) {
         const int acc = it & (p.nacc - 1);
         const uint32_t acc_phase = (uint32_t)((it >> p.nacc_log2) & 1);
-        long long tq0 = 0; if (p.dbg) tq0 = clock64();
+        long long tq0 = 0; if (dbg_on) tq0 = clock64();
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
-        if (p.dbg) dbg_wtm += clock64() - tq0;
+        if (dbg_on) dbg_wtm += clock64() - tq0;
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
         for (int j = 0; j < p.nchunks; ++j) {
-          if (p.dbg) tq0 = clock64();
-          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->a_full[slot]), phase);
-          if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (first_chunk) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
+          if (dbg_on) tq0 = clock64();
+          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->a_full[sbase + slot]), phase);
+          if (dbg_on) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (first_chunk) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
           first_chunk = false;
           ptx::tc_fence_after_sync();
-          const uint32_t a_slot = a_base + (uint32_t)(slot * p.slot_bytes);
+          const uint32_t a_slot = a_base + (uint32_t)((sbase + slot) * p.slot_bytes);
           const uint32_t brow = (uint32_t)p.bkc[j] * 2u;          // weight block row bytes == its swizzle span
           const int nk = p.kreal[j] / 16;
           int nslot = slot + 1;
           uint32_t nphase = phase;
-          if (nslot == p.nslots) { nslot = 0; nphase ^= 1u; }
-          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->a_full[nslot]), nphase);
+          if (nslot == ring) { nslot = 0; nphase ^= 1u; }
+          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->a_full[sbase + nslot]), nphase);
           // 9 taps x NK K16-steps, fully unrolled: every descriptor is base + compile-time offset
           const uint64_t a0 = ptx::umma_desc_kmajor(a_slot, 128u, (uint32_t)kPatchPW * 128u);
           const uint64_t b0 = ptx::umma_desc_kmajor(p.b_stream ? a_slot + (uint32_t)p.a_slot_bytes : b_base + (uint32_t)p.boff[j],
@@ -259,16 +275,16 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
             default: issue_taps<1, kPair>(d_tmem, a0, b0, bstep, idesc, first); break;
           }
           // frees the patch slot (pair: in both CTAs) when the MMAs retire
-          if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[slot]));
-          else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->a_empty[slot]), mc_mask);
+          if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sbase + slot]));
+          else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->a_empty[sbase + slot]), mc_mask);
           slot = nslot; phase = nphase; ready = nready;
-          if (p.dbg) dbg_mma += clock64() - tq0;
+          if (dbg_on) dbg_mma += clock64() - tq0;
         }
         // accumulator ready (pair: for both CTAs' epilogues)
         if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
         else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->tmem_full[acc]), mc_mask);
       }
-      if (p.dbg) {
+      if (dbg_on) {
         p.dbg[blockIdx.x * 32 + 19] = (long long)ptx::globaltimer();
         p.dbg[blockIdx.x * 32 + 4] = dbg_wfull; p.dbg[blockIdx.x * 32 + 5] = dbg_wtm;
         p.dbg[blockIdx.x * 32 + 6] = dbg_mma; p.dbg[blockIdx.x * 32 + 7] = clock64() - dbg_t0;

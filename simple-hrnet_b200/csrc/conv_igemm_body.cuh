@@ -24,7 +24,7 @@
 //   warps 0-1 : TMA producers, alternating pipeline stages (one producer's wait -> expect_tx -> issue chain costs
 //               ~480 + 80/TMA clk per stage, profiles/r01_exp_tma_issue.log; two chains run concurrently)
 //   warp  2   : TMEM alloc + MMA issuer (tcgen05.mma / tcgen05.commit)
-//   warp  3   : idle
+//   warp  3   : k-block table; second MMA issuer (alternate tiles) when p.mma_warps == 2
 //   warps 4-7 / 8-11 : two epilogue warpgroups, alternating tiles: tcgen05.ld -> BN scale/bias (fp32) -> +residual
 //               -> ReLU -> fp16/fp32 NHWC store
 // All role loops are warp-uniform with one elected lane issuing (ptx::elect_one).
@@ -161,11 +161,18 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
     if (ptx::elect_one()) {
       long long dbg_wait = 0, dbg_issue = 0, dbg_t0 = p.dbg ? clock64() : 0;
       const int b_rows = p.n_tile / cs;   // pair: this CTA stages only its half of the weight tile
-      int L = 0;                            // running stage-load index over all tiles of this CTA
-      int stage = warp;                     // stage / phase of the next load of THIS producer (advances by 2; stages is even)
+      // One issuer (p.mma_warps == 1): the two producers alternate the stage loads of every tile over the whole ring.
+      // Two issuers: producer w, issuer w and epilogue warpgroup w form an independent pipeline over the tiles of parity
+      // w with its own half of the stage ring (a barrier is only ever waited on by one issuer, in consecutive phases).
+      const int nw = p.mma_warps == 2 ? 2 : 1;
+      const int ring = nw == 2 ? p.stages / 2 : p.stages;
+      const int sbase = nw == 2 ? warp * ring : 0;
+      const int step = nw == 2 ? 1 : 2;
+      int L = 0;                            // running stage-load index over the tiles of this ring
+      int stage = nw == 2 ? 0 : warp;       // ring-local stage / phase of the next load of THIS producer
       uint32_t phase = 0;
       bool ready = false;                   // result of the early try_wait on empty[stage]
-      for (int st = cluster_id; st < total_super; st += num_clusters) {
+      for (int st = cluster_id + (nw == 2 ? warp * num_clusters : 0); st < total_super; st += nw * num_clusters) {
         const int nt = st / m_super;
         const int mt = min((st - nt * m_super) * cs + (int)crank, p.m_tiles - 1);  // ghost CTAs redo the last tile
         const int m0 = mt * kTileM;
@@ -177,21 +184,21 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
         const int bh = oh0 * p.stride - p.pad_h;
         const int n0 = nt * p.n_tile;
         for (int ks = 0; ks < nstages_k; ++ks, ++L) {
-          if ((L & 1) != warp) continue;
+          if (nw == 1 && (L & 1) != warp) continue;
           const int kb0 = ks * p.bps;
           const int nblk = min(p.bps, p.nkb - kb0);
           long long tq0 = 0; if (p.dbg) tq0 = clock64();
-          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
+          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->empty[sbase + stage]), phase ^ 1u);
           if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq0; tq0 = t; }
-          const uint32_t full = ptx::smem_u32(&bars->full[stage]);
-          const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
+          const uint32_t full = ptx::smem_u32(&bars->full[sbase + stage]);
+          const uint32_t a_dst = smem_base + (uint32_t)((sbase + stage) * stage_bytes);
           const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
           const uint32_t tx = (uint32_t)(nblk * (kTileM * kKC * 2 + b_rows * kKC * 2));
           // this producer's next stage: ask for its barrier state now, look at the answer after the TMA issue
-          int nstage = stage + 2;
+          int nstage = stage + step;
           uint32_t nphase = phase;
-          if (nstage >= p.stages) { nstage -= p.stages; nphase ^= 1u; }
-          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->empty[nstage]), nphase ^ 1u);
+          if (nstage >= ring) { nstage -= ring; nphase ^= 1u; }
+          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->empty[sbase + nstage]), nphase ^ 1u);
           if constexpr (!kPair) {
             ptx::mbar_expect_tx(full, tx);
             for (int j = 0; j < nblk; ++j) {
@@ -222,41 +229,49 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       }
     }
     __syncwarp();
-  } else if (warp == 2 && (!pair || crank == 0)) {
-    // ===================================================================== MMA issuer (pair mode: leader CTA only)
+  } else if ((warp == 2 || (warp == 3 && p.mma_warps == 2)) && (!pair || crank == 0)) {
+    // ===================================================================== MMA issuer(s) (pair mode: leader CTA only)
+    // p.mma_warps == 2: warps 2 and 3 issue the MMAs of alternate tiles (tile parity = issuer = accumulator = epilogue
+    // warpgroup): two independent MMA -> epilogue pipelines fed by the same producers (conv3x3_patch_body.cuh).
+    const int mw = warp - 2;
+    const int nw = p.mma_warps == 2 ? 2 : 1;
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::umma_idesc_f16(pair ? 2 * kTileM : kTileM, p.n_tile);
       const int ctail = p.Cin - (p.cpt - 1) * kKC;          // real channels in the last k-block of a tap
-      int stage = 0;
+      // two issuers: this one owns the tiles of parity mw and the stage ring [sbase, sbase + ring) (see the producers)
+      const int ring = nw == 2 ? p.stages / 2 : p.stages;
+      const int sbase = nw == 2 ? mw * ring : 0;
+      int stage = 0;                        // ring-local
       uint32_t phase = 0;
       bool ready = false;                   // result of the early try_wait on full[stage]
-      int it = 0;
+      int it = mw;
       bool first_stage = true;
-      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = p.dbg ? clock64() : 0;
-      for (int st = cluster_id; st < total_super; st += num_clusters, ++it) {
+      const bool dbg_on = p.dbg != nullptr && mw == 0;
+      long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = dbg_on ? clock64() : 0;
+      for (int st = cluster_id + mw * num_clusters; st < total_super; st += nw * num_clusters, it += nw) {
         const int acc = it & 1;
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-        long long tq0 = 0; if (p.dbg) tq0 = clock64();
+        long long tq0 = 0; if (dbg_on) tq0 = clock64();
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
-        if (p.dbg) dbg_wtm += clock64() - tq0;
+        if (dbg_on) dbg_wtm += clock64() - tq0;
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
         int cblk = 0;                         // channel block of the stage's first k-block within its tap (kb % cpt, no division)
         for (int ks = 0; ks < nstages_k; ++ks) {
           const int kb0 = ks * p.bps;
           const int nblk = min(p.bps, p.nkb - kb0);
-          if (p.dbg) tq0 = clock64();
-          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
-          if (p.dbg) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (first_stage) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
+          if (dbg_on) tq0 = clock64();
+          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->full[sbase + stage]), phase);
+          if (dbg_on) { const long long t = clock64(); dbg_wfull += t - tq0; tq0 = t; if (first_stage) p.dbg[blockIdx.x * 32 + 18] = (long long)ptx::globaltimer(); }
           first_stage = false;
           ptx::tc_fence_after_sync();
-          const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
+          const uint32_t a_src = smem_base + (uint32_t)((sbase + stage) * stage_bytes);
           const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
           // the next stage's barrier state is requested before this stage's MMAs are issued
           int nstage = stage + 1;
           uint32_t nphase = phase;
-          if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
-          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->full[nstage]), nphase);
+          if (nstage == ring) { nstage = 0; nphase ^= 1u; }
+          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->full[sbase + nstage]), nphase);
           for (int j = 0; j < nblk; ++j) {
             const int nk = (cblk == p.cpt - 1 ? ctail : kKC) / 16;
             cblk = cblk + 1 == p.cpt ? 0 : cblk + 1;
@@ -271,16 +286,16 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
             }
           }
           // frees the smem slot (pair: in both CTAs) when the MMAs retire
-          if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
-          else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->empty[stage]), mc_mask);
+          if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->empty[sbase + stage]));
+          else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->empty[sbase + stage]), mc_mask);
           stage = nstage; phase = nphase; ready = nready;
-          if (p.dbg) dbg_mma += clock64() - tq0;
+          if (dbg_on) dbg_mma += clock64() - tq0;
         }
         // accumulator ready (pair: for both CTAs' epilogues)
         if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
         else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->tmem_full[acc]), mc_mask);
       }
-      if (p.dbg) {
+      if (dbg_on) {
         p.dbg[blockIdx.x * 32 + 19] = (long long)ptx::globaltimer();
         p.dbg[blockIdx.x * 32 + 4] = dbg_wfull; p.dbg[blockIdx.x * 32 + 5] = dbg_wtm;
         p.dbg[blockIdx.x * 32 + 6] = dbg_mma; p.dbg[blockIdx.x * 32 + 7] = clock64() - dbg_t0;

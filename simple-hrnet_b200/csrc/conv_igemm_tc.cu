@@ -51,7 +51,7 @@ int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms) {
       if (cudaOccupancyMaxActiveClusters(&nc, conv_igemm_tc_kernel<true, 0>, &cfg) == cudaSuccess && nc > 0) cached[cs] = nc;
       else { cudaGetLastError(); cached[cs] = num_sms / cs; }
     }
-    max_clusters = cached[cs];
+    max_clusters = std::min(cached[cs], num_sms / cs);   // num_sms may be a caller-imposed cap
   }
   return std::min(need, max_clusters) * cs;
 }

@@ -51,6 +51,7 @@ struct ConvTcCfg {
   int cs = 1;        // 2: CTA-pair mode (cta_group::2)
   int epi = 0;       // epilogue: 0 direct stores, 1 staged TMA stores, 2 warp-staged coalesced stores
   int epi_bytes = 0; // shared memory of the epilogue staging tiles
+  int mma_warps = 1; // 2: two MMA-issuing warps on alternate tiles
 };
 
 
@@ -68,6 +69,7 @@ struct ConvTcParams {
   int n_tile, n_tiles, m_tiles;
   int cs;            // cluster size along M (weights multicast): 1, 2 or 4
   int stages;
+  int mma_warps;     // 1, or 2: warps 2 and 3 issue the MMAs of alternate tiles
   int relu, out_f32;
   int tmem_cols;
   int a_blk_bytes, b_blk_bytes;
@@ -95,6 +97,7 @@ struct ConvPatchParams {
   int a_slot_bytes;            // bytes of the patch part of a slot (weights of a streamed chunk follow it)
   int slot_bytes, nslots;      // ring of patch slots (one channel chunk of one tile each)
   int nacc, nacc_log2;         // TMEM accumulator buffers (2 or 4)
+  int mma_warps;               // 1, or 2: warps 2 and 3 issue the MMAs of alternate tiles (two MMA -> epilogue pipelines)
   int cs;                      // 2: CTA-pair mode (cta_group::2), each CTA keeps Cout / 2 weight rows; else 1
   int relu, out_f32, tmem_cols;
   int epi_tma, epi_bytes;      // epilogue: 0 direct, 1 staged TMA stores, 2 warp-staged coalesced; staging follows the patch slots

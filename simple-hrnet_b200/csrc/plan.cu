@@ -180,6 +180,8 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
     if (op.k * op.k * op.cin < atoi(e)) c.cs = 1;
   }
   if (nt % 16 || (nt / 2) % 8) c.cs = 1;
+  // two MMA-issuing warps on alternate tiles (conv_igemm_body.cuh): HRNET_B200_IGEMM_MMA2=1 (all convs) or =<max N>
+  // (only tiles at most that wide, where the issue side rather than shared-memory bandwidth sets the pace)
   const int a_blk = (int)align_up((size_t)128 * c.kc * 2, 1024);
   const int b_blk = (int)align_up((size_t)(nt / c.cs) * c.kc * 2, 1024);
   const int stage = c.bps * (a_blk + b_blk);
@@ -189,6 +191,14 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   const int kstages = (nkb + c.bps - 1) / c.bps;
   c.stages = std::max(2, std::min({8, (budget - fixed) / stage, std::max(2, kstages * 2)}));
   c.stages &= ~1;   // two producer warps alternate stages
+  // two MMA-issuing warps on alternate tiles, each with half of the stage ring (conv_igemm_body.cuh): on for tiles at
+  // most 96 channels wide, where per-tile barrier / commit latencies rather than shared-memory bandwidth set the pace
+  // (forward 7.81 -> 7.71 ms); wider tiles lose more from the halved ring (C = 384 branch conv 35 -> 52 us).
+  // HRNET_B200_IGEMM_MMA2=0 (off) / 1 (all convs) / <max N> overrides.
+  int mma2_max_n = 96;
+  if (const char* e = getenv("HRNET_B200_IGEMM_MMA2")) { const int v = atoi(e); mma2_max_n = v == 1 ? 1 << 30 : v; }
+  c.mma_warps = nt <= mma2_max_n ? 2 : 1;
+  if (c.cs == 2 || c.stages < 4) c.mma_warps = 1;
   c.smem_bytes = fixed + c.stages * stage;
   int cols = 32;
   while (cols < 2 * nt) cols *= 2;
@@ -254,6 +264,13 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
   p.nacc = 4 * op.cout <= 512 ? 4 : 2;
   if (const char* e = getenv("HRNET_B200_PATCH_NACC")) { if (atoi(e) == 2) p.nacc = 2; }
   p.nacc_log2 = p.nacc == 4 ? 2 : 1;
+  // two MMA-issuing warps on alternate tiles, each with half of the slot ring (conv3x3_patch_body.cuh): on when every
+  // ring keeps two slots (C = 48 branch convs 39.7 -> 33.9 us, layer1 conv2 47.8 -> 44.8; with one slot per ring the
+  // C = 96 convs and the streamed-weight transition conv get slower, profiles/r01_exp_mma2_issuers.log).
+  // HRNET_B200_PATCH_MMA2=0/1 overrides.
+  p.mma_warps = p.nslots >= 4 ? 2 : 1;
+  if (const char* e = getenv("HRNET_B200_PATCH_MMA2")) p.mma_warps = atoi(e) ? 2 : 1;
+  if (p.cs == 2) p.mma_warps = 1;
   int cols = 32;
   while (cols < p.nacc * op.cout) cols *= 2;
   p.tmem_cols = cols;
@@ -280,7 +297,23 @@ int epi_policy() {
   if (!strcmp(e, "tma_igemm")) return 5;    // experiments: TMA epilogue on every im2col conv, auto elsewhere
   return 0;
 }
+// The epilogue staging tiles are carved out of the pipeline's shared memory: re-check that every issuer's ring keeps its
+// minimum depth once the final slot / stage counts are known.
+void finalize_mma_warps(Op& op) {
+  if (!op.use_tc) return;
+  if (op.use_patch) {
+    if (op.pp.mma_warps == 2 && op.pp.nslots < 4 && !getenv("HRNET_B200_PATCH_MMA2")) op.pp.mma_warps = 1;
+  } else if (op.tc.mma_warps == 2 && op.tc.stages < 4) {
+    op.tc.mma_warps = 1;
+  }
+}
+
+void choose_epi_impl(Op& op, bool out_f32, bool sub, bool has_res);
 void choose_epi(Op& op, bool out_f32, bool sub, bool has_res) {
+  choose_epi_impl(op, out_f32, sub, has_res);
+  finalize_mma_warps(op);
+}
+void choose_epi_impl(Op& op, bool out_f32, bool sub, bool has_res) {
   const int policy = epi_policy();
   if (!op.use_tc || policy == 1 || out_f32 || sub) return;
   const int width = op.use_patch ? op.pp.Cout : op.tc.n_tile;
@@ -877,7 +910,8 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     o << "],\"tc\":{\"kc\":" << op.tc.kc << ",\"bps\":" << op.tc.bps << ",\"n_tile\":" << op.tc.n_tile
       << ",\"cs\":" << op.tc.cs << ",\"stages\":" << op.tc.stages << ",\"smem\":" << op.tc.smem_bytes << ",\"tmem_cols\":" << op.tc.tmem_cols
       << ",\"epi\":" << (op.use_patch ? op.pp.epi_tma : op.tc.epi)
-      << ",\"patch_cs\":" << (op.use_patch ? op.pp.cs : 0) << ",\"patch_slots\":" << (op.use_patch ? op.pp.nslots : 0) << "}}";
+      << ",\"patch_cs\":" << (op.use_patch ? op.pp.cs : 0) << ",\"patch_slots\":" << (op.use_patch ? op.pp.nslots : 0)
+      << ",\"mma_warps\":" << (op.use_patch ? op.pp.mma_warps : op.tc.mma_warps) << "}}";
   }
   o << "]}";
   const std::string s = o.str();
@@ -995,7 +1029,7 @@ ConvTcParams fill_tc_params(HrnetPlan* P, const Op& op, int n) {
   p.kc = op.tc.kc; p.cpt = (op.cin + op.tc.kc - 1) / op.tc.kc; p.nkb = op.k * op.k * p.cpt; p.bps = op.tc.bps;
   p.n_tile = op.tc.n_tile; p.n_tiles = op.cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
   p.cs = op.tc.cs;
-  p.stages = op.tc.stages; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
+  p.stages = op.tc.stages; p.mma_warps = op.tc.mma_warps; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
   p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
   p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
   p.scale = (const float*)(P->wbase + pi.scale_offset);
@@ -1134,7 +1168,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.kc = op.tc.kc; p.cpt = (op.cin + op.tc.kc - 1) / op.tc.kc; p.nkb = op.k * op.k * p.cpt; p.bps = op.tc.bps;
         p.n_tile = op.tc.n_tile; p.n_tiles = op.cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
         p.cs = op.tc.cs;
-        p.stages = op.tc.stages; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
+        p.stages = op.tc.stages; p.mma_warps = op.tc.mma_warps; p.relu = op.relu; p.out_f32 = to.dtype == DT_F32; p.tmem_cols = op.tc.tmem_cols;
         p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
         p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
         p.scale = (const float*)(P->wbase + pi.scale_offset);
@@ -1498,7 +1532,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.kc = op.tc.kc; p.cpt = (cin + op.tc.kc - 1) / op.tc.kc; p.nkb = ksize * ksize * p.cpt; p.bps = op.tc.bps;
     p.n_tile = op.tc.n_tile; p.n_tiles = cout / op.tc.n_tile; p.m_tiles = (p.M_total + 127) / 128;
     p.cs = op.tc.cs;
-    p.stages = op.tc.stages; p.relu = relu; p.out_f32 = out_f32; p.tmem_cols = op.tc.tmem_cols;
+    p.stages = op.tc.stages; p.mma_warps = op.tc.mma_warps; p.relu = relu; p.out_f32 = out_f32; p.tmem_cols = op.tc.tmem_cols;
     p.a_blk_bytes = (int)align_up((size_t)128 * p.kc * 2, 1024);
     p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
