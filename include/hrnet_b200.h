@@ -145,6 +145,19 @@ int hrnet_fuse(const void* const* srcs, const int* shifts, const int* is_f32, in
 /* argmax decode of [n,J,Hh,Wh] fp32 heat-maps (SimpleHRNet.py:296-308). */
 int hrnet_argmax(const float* heatmaps, int n, int nof_joints, int hh, int wh, const float* boxes, float* joints,
                  int32_t* argmax_idx, void* stream);
+/* Evaluation-side decode, misc/utils.py:125-182 (get_max_preds + get_final_preds; training/COCO.py:218-224 is the caller):
+ * per joint the first maximum of the map (torch.max), (x, y) = (idx % wh, idx / wh) zeroed when the maximum is not > 0,
+ * with post_processing the quarter-pixel shift towards the higher neighbour, then -- when trans_2x3 is given -- the
+ * inverse affine `np.dot(t, [x, y, 1.])` of transform_preds in float64 (t = the host-built cv2.getAffineTransform
+ * matrix of misc/utils.py:46-79, one [2][3] float64 block per person, device memory).
+ *   preds_xy [n,J,2] fp32 (x, y)   maxvals [n,J] fp32 (the [n,J,1] tensor of the reference) */
+int hrnet_final_preds(const float* heatmaps, int n, int nof_joints, int hh, int wh, int post_processing,
+                      const double* trans_2x3, float* preds_xy, float* maxvals, void* stream);
+/* Flip test, training/COCO.py:206-212 with misc/utils.py:19-29: averaged = (output + flip_back(output_flipped)) * 0.5 on
+ * [n,J,hh,wh] fp32 device maps.  joint_perm_host[j] (HOST array of J ints, J <= 32) = the joint whose flipped map becomes
+ * joint j (identity outside the left/right pairs).  averaged may alias output. */
+int hrnet_flip_average(const float* output, const float* output_flipped, const int32_t* joint_perm_host, int n,
+                       int nof_joints, int hh, int wh, float* averaged, void* stream);
 /* median device time in microseconds of `iters` launches of one conv (CUDA events on `stream`),
  * same arguments as hrnet_conv_bn_act; used by bench.py for the per-kernel roofline. */
 int hrnet_conv_bench(const void* in_nhwc_f16, const void* w_f16, const float* scale, const float* bias,

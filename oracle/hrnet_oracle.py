@@ -16,6 +16,11 @@ What is restated (reference file:line, relative to stefanopini/simple-HRNet):
 * `decode_joints`        <- SimpleHRNet.py:296-308 (dup 431-443)
 * `preprocess`           <- SimpleHRNet.py:216-222, 350-366, 149-153
 * `predict`              <- SimpleHRNet.py:174-210 (multiperson=False branches only)
+* `get_max_preds`, `get_final_preds`, `inverse_affine`
+                         <- misc/utils.py:125-182, :46-79, :115-122 (evaluation-side decode)
+* `flip_average`         <- training/COCO.py:206-212, misc/utils.py:9-29 (flip test)
+* `adapt_box`, `multiperson_crops`
+                         <- SimpleHRNet.py:227-278, :166-171 (multi-person glue around the path)
 
 The arithmetic itself lives in a third-party dependency that is not vendored in
 the reference tree: PyTorch (requirements.txt `torch>=1.4.0`, unpinned; this
@@ -365,3 +370,137 @@ def predict(sd, images_bgr_u8: np.ndarray, resolution: Tuple[int, int], model: s
     if not single:
         pts = np.expand_dims(pts, axis=1)
     return [hm, boxes, pts]
+
+
+# --------------------------------------------------------------------------------------
+# Evaluation-side decode: get_max_preds / get_final_preds / flip test
+# --------------------------------------------------------------------------------------
+
+def get_max_preds(batch_heatmaps: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """misc/utils.py:125-151.  heatmaps [n,J,Hh,Wh] f32 -> (preds [n,J,2] f32 as (x, y) in heat-map pixels,
+    maxvals [n,J,1] f32).  torch.max over the flattened map: first maximal index, a NaN counts as the maximum
+    (== np.argmax); `idx % width` / `floor(idx / width)` are evaluated on float32 indices (exact below 2^24);
+    joints whose maximum is not > 0 are zeroed (`preds *= pred_mask`)."""
+    n, J, Hh, Wh = batch_heatmaps.shape
+    flat = batch_heatmaps.reshape(n, J, Hh * Wh)
+    idx = np.argmax(flat, axis=2)
+    maxvals = np.take_along_axis(flat, idx[:, :, None], axis=2)
+    idxf = idx.astype(np.float32)
+    preds = np.zeros((n, J, 2), dtype=np.float32)
+    preds[:, :, 0] = np.fmod(idxf, np.float32(Wh))
+    preds[:, :, 1] = np.floor(idxf / np.float32(Wh))
+    mask = (maxvals > 0.0).astype(np.float32)          # NaN > 0 is False, like torch.gt
+    preds *= mask
+    return preds, maxvals.astype(np.float32)
+
+
+def inverse_affine(center, scale, pixel_std, output_size) -> np.ndarray:
+    """misc/utils.py:46-79 with rot = 0, shift = 0, inv = 1 (the call made by transform_preds, :115-122): the 2x3
+    float64 matrix that maps heat-map pixels back to image pixels.  cv2.getAffineTransform solves the 3-point system,
+    so the same routine is called here on the same three point pairs."""
+    import cv2
+    scale = np.asarray(scale) if np.ndim(scale) else np.array([scale, scale])   # dtype kept: f32 * python float stays f32
+    center = np.asarray(center)
+    scale_tmp = scale * 1.0 * pixel_std
+    src_w = scale_tmp[0]
+    dst_w, dst_h = output_size[0], output_size[1]
+    zero_shift = np.array([0, 0], dtype=np.float32)
+    src_dir = [0 * 1.0 - (src_w * -0.5) * 0.0, 0 * 0.0 + (src_w * -0.5) * 1.0]    # get_dir([0, -src_w / 2], 0): sin 0 = 0, cos 0 = 1
+    src = np.zeros((3, 2), dtype=np.float32)
+    dst = np.zeros((3, 2), dtype=np.float32)
+    src[0, :] = center + scale_tmp * zero_shift
+    src[1, :] = center + src_dir + scale_tmp * zero_shift
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5]) + np.array([0, dst_w * -0.5], np.float32)
+
+    def third(a, b):
+        d = a - b
+        return b + np.array([-d[1], d[0]], dtype=np.float32)
+
+    src[2:, :] = third(src[0, :], src[1, :])
+    dst[2:, :] = third(dst[0, :], dst[1, :])
+    return cv2.getAffineTransform(np.float32(dst), np.float32(src))
+
+
+def get_final_preds(post_processing: bool, batch_heatmaps: np.ndarray, center, scale, pixel_std) -> Tuple[np.ndarray, np.ndarray]:
+    """misc/utils.py:154-182: get_max_preds, optional quarter-pixel shift towards the higher neighbour (float32,
+    `torch.sign`: 0 for 0 and for NaN), then the inverse affine of every joint evaluated in float64
+    (`np.dot(t, [x, y, 1.])`) and stored to float32.  center/scale [n,2]; returns (preds [n,J,2] f32, maxvals [n,J,1])."""
+    coords, maxvals = get_max_preds(batch_heatmaps)
+    n, J, Hh, Wh = batch_heatmaps.shape
+    if post_processing:
+        for i in range(n):
+            for p in range(J):
+                hm = batch_heatmaps[i, p]
+                px = int(math.floor(coords[i, p, 0] + 0.5))
+                py = int(math.floor(coords[i, p, 1] + 0.5))
+                if 1 < px < Wh - 1 and 1 < py < Hh - 1:
+                    with np.errstate(invalid="ignore"):
+                        diff = np.array([hm[py][px + 1] - hm[py][px - 1], hm[py + 1][px] - hm[py - 1][px]], dtype=np.float32)
+                    sgn = np.where(diff > 0, np.float32(1), np.where(diff < 0, np.float32(-1), np.float32(0))).astype(np.float32)
+                    coords[i, p] += sgn * np.float32(.25)
+    preds = coords.copy()
+    for i in range(n):
+        t = inverse_affine(center[i], scale[i], pixel_std, [Wh, Hh])
+        for p in range(J):
+            new_pt = np.array([coords[i, p, 0], coords[i, p, 1], 1.]).T
+            preds[i, p, 0:2] = np.dot(t, new_pt)[:2]
+    return preds, maxvals
+
+
+def flip_average(output: np.ndarray, output_flipped: np.ndarray, flip_pairs) -> np.ndarray:
+    """training/COCO.py:206-212 + misc/utils.py:9-29: `(output + flip_back(output_flipped, pairs)) * 0.5` on
+    [n,J,Hh,Wh] f32 maps: the flipped output is mirrored along x and its left/right joints swapped back."""
+    fb = output_flipped[:, :, :, ::-1].copy()
+    for a, b in flip_pairs:
+        tmp = fb[:, a].copy()
+        fb[:, a] = fb[:, b]
+        fb[:, b] = tmp
+    return (output + fb) * np.float32(0.5)
+
+
+# --------------------------------------------------------------------------------------
+# Multi-person glue (SURVEY section 8f rank 3): box adaptation + crop of SimpleHRNet._predict_single
+# --------------------------------------------------------------------------------------
+
+def adapt_box(x1: int, y1: int, x2: int, y2: int, resolution: Tuple[int, int]):
+    """SimpleHRNet.py:244-276: pad (not enlarge) a detection so that it matches the network's aspect ratio.
+    Integer box in, (x1_new, y1_new, x2_new, y2_new), np.pad tuple or None out."""
+    correction_factor = resolution[0] / resolution[1] * (x2 - x1) / (y2 - y1)
+    if correction_factor > 1:
+        center = y1 + (y2 - y1) // 2
+        length = int(round((y2 - y1) * correction_factor))
+        y1_new = int(center - length // 2)
+        y2_new = int(center + length // 2)
+        pad = (int(abs(y1_new - y1))), int(abs(y2_new - y2))
+        return (x1, y1_new, x2, y2_new), (pad, (0, 0), (0, 0))
+    elif correction_factor < 1:
+        center = x1 + (x2 - x1) // 2
+        length = int(round((x2 - x1) * 1 / correction_factor))
+        x1_new = int(center - length // 2)
+        x2_new = int(center + length // 2)
+        pad = (abs(x1_new - x1)), int(abs(x2_new - x2))
+        return (x1_new, y1, x2_new, y2), ((0, 0), pad, (0, 0))
+    return (x1, y1, x2, y2), None
+
+
+def multiperson_crops(image_bgr_u8: np.ndarray, detections, resolution: Tuple[int, int]):
+    """SimpleHRNet.py:227-278: detections (rows x1, y1, x2, y2, ...) -> (network inputs [m,3,H,W] f32, boxes [m,4] int32).
+    Each crop is `image[y1:y2, x1:x2, ::-1]` (BGR -> RGB), zero-padded to the network aspect ratio and passed through
+    ToPILImage -> Resize((H, W)) -> ToTensor -> Normalize (:166-171)."""
+    from torchvision.transforms import transforms
+    tf = transforms.Compose([transforms.ToPILImage(), transforms.Resize((resolution[0], resolution[1])),
+                             transforms.ToTensor(),
+                             transforms.Normalize(mean=list(IMAGENET_MEAN), std=list(IMAGENET_STD))])
+    m = len(detections) if detections is not None else 0
+    boxes = np.empty((m, 4), dtype=np.int32)
+    images = torch.empty((m, 3, resolution[0], resolution[1]))
+    for i in range(m):
+        x1, y1, x2, y2 = [int(round(float(v))) for v in detections[i][:4]]
+        box, pad = adapt_box(x1, y1, x2, y2, resolution)
+        crop = image_bgr_u8[y1:y2, x1:x2, ::-1]
+        if pad is not None:
+            crop = np.pad(crop, pad)
+        images[i] = tf(crop)
+        boxes[i] = box
+    return images, boxes

@@ -50,6 +50,8 @@ SYMBOLS = {
     "hrnet_conv_bn_act": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "hrnet_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "hrnet_argmax": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "hrnet_final_preds": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "hrnet_flip_average": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_int32), _i, _i, _i, _i, _vp, _vp]),
     "hrnet_conv_bench": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                               ctypes.POINTER(ctypes.c_float), _vp]),
 }

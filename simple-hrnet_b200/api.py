@@ -1,9 +1,12 @@
 """SimpleHRNet: the reference's user-facing class (SimpleHRNet.py:12-496) re-hosted on the B200
-engine for the multiperson=False path (the hot path named by BASELINE.json).  Same constructor
-arguments, same `predict()` input/return formats, same error strings.
+engine.  Same constructor arguments, same `predict()` input/return formats, same error strings.
 
-Out of scope here: the YOLO person detectors (multiperson=True) and the TensorRT
-loader; both raise NotImplementedError instead of silently doing something else."""
+multiperson=False is the hot path named by BASELINE.json.  multiperson=True runs the
+reference's glue around the path -- detection boxes -> aspect-ratio adaptation -> crops -> network -> joints rescaled
+into the boxes by the decode kernel -- with a person detector supplied by the caller (`detector=`: any object with the
+reference detectors' `predict_single(image)` / `predict(images)` methods, models_/detectors/YOLOv3.py:88,117): the YOLO
+networks themselves are out of scope, so without a detector the constructor raises
+NotImplementedError instead of silently doing something else.  The TensorRT loader raises as well."""
 import numpy as np
 import torch
 
@@ -18,7 +21,7 @@ class SimpleHRNet:
                  interpolation=None, multiperson=True, return_heatmaps=False, return_bounding_boxes=False,
                  max_batch_size=32, yolo_version='v3', yolo_model_def=None, yolo_class_path=None,
                  yolo_weights_path=None, device=torch.device("cuda"), enable_tensorrt=False, engine_flags=0,
-                 device_preprocess=True):
+                 device_preprocess=True, detector=None):
         self.c = c
         self.nof_joints = nof_joints
         self.checkpoint_path = checkpoint_path
@@ -36,8 +39,11 @@ class SimpleHRNet:
         if self.multiperson:
             if self.yolo_version not in ('v3', 'v5'):
                 raise ValueError('Unsopported YOLO version.')           # SimpleHRNet.py:107 (sic)
-            raise NotImplementedError("multiperson=True needs the YOLO person detector, which is outside the "
-                                      "B200 hot path; crop people yourself and call predict() on the crops")
+            if detector is None:
+                raise NotImplementedError("multiperson=True needs a person detector and the reference's YOLO networks are "
+                                          "outside the B200 hot path: pass detector=<object with predict_single(image) / "
+                                          "predict(images)>, or crop people yourself and call predict() on the crops")
+        self.detector = detector
         if self.enable_tensorrt:
             raise NotImplementedError("enable_tensorrt: the B200 engine already occupies the TensorRT seam")
         if model_name in ('HRNet', 'hrnet'):
@@ -61,7 +67,8 @@ class SimpleHRNet:
             self.model.load_state_dict(checkpoint)
         # device-side transform (uint8 in) for HRNet at a fixed resolution; set device_preprocess=False to feed the
         # host-normalised fp32 tensor exactly like the reference does
-        self._u8_path = bool(device_preprocess) and arch == "hrnet" and self.resolution is not None
+        self._u8_path = bool(device_preprocess) and arch == "hrnet" and self.resolution is not None and not self.multiperson
+        self._mp_transform = None
         self._mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1, 1)
         self._std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1, 1)
 
@@ -134,7 +141,98 @@ class SimpleHRNet:
         res.append(pts)
         return res if len(res) > 1 else res[0]
 
+    # ---- multi-person glue (SimpleHRNet.py:227-278 single image, :376-412 batch) -------------------------------------
+    def _crop_to_input(self, crop_rgb):
+        """ToPILImage -> Resize((H, W)) -> ToTensor -> Normalize of SimpleHRNet.py:166-171 (torchvision, on the host)."""
+        if self._mp_transform is None:
+            from torchvision.transforms import transforms
+            self._mp_transform = transforms.Compose([
+                transforms.ToPILImage(), transforms.Resize((self.resolution[0], self.resolution[1])),
+                transforms.ToTensor(), transforms.Normalize(mean=list(IMAGENET_MEAN), std=list(IMAGENET_STD))])
+        return self._mp_transform(crop_rgb)
+
+    @staticmethod
+    def _rounded_box(det):
+        x1, y1, x2, y2 = [int(round(v.item() if hasattr(v, "item") else float(v))) for v in det[:4]]
+        return x1, y1, x2, y2
+
+    def _aspect(self, x1, y1, x2, y2):
+        return self.resolution[0] / self.resolution[1] * (x2 - x1) / (y2 - y1)
+
+    def _predict_single_multiperson(self, image):
+        detections = self.detector.predict_single(image)
+        m = len(detections) if detections is not None else 0
+        boxes = np.empty((m, 4), dtype=np.int32)
+        x = torch.empty((m, 3, self.resolution[0], self.resolution[1]))
+        for i in range(m):
+            x1, y1, x2, y2 = self._rounded_box(detections[i])
+            cf = self._aspect(x1, y1, x2, y2)
+            nx1, ny1, nx2, ny2, pad = x1, y1, x2, y2, None
+            if cf > 1:       # too wide for the network: grow the box in y and zero-pad the crop (no neighbours pulled in)
+                mid, length = y1 + (y2 - y1) // 2, int(round((y2 - y1) * cf))
+                ny1, ny2 = int(mid - length // 2), int(mid + length // 2)
+                pad = ((int(abs(ny1 - y1)), int(abs(ny2 - y2))), (0, 0), (0, 0))
+            elif cf < 1:     # too tall: same along x
+                mid, length = x1 + (x2 - x1) // 2, int(round((x2 - x1) * 1 / cf))
+                nx1, nx2 = int(mid - length // 2), int(mid + length // 2)
+                pad = ((0, 0), (abs(nx1 - x1), int(abs(nx2 - x2))), (0, 0))
+            crop = image[y1:y2, x1:x2, ::-1]
+            if pad is not None:
+                crop = np.pad(crop, pad)
+            x[i] = self._crop_to_input(crop)
+            boxes[i] = [nx1, ny1, nx2, ny2]
+        if m > 0:
+            heatmaps, pts = self._run(x, boxes)
+        else:
+            heatmaps = np.zeros((0, self.nof_joints, self.resolution[0] // 4, self.resolution[1] // 4), dtype=np.float32)
+            pts = np.empty((0, 0, 3), dtype=np.float32)                  # SimpleHRNet.py:331
+        return self._pack(heatmaps, boxes, pts)
+
+    def _predict_batch_multiperson(self, images):
+        image_detections = self.detector.predict(images)
+        m = int(np.sum([len(d) for d in image_detections if d is not None]))
+        boxes = np.empty((m, 4), dtype=np.int32)
+        x = torch.empty((m, 3, self.resolution[0], self.resolution[1]))
+        base = 0
+        for d, detections in enumerate(image_detections):
+            image = images[d]
+            if detections is None or len(detections) == 0:
+                continue
+            for i in range(len(detections)):
+                x1, y1, x2, y2 = self._rounded_box(detections[i])
+                cf = self._aspect(x1, y1, x2, y2)
+                if cf > 1:       # the batch path enlarges the box (clamped to the frame) instead of padding (:395-405)
+                    mid, length = y1 + (y2 - y1) // 2, int(round((y2 - y1) * cf))
+                    y1, y2 = max(0, mid - length // 2), min(image.shape[0], mid + length // 2)
+                elif cf < 1:
+                    mid, length = x1 + (x2 - x1) // 2, int(round((x2 - x1) * 1 / cf))
+                    x1, x2 = max(0, mid - length // 2), min(image.shape[1], mid + length // 2)
+                boxes[base + i] = [x1, y1, x2, y2]
+                x[base + i] = self._crop_to_input(image[y1:y2, x1:x2, ::-1])
+            base += len(detections)
+        J, Hh, Wh = self.nof_joints, self.resolution[0] // 4, self.resolution[1] // 4
+        if m > 0:
+            heatmaps, pts = self._run(x, boxes)
+            hm_b, box_b, pts_b, index = [], [], [], 0
+            for detections in image_detections:                          # re-add the per-frame axis (:448-470)
+                k = len(detections) if detections is not None else 0
+                if detections is not None:
+                    pts_b.append(pts[index:index + k]); hm_b.append(heatmaps[index:index + k])
+                    box_b.append(boxes[index:index + k])
+                else:
+                    pts_b.append(np.zeros((0, J, 3), dtype=np.float32))
+                    hm_b.append(np.zeros((0, J, Hh, Wh), dtype=np.float32))
+                    box_b.append(np.zeros((0, 4), dtype=np.float32))
+                index += k
+            return self._pack(hm_b, box_b, pts_b)
+        heatmaps = np.zeros((0, J, Hh, Wh), dtype=np.float32)
+        boxes = np.asarray([], dtype=np.int32)                            # :478
+        pts = [np.zeros((0, J, 3), dtype=np.float32) for _ in range(len(image_detections))]
+        return self._pack(heatmaps, boxes, pts)
+
     def _predict_single(self, image):
+        if self.multiperson:
+            return self._predict_single_multiperson(image)
         old_res = image.shape
         boxes = np.asarray([[0, 0, old_res[1], old_res[0]]], dtype=np.float32)   # [x1, y1, x2, y2]
         if self._u8_path:
@@ -144,6 +242,8 @@ class SimpleHRNet:
         return self._pack(heatmaps, boxes, pts)
 
     def _predict_batch(self, images):
+        if self.multiperson:
+            return self._predict_batch_multiperson(images)
         if images.shape[0] == 0:
             raise ValueError  # the reference reaches `raise ValueError` for an empty non-multiperson batch (:487)
         old_res = images[0].shape

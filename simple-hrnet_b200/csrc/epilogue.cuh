@@ -154,6 +154,11 @@ __device__ __forceinline__ void epi_tma_tile(const EpiTma& e, uint32_t t_row, in
                        : "=r"(cur[k].x), "=r"(cur[k].y), "=r"(cur[k].z), "=r"(cur[k].w)
                        : "r"(my_res + (((uint32_t)k ^ sw) << 4)));
     }
+    // The residual rows were read through the generic proxy and stage_res is about to be overwritten by the next TMA
+    // load (async proxy): without this cross-proxy fence the overwrite is not ordered after the reads.  Observed on
+    // B200 as run-to-run differences of layer1 conv3 inside the network for 3 <= batch < 64 (never in isolation);
+    // CUTLASS's TMA epilogues fence the same way before releasing a TMA-loaded source buffer.
+    if (e.has_res) ptx::fence_proxy_async_smem();
     if (leader) ptx::tma_store_wait_read();      // the previous chunk's store no longer reads stage_out
     ptx::bar_sync(e.bar_id, 128);                // residual tile consumed by everyone, stage_out free
     if (e.has_res && leader && c64 + 64 < e.ncols) epi_tma_issue_residual(e, c64 + 64);
@@ -259,6 +264,7 @@ __device__ __forceinline__ void epi_wtma_tile(const EpiWarpTma& e, uint32_t t_ro
       for (int k = 0; k < 8; ++k)
         if (8 * k < nc) cur[k] = ptx::lds128(my_res + (((uint32_t)k ^ sw) << 4));
     }
+    if (e.has_res) ptx::fence_proxy_async_smem();       // generic-proxy reads of stage_res before its next TMA overwrite (see above)
     if (ptx::elect_one()) ptx::tma_store_wait_read();   // the previous store no longer reads stage_out
     __syncwarp();                                        // ... and every lane has read its residual row
     if (e.has_res && c64 + 64 < e.ncols) {

@@ -188,6 +188,10 @@ cudaError_t launch_head(const __half* in, const float* w, const float* bias, flo
                         int J, cudaStream_t st);
 cudaError_t launch_argmax(const float* hm, int N, int J, int Hh, int Wh, const float* boxes, float* joints,
                           int32_t* idx, cudaStream_t st);
+cudaError_t launch_final_preds(const float* hm, int N, int J, int Hh, int Wh, int post, const double* trans, float* preds,
+                               float* maxvals, cudaStream_t st);
+cudaError_t launch_flip_average(const float* a, const float* b, float* out, const int* perm, int N, int J, int Hh, int Wh,
+                                cudaStream_t st);
 cudaError_t launch_maxpool(const __half* in, __half* out, int N, int IH, int IW, int C, cudaStream_t st);
 cudaError_t launch_stem7(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
                          int N, int H, int W, cudaStream_t st);

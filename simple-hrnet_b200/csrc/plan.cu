@@ -1246,6 +1246,21 @@ int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, flo
     int rc = launch_op(P, op, n, in_ext, hm_ext, joints, idx, boxes, st);
     if (rc) return rc;
     if (op.needs_event) CK(cudaEventRecord(P->events[i], st));
+    // debug (HRNET_FLAG_NO_GRAPH only): synchronise after every op and print a hash of the n images of its output, so
+    // two runs can be diffed op by op (tools/dbg_invariance.py)
+    if ((P->desc.flags & HRNET_FLAG_NO_GRAPH) && op.out >= 0 && P->tensors[op.out].offset != (size_t)-1) {
+      static const bool on = getenv("HRNET_B200_DBG_CHECKSUM") != nullptr;
+      if (on) {
+        CK(cudaStreamSynchronize(st));
+        const size_t bytes = P->tensors[op.out].bytes(n);
+        std::vector<uint8_t> h(bytes);
+        CK(cudaMemcpy(h.data(), P->abase + P->tensors[op.out].offset, bytes, cudaMemcpyDeviceToHost));
+        uint64_t hash = 1469598103934665603ull;
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(h.data());
+        for (size_t k = 0; k < bytes / 8; ++k) { hash ^= w[k]; hash *= 1099511628211ull; }
+        fprintf(stderr, "[cs] %d %s %016llx\n", i, op.name.c_str(), (unsigned long long)hash);
+      }
+    }
   }
   return 0;
 }
@@ -1608,6 +1623,26 @@ int hrnet_argmax(const float* heatmaps, int n, int J, int hh, int wh, const floa
   if (n == 0) return HRNET_OK;
   if (!heatmaps || !joints) return fail(HRNET_E_INVALID, "null argument");
   CK(launch_argmax(heatmaps, n, J, hh, wh, boxes, joints, argmax_idx, (cudaStream_t)stream));
+  return HRNET_OK;
+}
+
+int hrnet_final_preds(const float* heatmaps, int n, int J, int hh, int wh, int post_processing, const double* trans_2x3,
+                      float* preds_xy, float* maxvals, void* stream) {
+  if (n < 0 || J <= 0 || hh <= 0 || wh <= 0) return fail(HRNET_E_INVALID, "bad shape");
+  if (n == 0) return HRNET_OK;
+  if (!heatmaps || !preds_xy || !maxvals) return fail(HRNET_E_INVALID, "null argument");
+  CK(launch_final_preds(heatmaps, n, J, hh, wh, post_processing ? 1 : 0, trans_2x3, preds_xy, maxvals, (cudaStream_t)stream));
+  return HRNET_OK;
+}
+
+int hrnet_flip_average(const float* output, const float* output_flipped, const int32_t* joint_perm_host, int n, int J, int hh,
+                       int wh, float* averaged, void* stream) {
+  if (n < 0 || J <= 0 || J > 32 || hh <= 0 || wh <= 0) return fail(HRNET_E_INVALID, "bad shape (nof_joints <= 32)");
+  if (n == 0) return HRNET_OK;
+  if (!output || !output_flipped || !joint_perm_host || !averaged) return fail(HRNET_E_INVALID, "null argument");
+  for (int j = 0; j < J; ++j)
+    if (joint_perm_host[j] < 0 || joint_perm_host[j] >= J) return fail(HRNET_E_INVALID, "joint_perm entry out of range");
+  CK(launch_flip_average(output, output_flipped, averaged, joint_perm_host, n, J, hh, wh, (cudaStream_t)stream));
   return HRNET_OK;
 }
 

@@ -5,6 +5,8 @@
 //   fuse_sum         : models_/hrnet.py:60-69    (sum of identity / nearest-upsampled / down-sampled terms + ReLU)
 //   head_conv1x1     : models_/hrnet.py:187      (c->J 1x1 conv with bias, fp32 NCHW heatmaps)
 //   argmax_decode    : SimpleHRNet.py:296-308    (np.argmax first-occurrence + (y, x, conf) scaling)
+//   final_preds      : misc/utils.py:125-182     (get_max_preds + quarter-pixel refine + inverse affine, evaluation side)
+//   flip_average     : training/COCO.py:206-212  (flip-test average of the heat-maps)
 //   conv_simt        : generic direct conv used as the debug cross-check of the tcgen05 path and for shapes
 //                      the implicit GEMM does not cover (Cin or Cout not a multiple of 16)
 #include "hrnet_internal.h"
@@ -384,6 +386,119 @@ cudaError_t launch_argmax(const float* hm, int N, int J, int Hh, int Wh, const f
                           int32_t* idx, cudaStream_t st) {
   if (N * J == 0) return cudaSuccess;
   argmax_decode_kernel<<<N * J, 256, 0, st>>>(hm, J, Hh, Wh, boxes, joints, idx);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ evaluation decode
+// get_max_preds + the quarter-pixel refinement + the inverse affine of get_final_preds (misc/utils.py:125-182), one
+// 256-thread block per (person, joint) heat-map.  Same first-maximum / NaN rule as the argmax above (torch.max == np.argmax).
+//   preds (x, y) = (idx % W, floor(idx / W)) as float32, zeroed when the maximum is not > 0 (`preds *= pred_mask`);
+//   post_processing: px = floor(x + .5), py likewise; if 1 < px < W-1 and 1 < py < H-1 the joint moves a quarter pixel
+//     towards the higher neighbour: += sign(hm[py][px+1] - hm[py][px-1]) * .25 (torch.sign: 0 for 0 and for NaN);
+//   trans (optional, [n][2][3] float64 = cv2.getAffineTransform of misc/utils.py:46-79 with inv = 1, built on the host):
+//     (x, y) <- t . (x, y, 1) evaluated in float64 without contraction, stored as float32 (np.dot of transform_preds).
+__global__ void __launch_bounds__(256)
+final_preds_kernel(const float* __restrict__ hm, int J, int Hh, int Wh, int post, const double* __restrict__ trans,
+                   float* __restrict__ preds, float* __restrict__ maxvals) {
+  const int pj = blockIdx.x;  // person * J + joint
+  const int HW = Hh * Wh;
+  const float* p = hm + (size_t)pj * HW;
+  float best = 0.f;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < HW; i += 256) {
+    const float v = __ldg(p + i);
+    if (bi == 0x7fffffff || better(v, i, best, bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ob, oi, best, bi))) { best = ob; bi = oi; }
+  }
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (warp != 0) return;
+  best = lane < 8 ? sv[lane] : 0.f;
+  bi = lane < 8 ? si[lane] : 0x7fffffff;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ob, oi, best, bi))) { best = ob; bi = oi; }
+  }
+  if (lane != 0) return;
+  const int r = bi / Wh, c = bi - r * Wh;
+  float x = (float)c, y = (float)r;
+  if (!(best > 0.f)) { x = 0.f; y = 0.f; }
+  if (post) {
+    const int px = (int)floorf(x + 0.5f), py = (int)floorf(y + 0.5f);
+    if (1 < px && px < Wh - 1 && 1 < py && py < Hh - 1) {
+      const float dx = __fsub_rn(__ldg(p + py * Wh + px + 1), __ldg(p + py * Wh + px - 1));
+      const float dy = __fsub_rn(__ldg(p + (py + 1) * Wh + px), __ldg(p + (py - 1) * Wh + px));
+      x += dx > 0.f ? 0.25f : (dx < 0.f ? -0.25f : 0.f);
+      y += dy > 0.f ? 0.25f : (dy < 0.f ? -0.25f : 0.f);
+    }
+  }
+  if (trans != nullptr) {
+    const double* t = trans + (size_t)(pj / J) * 6;
+    const double xd = (double)x, yd = (double)y;
+    const double nx = __dadd_rn(__dadd_rn(__dmul_rn(t[0], xd), __dmul_rn(t[1], yd)), t[2]);
+    const double ny = __dadd_rn(__dadd_rn(__dmul_rn(t[3], xd), __dmul_rn(t[4], yd)), t[5]);
+    x = (float)nx; y = (float)ny;
+  }
+  preds[(size_t)pj * 2 + 0] = x;
+  preds[(size_t)pj * 2 + 1] = y;
+  maxvals[pj] = best;
+}
+
+cudaError_t launch_final_preds(const float* hm, int N, int J, int Hh, int Wh, int post, const double* trans, float* preds,
+                               float* maxvals, cudaStream_t st) {
+  if (N * J == 0) return cudaSuccess;
+  final_preds_kernel<<<N * J, 256, 0, st>>>(hm, J, Hh, Wh, post, trans, preds, maxvals);
+  return cudaGetLastError();
+}
+
+// Flip test (training/COCO.py:206-212, misc/utils.py:9-29): out = (a + flip_back(b)) * 0.5 where flip_back mirrors every
+// map along x and swaps the left / right joints back: out[n, j, h, w] = (a[n, j, h, w] + b[n, perm[j], h, W-1-w]) * 0.5.
+// HBM-bound (three maps of 4 * J * Hh * Wh bytes per person); one thread per 4 consecutive output pixels when W % 4 == 0.
+struct FlipPerm { int v[32]; };
+__global__ void __launch_bounds__(256)
+flip_average_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, const FlipPerm perm,
+                    int J, int Hh, int Wh, long total_rows, int vec) {
+  const int wq = vec ? Wh / 4 : Wh;
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total_rows * wq) return;
+  const long row = i / wq;                 // (n * J + j) * Hh + h
+  const int wi = (int)(i - row * wq);
+  const long nj = row / Hh;
+  const int h = (int)(row - nj * Hh);
+  const long n = nj / J;
+  const int j = (int)(nj - n * J);
+  const long brow = ((n * J + perm.v[j]) * Hh + h) * (long)Wh;
+  if (vec) {
+    const float4 av = __ldg(reinterpret_cast<const float4*>(a + row * Wh) + wi);
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(b + brow) + (wq - 1 - wi));
+    float4 o;
+    o.x = __fmul_rn(__fadd_rn(av.x, bv.w), 0.5f); o.y = __fmul_rn(__fadd_rn(av.y, bv.z), 0.5f);
+    o.z = __fmul_rn(__fadd_rn(av.z, bv.y), 0.5f); o.w = __fmul_rn(__fadd_rn(av.w, bv.x), 0.5f);
+    reinterpret_cast<float4*>(out + row * Wh)[wi] = o;
+  } else {
+    out[row * Wh + wi] = __fmul_rn(__fadd_rn(__ldg(a + row * Wh + wi), __ldg(b + brow + (Wh - 1 - wi))), 0.5f);
+  }
+}
+
+cudaError_t launch_flip_average(const float* a, const float* b, float* out, const int* perm, int N, int J, int Hh, int Wh,
+                                cudaStream_t st) {
+  if ((long)N * J * Hh * Wh == 0) return cudaSuccess;
+  FlipPerm fp;
+  for (int j = 0; j < 32; ++j) fp.v[j] = j < J ? perm[j] : j;
+  const int vec = (Wh % 4 == 0) && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15u) == 0);
+  const long rows = (long)N * J * Hh;
+  const long work = rows * (vec ? Wh / 4 : Wh);
+  flip_average_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(a, b, out, fp, J, Hh, Wh, rows, vec);
   return cudaGetLastError();
 }
 
