@@ -146,3 +146,25 @@ def test_workspace_tensors_do_not_overlap_within_a_module():
                 a_live = (firsts[a], max(readers.get(a, [last_write[a]]) + [last_write[a]]))
                 b_live = (firsts[b], max(readers.get(b, [last_write[b]]) + [last_write[b]]))
                 assert a_live[1] < b_live[0] or b_live[1] < a_live[0], (a, b, a_live, b_live)
+
+
+@pytest.mark.parametrize("arch,c,res", [("hrnet", 48, (384, 288)), ("hrnet", 32, (256, 192)), ("poseresnet", 50, (256, 192))])
+def test_two_issuer_pipelines_keep_their_ring_depth(arch, c, res):
+    """mma_warps == 2 splits the slot / stage ring between two independent issuer pipelines: every ring must keep two
+    buffers, CTA-pair kernels keep one issuer, and wide / deep-K im2col tiles (where the halved ring costs more than the
+    overlap gains, profiles/r01_exp_mma2_issuers.log) stay on one issuer."""
+    d = Plan(arch, c, 17, res, 8).describe()
+    n2 = 0
+    for op in d["ops"]:
+        if not op.get("use_tc"):
+            continue
+        t = op["tc"]
+        if t["mma_warps"] == 2:
+            n2 += 1
+            if op["use_patch"]:
+                assert t["patch_slots"] >= 4 and t["patch_cs"] == 1, op["name"]
+            else:
+                assert t["stages"] >= 4 and t["n_tile"] <= 96 and t["cs"] == 1, op["name"]
+        else:
+            assert t["mma_warps"] == 1, op["name"]
+    assert n2 > 0
