@@ -6,6 +6,7 @@ mkdir -p gpurun_out; rm -f gpurun_out/parity.log
 timeout 1500 python -m pytest tests -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 300 python tools/dbg_invariance.py 0 3,5,8,16,33,64 2>&1 | tail -1   # forward(x[:k]) == forward(x)[:k], bit for bit, three runs each
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 python -c "
 import json; d=json.load(open('gpurun_out/bench.json')); print('BENCH', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'roof', d['roofline']['achieved'], d['roofline']['frac'], [(b['C'],b['us_avg']) for b in d['roofline']['per_branch']], 'cpu', d['cpu_baseline'], d['clocks']); print({k:(v['us'],v['launches']) for k,v in d['layer_breakdown']['classes'].items()})"
