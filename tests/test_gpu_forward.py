@@ -128,6 +128,23 @@ def test_batch_invariance_and_chunking_full_size():
     assert err <= 1e-3
 
 
+@pytest.mark.parametrize("arch,c,B,ks", [("hrnet", 32, 32, (3, 8, 16)), ("poseresnet", 50, 64, (3, 8, 33))])
+def test_batch_invariance_other_baseline_configs(arch, c, B, ks):
+    """BASELINE configs 2 (HRNet-W32 256x192, batch 32) and 5 (PoseResNet-50 256x192, batch 64) at full size: a rerun
+    gives the same bits and forward(x[:k]) == forward(x)[:k] for intermediate k (wide-tile staged TMA epilogues with a
+    residual are everywhere in the ResNet bottlenecks)."""
+    spec = O.hrnet_param_spec(c, 17) if arch == "hrnet" else O.poseresnet_param_spec(c, 17)
+    sd = O.make_state_dict(spec, seed=0, bn="default")
+    e = _engine(arch, c, (256, 192), B, sd)
+    x = torch.randn(B, 3, 256, 192, generator=torch.Generator().manual_seed(3)).cuda()
+    _, _, hB = e.forward_decode(x, return_heatmaps=True)
+    hB = hB.clone()
+    assert torch.equal(e.forward_decode(x, return_heatmaps=True)[2], hB)
+    for k in ks:
+        for _ in range(2):
+            assert torch.equal(e.forward_decode(x[:k], return_heatmaps=True)[2], hB[:k]), f"n={k}"
+
+
 def test_forward_host_equals_device_path():
     sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=2, bn="default")
     e = _engine("hrnet", 32, (256, 192), 8, sd)
