@@ -28,8 +28,22 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compiles and links in-tree.  Several processes may get here at once (one rank per GPU under torchrun): an
+    exclusive file lock serialises them and the losers find the library already up to date."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     objs = []
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
     if verbose:
