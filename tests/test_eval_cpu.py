@@ -129,3 +129,31 @@ def test_multiperson_without_detector_raises():
         SimpleHRNet(32, 17, {}, multiperson=True, device=torch.device("cuda"))
     with pytest.raises(ValueError, match="Unsopported YOLO version."):
         SimpleHRNet(32, 17, {}, multiperson=True, yolo_version="v9", device=torch.device("cuda"))
+
+
+@pytest.mark.parametrize("tag", ["4x3", "1x1"])
+def test_box_adaptation_many_cases_match_reference(golden_dir, tag):
+    """120 random detections per network aspect ratio (some touching the frame border): the boxes produced by the product's
+    single-frame (zero padding) and stacked-frame (clamped enlargement) glue equal those of the reference's
+    _predict_single / _predict_batch (network stubbed out when the fixture was generated)."""
+    g = _load(golden_dir, "multiperson_boxes")
+    res = tuple(int(v) for v in g[f"res_{tag}"])
+    dets = g[f"dets_{tag}"]
+    img = np.zeros(tuple(g["img_shape"]), dtype=np.uint8)
+    m, seen = _cpu_api({"res": np.asarray(res), "detections": dets}, None)
+    J = 17
+
+    def _run(self, x, boxes):                       # network stubbed out like in the fixture
+        return (np.zeros((len(boxes), J, res[0] // 4, res[1] // 4), dtype=np.float32),
+                np.zeros((len(boxes), J, 3), dtype=np.float32))
+
+    m._run = types.MethodType(_run, m)
+    m.max_batch_size = 64
+    m.detector = types.SimpleNamespace(predict_single=lambda image: torch.from_numpy(dets),
+                                       predict=lambda images: [torch.from_numpy(dets[:60]), torch.from_numpy(dets[60:])])
+    _, boxes, _ = m.predict(img)
+    assert np.array_equal(boxes, g[f"boxes_single_{tag}"])
+    oboxes = np.asarray([O.adapt_box(*[int(round(float(v))) for v in d[:4]], res)[0] for d in dets], dtype=np.int32)
+    assert np.array_equal(oboxes, g[f"boxes_single_{tag}"])
+    _, bboxes, _ = m.predict(np.stack([img, img]))
+    assert np.array_equal(np.concatenate(bboxes), g[f"boxes_batch_{tag}"])
