@@ -73,7 +73,7 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t a0, uint64_
 // Body of one CTA working on problem `p` as CTA `cta` of `nctas` (its own persistent tile loop); shared by the
 // single-problem kernel and the grouped multi-problem kernel (conv_group.cu).
 // kEpi selects the epilogue at compile time (p.epi_tma must agree): 0 direct row-per-thread stores, 1 staged TMA stores,
-// 2 warp-staged coalesced stores (epilogue.cuh).  Keeping several epilogues in one kernel cost the direct path
+// 2 warp-staged coalesced stores, 3 direct stores with batched TMEM loads for tiles <= 64 channels (epilogue.cuh).  Keeping several epilogues in one kernel cost the direct path
 // registers (spills) and ~15 % of its speed.
 // kPair (p.cs == 2, launched as clusters of two CTAs): `tcgen05.mma.cta_group::2`.  The two CTAs work on neighbouring
 // tiles; one M = 256 instruction issued by the leader spans both, each CTA feeds its own patch and only HALF of the
@@ -365,7 +365,8 @@ __device__ __forceinline__ void conv3x3_patch_body(const PatchMaps& maps, const 
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
       if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
       ptx::tc_fence_after_sync();
-      epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout));
+      if constexpr (kEpi == 3) epi_store_row_batched(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout));
+      else epi_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout));
       if (p.dbg) dbg_work += clock64() - tq0;
       ptx::tc_fence_before_sync();
       if (!kPair || crank == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));

@@ -21,6 +21,7 @@ cudaError_t conv_patch_set_attributes(int max_smem) {
   cudaError_t e = set_attr<false, 0>(max_smem);
   if (e == cudaSuccess) e = set_attr<false, 1>(max_smem);
   if (e == cudaSuccess) e = set_attr<false, 2>(max_smem);
+  if (e == cudaSuccess) e = set_attr<false, 3>(max_smem);
   if (e == cudaSuccess) e = set_attr<true, 0>(max_smem);
   if (e == cudaSuccess) e = set_attr<true, 1>(max_smem);
   if (e == cudaSuccess) e = set_attr<true, 2>(max_smem);
@@ -82,6 +83,7 @@ cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, 
   }
   if (p.epi_tma == 1) return cudaLaunchKernelEx(&cfg, conv3x3_patch_tc_kernel<false, 1>, m, p);
   if (p.epi_tma == 2) return cudaLaunchKernelEx(&cfg, conv3x3_patch_tc_kernel<false, 2>, m, p);
+  if (p.epi_tma == 3) return cudaLaunchKernelEx(&cfg, conv3x3_patch_tc_kernel<false, 3>, m, p);
   return cudaLaunchKernelEx(&cfg, conv3x3_patch_tc_kernel<false, 0>, m, p);
 }
 

@@ -73,7 +73,7 @@ __device__ __forceinline__ void issue_k16(uint32_t d_tmem, uint64_t adesc, uint6
 // Body of one CTA working on problem `p` as CTA `cta` of `nctas`; shared by the single-problem kernels and the grouped
 // multi-problem kernel (conv_group.cu, kPair = false only).
 // kEpi selects the epilogue at compile time (p.epi_tma must agree): 0 direct row-per-thread stores, 1 staged TMA stores,
-// 2 warp-staged coalesced stores (epilogue.cuh).
+// 2 warp-staged coalesced stores, 3 direct stores with batched TMEM loads for tiles <= 64 channels (epilogue.cuh).
 template <bool kPair, int kEpi>
 __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmO,
                                                 const CUtensorMap* tmR, const ConvTcParams& p, const int cta,
@@ -376,7 +376,8 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
       if (p.dbg) { const long long t = clock64(); dbg_wacc += t - tq0; tq0 = t; }
       ptx::tc_fence_after_sync();
-      epi_store_row(rres, e, t_row);
+      if constexpr (kEpi == 3) epi_store_row_batched(rres, e, t_row);
+      else epi_store_row(rres, e, t_row);
       if (p.dbg) dbg_work += clock64() - tq0;
       // all TMEM reads of this thread are complete (wait::ld inside): release the accumulator
       ptx::tc_fence_before_sync();

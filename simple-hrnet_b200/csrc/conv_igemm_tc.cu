@@ -23,6 +23,7 @@ cudaError_t conv_tc_set_attributes(int max_smem) {
   cudaError_t e = set_attr<false, 0>(max_smem);
   if (e == cudaSuccess) e = set_attr<false, 1>(max_smem);
   if (e == cudaSuccess) e = set_attr<false, 2>(max_smem);
+  if (e == cudaSuccess) e = set_attr<false, 3>(max_smem);
   if (e == cudaSuccess) e = set_attr<true, 0>(max_smem);
   if (e == cudaSuccess) e = set_attr<true, 1>(max_smem);
   if (e == cudaSuccess) e = set_attr<true, 2>(max_smem);
@@ -92,6 +93,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const
   }
   if (p.epi_tma == 1) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, 1>, tmA, tmB, tmO, tmR, p);
   if (p.epi_tma == 2) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, 2>, tmA, tmB, tmO, tmR, p);
+  if (p.epi_tma == 3) return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, 3>, tmA, tmB, tmO, tmR, p);
   return cudaLaunchKernelEx(&cfg, conv_igemm_tc_kernel<false, 0>, tmA, tmB, tmO, tmR, p);
 }
 

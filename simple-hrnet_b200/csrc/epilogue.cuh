@@ -102,6 +102,22 @@ __device__ __forceinline__ void epi_store_row(uint4 (&r)[8], const EpiRow& e, ui
   }
 }
 
+// kEpi == 3 (opt-in, HRNET_B200_EPI=batch; NOT yet run on hardware): the same thread-per-row epilogue for tiles at most 64
+// channels wide with all tcgen05.ld of the tile issued before ONE tcgen05.wait::ld (epi_store_row waits once per 32
+// columns: two TMEM round trips for a 48-channel tile).  `r` holds the residual of channels [0, 64) like above.
+__device__ __forceinline__ void epi_store_row_batched(uint4 (&r)[8], const EpiRow& e, uint32_t t_row) {
+  uint32_t v[4][16];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (16 * k < e.ncols) ptx::tmem_ld16(t_row + (uint32_t)(16 * k), v[k]);     // warp-uniform
+  ptx::tmem_ld_wait();
+  if (e.valid) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (16 * k < e.ncols) epi_cols16(v[k], r[2 * k], r[2 * k + 1], e, 16 * k);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Shared-memory-staged epilogue with TMA stores (fp16 output, no sub-pixel remap).
 //

@@ -285,7 +285,8 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
 //   1 staged TMA stores        : tiles at least 256 channels wide (layer1 conv3 / downsample: 136 -> 104 us)
 //   2 warp-staged coalesced    : everything else, when the 36 KB of staging fit next to the pipeline
 //   0 direct row-per-thread    : fp32 outputs, sub-pixel phases, or no shared memory left (C = 96 halo-patch conv)
-// HRNET_B200_EPI = auto (default) | direct | tma (TMA wherever eligible) | coal (coalesced wherever it fits); read at
+// HRNET_B200_EPI = auto (default) | direct | tma (TMA wherever eligible) | coal (coalesced wherever it fits) |
+// batch (kind 3: direct stores with batched TMEM loads on tiles <= 64 channels, not yet run on hardware); read at
 // plan time.  The staging tiles are carved out of the pipeline's shared memory.
 int epi_policy() {
   const char* e = getenv("HRNET_B200_EPI");
@@ -295,6 +296,7 @@ int epi_policy() {
   if (!strcmp(e, "coal")) return 3;
   if (!strcmp(e, "tma_patch")) return 4;    // experiments: TMA epilogue on every halo-patch conv, auto elsewhere
   if (!strcmp(e, "tma_igemm")) return 5;    // experiments: TMA epilogue on every im2col conv, auto elsewhere
+  if (!strcmp(e, "batch")) return 6;        // experiments: batched TMEM loads (kind 3) on tiles <= 64 channels, auto elsewhere
   return 0;
 }
 // The epilogue staging tiles are carved out of the pipeline's shared memory: re-check that every issuer's ring keeps its
@@ -317,6 +319,10 @@ void choose_epi_impl(Op& op, bool out_f32, bool sub, bool has_res) {
   const int policy = epi_policy();
   if (!op.use_tc || policy == 1 || out_f32 || sub) return;
   const int width = op.use_patch ? op.pp.Cout : op.tc.n_tile;
+  if (policy == 6 && width <= 64 && (op.use_patch ? op.pp.cs : op.tc.cs) == 1) {   // no staging memory needed
+    if (op.use_patch) op.pp.epi_tma = 3; else op.tc.epi = 3;
+    return;
+  }
   // CTA-pair halo-patch convs need the cheap per-warp TMA epilogue to keep up with the halved MMA time
   const bool want_tma = policy == 2 || (policy == 4 && op.use_patch) || (policy == 5 && !op.use_patch) || width >= 256 ||
                         (op.use_patch && op.pp.cs == 2);
