@@ -46,6 +46,14 @@ extern "C" {
 #define HRNET_FLAG_NO_PATCH 16u    /* debug: disable the halo-patch 3x3 kernel (im2col kernel everywhere) */
 #define HRNET_FLAG_GROUP 64u       /* experiment: issue the k-th convs of all branches as one multi-problem kernel (same speed) */
 #define HRNET_FLAG_PARTITION 32u   /* experiment: split the SMs between the concurrent branch chains (slower) */
+#define HRNET_FLAG_NO_CHAIN 128u   /* debug / cross-check: launch the eight convs of a StageModule branch one by one
+                                      instead of as one persistent branch-chain kernel (bit-identical results)     */
+
+/* Tuning knobs of a plan (HrnetDesc.tune[]); 0 = the library's default.  They change speed only, never results. */
+#define HRNET_TUNE_CHAIN_SHARE0 0  /* [0..3] per-mille share of the SMs given to the branch-0..3 chain kernel of a
+                                      StageModule with four branches (three / two branches: renormalised)          */
+#define HRNET_TUNE_CHAIN_GRID_CAP 4 /* upper bound on any chain kernel's grid (experiments)                         */
+#define HRNET_TUNE_COUNT 8
 
 typedef struct HrnetPlan HrnetPlan;
 
@@ -59,6 +67,7 @@ typedef struct HrnetDesc {
   int32_t width;       /* network input width, multiple of 32                       */
   int32_t max_batch;   /* largest n accepted by hrnet_forward                       */
   uint32_t flags;      /* HRNET_FLAG_*                                              */
+  int32_t tune[HRNET_TUNE_COUNT]; /* HRNET_TUNE_*; zero-initialise for the defaults        */
 } HrnetDesc;
 
 /* One weight-carrying layer of the plan; tells the host-side packer which state_dict entries

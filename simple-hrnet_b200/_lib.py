@@ -15,7 +15,7 @@ class HrnetError(RuntimeError):
 class HrnetDesc(ctypes.Structure):
     _fields_ = [("arch", ctypes.c_int32), ("c", ctypes.c_int32), ("nof_joints", ctypes.c_int32),
                 ("height", ctypes.c_int32), ("width", ctypes.c_int32), ("max_batch", ctypes.c_int32),
-                ("flags", ctypes.c_uint32)]
+                ("flags", ctypes.c_uint32), ("tune", ctypes.c_int32 * 8)]
 
 
 class HrnetParamInfo(ctypes.Structure):
@@ -28,6 +28,8 @@ class HrnetParamInfo(ctypes.Structure):
 
 ARCH_HRNET, ARCH_POSERESNET = 0, 1
 FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F32, FLAG_SERIAL, FLAG_NO_PATCH, FLAG_PARTITION, FLAG_GROUP = 1, 2, 4, 8, 16, 32, 64
+FLAG_NO_CHAIN = 128
+TUNE_CHAIN_SHARE0, TUNE_CHAIN_GRID_CAP, TUNE_COUNT = 0, 4, 8
 
 # every symbol include/hrnet_b200.h declares: (name, restype, argtypes)
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t

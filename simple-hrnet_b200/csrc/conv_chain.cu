@@ -1,0 +1,716 @@
+// Branch chains: the eight 3x3 stride-1 convs (4 BasicBlocks, reference models_/modules.py:56-72 instantiated at
+// models_/hrnet.py:15-20) of one StageModule branch run in ONE persistent kernel instead of eight launches.
+//
+// Why: at 64 crops a branch conv is 23 / 6.5 / 1.5 / 0.7 tiles per SM.  Launched one by one, every
+// conv pays a 3-5 us prologue (barrier / TMEM setup, resident weights, first operands) and a tail that cannot overlap
+// its successor (one CTA fills an SM), and the 216- / 108-tile convs of the 24x18 / 12x9 maps waste half of their
+// second / only wave.  Here the tiles of all convs of the chain form ONE ordered ticket sequence (conv-major):
+//
+//   * a CTA draws tickets from a global counter (dynamic scheduling: a CTA only ever waits for tiles with a LOWER
+//     ticket, which are owned by CTAs that are already running -> no deadlock whatever subset of the grid is resident,
+//     e.g. when two forwards or the four branch chains of a module share the SMs);
+//   * tile (conv k, position t) may start when the tiles of conv k-1 that cover its 3x3 halo are stored.  Finished
+//     tiles are counted per UNIT of the output map -- a row of 8x16 tiles of one image (halo-patch kernel) or a
+//     128-pixel M-tile (im2col kernel; one arrival per N-tile): after the epilogue warpgroup's stores a
+//     __threadfence + red.add on `counters[k][unit]`.  The scheduler warp reads the three units u-1, u, u+1 of conv
+//     k-1 with relaxed loads followed by one acquire fence.  The last CTA to exit clears the counters and the ticket
+//     (every other CTA is gone by then), so nothing has to be cleared between forwards or graph replays and any batch
+//     size can follow any other;
+//   * write-after-read hazards on the rotating t / y0 / y1 buffers are covered by the same chain of dependencies (a
+//     tile of conv k+1 depends on every tile of conv k that read the region it overwrites);
+//   * data written earlier in the same launch is read through TMA (L2) or ld.global.cg -- never through L1 / ld.nc.
+//
+// Inside the CTA the pipelines are the ones of conv_igemm_body.cuh / conv3x3_patch_body.cuh (same MMA order, same
+// epilogue arithmetic -> results are bit-identical to the per-conv launches, which is what tests/test_gpu_chain.py
+// asserts), plus a scheduler (warp 3 of the im2col kernel, warp 1 of the halo-patch kernel) that feeds a small ring of
+// tile descriptors to the producer / MMA / epilogue roles.
+#include <algorithm>
+#include <cstdlib>
+
+#include "conv3x3_patch_body.cuh"
+#include "conv_igemm_body.cuh"
+
+namespace hrnet {
+
+constexpr int kChainRing = 4;
+constexpr uint32_t kChainDone = 0xffffffffu;
+
+struct ChainRing {
+  uint64_t full[kChainRing];
+  uint64_t empty[kChainRing];
+  uint32_t info[kChainRing];
+  uint32_t pad[4];
+};
+
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_relaxed_gpu(unsigned* p, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// generic-proxy accesses before / async-proxy (TMA) accesses after, all state spaces
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// A dependency that never arrives would hang the GPU: after ~2 s of polling the CTA traps (launch failure on the host).
+static __device__ __noinline__ void chain_wait_counter_slow(const unsigned* c, unsigned want) {
+  const long long t0 = clock64();
+  while (ld_relaxed_gpu(c) < want) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000ll) {
+      printf("hrnet_b200: chain dependency timeout (block %d counter %p want %u have %u)\n", (int)blockIdx.x, (const void*)c,
+             want, ld_relaxed_gpu(c));
+      __trap();
+    }
+  }
+}
+// Units lo .. hi (at most three) of one conv have all `want` arrivals.  The loads are issued back to back (one L2 round
+// trip); the acquire fence orders everything the caller does afterwards behind the arrivals it has observed.
+__device__ __forceinline__ void chain_wait_units(const unsigned* c, int lo, int hi, unsigned want) {
+  const unsigned v0 = ld_relaxed_gpu(c + lo);
+  const unsigned v1 = lo + 1 <= hi ? ld_relaxed_gpu(c + lo + 1) : want;
+  const unsigned v2 = lo + 2 <= hi ? ld_relaxed_gpu(c + lo + 2) : want;
+  if (v0 < want) chain_wait_counter_slow(c + lo, want);
+  if (v1 < want) chain_wait_counter_slow(c + lo + 1, want);
+  if (v2 < want) chain_wait_counter_slow(c + lo + 2, want);
+  fence_acq_rel_gpu();
+}
+// Ring consumer: every consuming thread walks every entry (tile descriptor or kChainDone), in order.
+struct RingReader {
+  uint32_t full0, empty0, info0;
+  int i;
+  __device__ __forceinline__ void init(ChainRing* r) {
+    full0 = ptx::smem_u32(&r->full[0]); empty0 = ptx::smem_u32(&r->empty[0]); info0 = ptx::smem_u32(&r->info[0]);
+    i = 0;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    const uint32_t slot = (uint32_t)(i % kChainRing);
+    const uint32_t ph = (uint32_t)((i / kChainRing) & 1);
+    ptx::mbar_wait(full0 + 8u * slot, ph);
+    const uint32_t v = lds_volatile_u32(info0 + 4u * slot);
+    ptx::mbar_arrive(empty0 + 8u * slot);
+    ++i;
+    return v;
+  }
+};
+
+// Ring producer side of the scheduler thread.
+struct RingWriter {
+  uint32_t full0, empty0, info0;
+  int i;
+  __device__ __forceinline__ void init(ChainRing* r) {
+    full0 = ptx::smem_u32(&r->full[0]); empty0 = ptx::smem_u32(&r->empty[0]); info0 = ptx::smem_u32(&r->info[0]);
+    i = 0;
+  }
+  __device__ __forceinline__ void acquire_slot() {
+    const uint32_t slot = (uint32_t)(i % kChainRing);
+    const uint32_t ph = (uint32_t)((i / kChainRing) & 1);
+    ptx::mbar_wait(empty0 + 8u * slot, ph ^ 1u);
+  }
+  __device__ __forceinline__ void publish(uint32_t v) {
+    const uint32_t slot = (uint32_t)(i % kChainRing);
+    sts_volatile_u32(info0 + 4u * slot, v);
+    ptx::mbar_arrive(full0 + 8u * slot);     // release at CTA scope: the descriptor is visible to the waiters
+    ++i;
+  }
+};
+
+// Block-wide, after the final __syncthreads: the last CTA of the launch clears the unit counters it and the others used
+// (`nconv` x `units`, row pitch `stride`) and re-arms the ticket.  `flag` is a shared-memory word.
+__device__ __forceinline__ void chain_exit(unsigned* ctrl, unsigned* counters, int nconv, int units, int stride, uint32_t* flag) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *flag = atomicAdd(&ctrl[1], 1u) == gridDim.x - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (*flag == 0u) return;
+  __threadfence();
+  for (int k = 0; k < nconv; ++k)
+    for (int u = threadIdx.x; u < units; u += blockDim.x) counters[(size_t)k * stride + u] = 0u;
+  if (threadIdx.x == 0) { ctrl[0] = 0u; ctrl[1] = 0u; }
+}
+
+// Epilogue of one row with coherent residual loads (ld.global.cg: the residual was written earlier in this launch by
+// another SM; .nc / L1-cached loads could return a stale line).  Arithmetic identical to epi_store_row.
+__device__ __forceinline__ void chain_load_residual(uint4 (&r)[8], const EpiRow& e, int c_begin) {
+  if (e.residual == nullptr || !e.valid) return;
+  const uint4* rp = reinterpret_cast<const uint4*>(e.residual + e.row_off + c_begin);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (c_begin + 8 * i < e.ncols) r[i] = __ldcg(rp + i);
+}
+__device__ __forceinline__ void chain_store_row(uint4 (&r)[8], const EpiRow& e, uint32_t t_row) {
+  for (int c64 = 0; c64 < e.ncols; c64 += 64) {
+    uint4 cur[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur[i] = r[i];
+    if (c64 + 64 < e.ncols) chain_load_residual(r, e, c64 + 64);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c64 + 32 * h;
+      if (c < e.ncols) {                       // warp-uniform
+        uint32_t v0[16], v1[16];
+        const bool two = c + 16 < e.ncols;     // warp-uniform
+        ptx::tmem_ld16(t_row + (uint32_t)c, v0);
+        if (two) ptx::tmem_ld16(t_row + (uint32_t)(c + 16), v1);
+        ptx::tmem_ld_wait();
+        if (e.valid) {
+          epi_cols16(v0, cur[4 * h], cur[4 * h + 1], e, c);
+          if (two) epi_cols16(v1, cur[4 * h + 2], cur[4 * h + 3], e, c + 16);
+        }
+      }
+    }
+  }
+}
+
+// After a warpgroup has stored its tile: make the stores visible GPU-wide and count the tile in its unit.
+__device__ __forceinline__ void chain_publish_tile(unsigned* counter, int bar_id, bool leader) {
+  ptx::bar_sync(bar_id, 128);                  // all four warps of the warpgroup have issued their stores
+  if (leader) {
+    fence_proxy_async_all();                   // generic-proxy stores before later async-proxy (TMA) reads
+    __threadfence();
+    red_add_relaxed_gpu(counter, 1u);
+  }
+}
+
+// =====================================================================================================================
+// im2col chain (branches whose map does not tile into 8x16 patches / whose weights do not fit: C = 192, 384 at W48)
+// =====================================================================================================================
+constexpr int kCIThreads = 384;
+
+struct __align__(8) ChainIgemmBars {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  ChainRing ring;
+  uint32_t tmem_base;
+  uint32_t pad;
+  uint32_t kb_tab[kMaxKBlocks];
+};
+
+__global__ void __launch_bounds__(kCIThreads, 1)
+conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const ChainIgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int warp = ptx::warp_idx_uniform();
+  const int lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
+
+  const int a_stage_bytes = p.bps * p.a_blk_bytes;
+  const int b_stage_bytes = p.bps * p.b_blk_bytes;
+  const int stage_bytes = a_stage_bytes + b_stage_bytes;
+  ChainIgemmBars* bars = reinterpret_cast<ChainIgemmBars*>(smem_aligned + (size_t)p.stages * stage_bytes);
+  const int nstages_k = (p.nkb + p.bps - 1) / p.bps;
+  const int tiles_per_conv = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.nconv * tiles_per_conv;
+
+  if (warp == 0 && lane == 0) {
+    for (int k = 0; k < p.nconv; ++k) { ptx::prefetch_tmap(&maps.a[k]); ptx::prefetch_tmap(&maps.b[k]); }
+    for (int i = 0; i < p.stages; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars->full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128u);
+    }
+    for (int i = 0; i < kChainRing; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars->ring.full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->ring.empty[i]), 2u + 1u + 256u);   // producers, MMA issuer, epilogue threads
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+  uint32_t* kb_tab = bars->kb_tab;
+  if (warp == 3) {
+    for (int kb = lane; kb < p.nkb; kb += 32) {
+      const int tap = kb / p.cpt;
+      const int c0 = (kb - tap * p.cpt) * kKC;
+      const int r = tap / 3;
+      const int sx = tap - r * 3;
+      kb_tab[kb] = (uint32_t)(tap * p.C + c0) | ((uint32_t)c0 << 15) | ((uint32_t)sx << 27) | ((uint32_t)r << 29);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::pdl_wait();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const long long t_begin = p.dbg ? clock64() : 0;
+
+  if (warp == 3) {
+    // ===================================================================== scheduler
+    if (ptx::elect_one()) {
+      RingWriter rw; rw.init(&bars->ring);
+      long long dbg_dep = 0; int dbg_tiles = 0;
+      unsigned next = atomicAdd(&p.ctrl[0], 1u);
+      for (;;) {
+        const unsigned t = next;
+        rw.acquire_slot();
+        if (t >= (unsigned)total_tiles) { rw.publish(kChainDone); break; }
+        next = atomicAdd(&p.ctrl[0], 1u);            // in flight while this tile's dependencies are polled
+        const int k = (int)t / tiles_per_conv;
+        const int r = (int)t - k * tiles_per_conv;
+        const int mt = r / p.n_tiles;
+        const int nt = r - mt * p.n_tiles;
+        if (k > 0) {
+          // rows [m0 - (OW + 1), m0 + 127 + OW + 1] of conv k-1: OW + 1 < 128, so M-tiles mt-1 .. mt+1 (all N-tiles)
+          const long long tq = p.dbg ? clock64() : 0;
+          chain_wait_units(p.counters + (size_t)(k - 1) * p.unit_stride, max(mt - 1, 0), min(mt + 1, p.m_tiles - 1),
+                           (unsigned)p.n_tiles);
+          if (p.dbg) dbg_dep += clock64() - tq;
+        }
+        rw.publish(((uint32_t)k << 28) | ((uint32_t)nt << 24) | (uint32_t)mt);
+        ++dbg_tiles;
+      }
+      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_dep; p.dbg[blockIdx.x * 8 + 1] = dbg_tiles; }
+    }
+    __syncwarp();
+  } else if (warp < 2) {
+    // ===================================================================== TMA producers (alternate stage loads)
+    if (ptx::elect_one()) {
+      RingReader rr; rr.init(&bars->ring);
+      int L = 0;
+      int stage = warp;
+      uint32_t phase = 0;
+      for (;;) {
+        const uint32_t info = rr.next();
+        if (info == kChainDone) break;
+        const int k = (int)(info >> 28), nt = (int)((info >> 24) & 15u), mt = (int)(info & 0xffffffu);
+        const int m0 = mt * kTileM;
+        const int img = m0 / p.OHW;
+        const int rem = m0 - img * p.OHW;
+        const int oh0 = rem / p.OW;
+        const int ow0 = rem - oh0 * p.OW;
+        const int bw = ow0 - 1, bh = oh0 - 1;
+        const int n0 = nt * p.n_tile;
+        fence_proxy_async_all();       // the scheduler's acquire (generic proxy) before this tile's TMA reads
+        for (int ks = 0; ks < nstages_k; ++ks, ++L) {
+          if ((L & 1) != warp) continue;
+          const int kb0 = ks * p.bps;
+          const int nblk = min(p.bps, p.nkb - kb0);
+          ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
+          const uint32_t full = ptx::smem_u32(&bars->full[stage]);
+          const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
+          const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
+          ptx::mbar_expect_tx(full, (uint32_t)(nblk * (kTileM * kKC * 2 + p.n_tile * kKC * 2)));
+          for (int j = 0; j < nblk; ++j) {
+            const uint32_t e = kb_tab[kb0 + j];
+            ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &maps.a[k], full, (int)((e >> 15) & 0xfffu), bw, bh,
+                                    img, (uint16_t)((e >> 27) & 3u), (uint16_t)(e >> 29));
+            ptx::tma_load_2d(b_dst + (uint32_t)(j * p.b_blk_bytes), &maps.b[k], full, (int)(e & 0x7fffu), n0);
+          }
+          stage += 2;
+          if (stage >= p.stages) { stage -= p.stages; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ===================================================================== MMA issuer
+    if (ptx::elect_one()) {
+      RingReader rr; rr.init(&bars->ring);
+      const uint32_t idesc = ptx::umma_idesc_f16(kTileM, p.n_tile);
+      const int ctail = p.C - (p.cpt - 1) * kKC;
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ready = false;
+      for (int it = 0;; ++it) {
+        const uint32_t info = rr.next();
+        if (info == kChainDone) break;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+        int cblk = 0;
+        for (int ks = 0; ks < nstages_k; ++ks) {
+          const int kb0 = ks * p.bps;
+          const int nblk = min(p.bps, p.nkb - kb0);
+          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
+          const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
+          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->full[nstage]), nphase);
+          for (int j = 0; j < nblk; ++j) {
+            const int nk = (cblk == p.cpt - 1 ? ctail : kKC) / 16;
+            cblk = cblk + 1 == p.cpt ? 0 : cblk + 1;
+            const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)(j * p.a_blk_bytes), 128u, 1024u);
+            const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), 128u, 1024u);
+            const uint32_t first = (uint32_t)((kb0 + j) != 0);
+            switch (nk) {
+              case 4: issue_k16<4, false>(d_tmem, adesc, bdesc, idesc, first); break;
+              case 3: issue_k16<3, false>(d_tmem, adesc, bdesc, idesc, first); break;
+              case 2: issue_k16<2, false>(d_tmem, adesc, bdesc, idesc, first); break;
+              default: issue_k16<1, false>(d_tmem, adesc, bdesc, idesc, first); break;
+            }
+          }
+          ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
+          stage = nstage; phase = nphase; ready = nready;
+        }
+        ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (two warpgroups, alternating tiles)
+    const int g = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool leader = (q == 0) && (lane == 0);
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile);
+    RingReader rr; rr.init(&bars->ring);
+    for (int it = 0;; ++it) {
+      const uint32_t info = rr.next();
+      if (info == kChainDone) break;
+      if ((it & 1) != g) continue;
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int k = (int)(info >> 28), nt = (int)((info >> 24) & 15u), mt = (int)(info & 0xffffffu);
+      const ChainConv& cv = p.conv[k];
+      const int m = mt * kTileM + row;
+      const int n0 = nt * p.n_tile;
+      EpiRow e;
+      e.s_scale = cv.scale; e.s_bias = cv.bias; e.residual = cv.residual; e.out = cv.out;
+      e.row_off = (size_t)m * p.C + n0;
+      e.ch0 = n0; e.ncols = p.n_tile; e.relu = cv.relu; e.out_f32 = 0; e.valid = m < p.M_total;
+      uint4 rres[8];
+      chain_load_residual(rres, e, 0);
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
+      ptx::tc_fence_after_sync();
+      chain_store_row(rres, e, t_row);
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
+      chain_publish_tile(p.counters + (size_t)k * p.unit_stride + mt, 1 + g, leader);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin;
+  chain_exit(p.ctrl, p.counters, p.nconv, p.m_tiles, p.unit_stride, &bars->pad);
+}
+
+// =====================================================================================================================
+// halo-patch chain (C = 48, 96 at W48; C = 32, 64 at W32): resident weights are swapped at every conv boundary
+// =====================================================================================================================
+// Warp 0 producer (one TMA per channel chunk of a tile: a single issuing thread keeps up, unlike the im2col kernel's
+// per-k-block loads), warp 1 scheduler, warps 2-3 MMA issuers (3 only when pp.mma_warps == 2), warps 4-11 epilogue.
+// (A 13th warp would put four warps on one scheduler partition and cap every thread at 128 registers.)
+constexpr int kCPThreads = 384;
+
+struct __align__(8) ChainPatchBars {
+  uint64_t b_full;          // resident weights of the current conv have landed (one phase per conv of this CTA)
+  uint64_t b_empty;         // every MMA issuer has retired its MMAs on the previous conv's weights
+  uint64_t a_full[kPMaxSlots];
+  uint64_t a_empty[kPMaxSlots];
+  uint64_t tmem_full[4];
+  uint64_t tmem_empty[4];
+  ChainRing ring;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kCPThreads, 1)
+conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const ChainPatchParams cp) {
+  extern __shared__ uint8_t smem_raw[];
+  const ConvPatchParams& p = cp.pp;
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_aligned = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  const int warp = ptx::warp_idx_uniform();
+  const int lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
+
+  const uint32_t b_base = smem_base;
+  const uint32_t a_base = smem_base + (uint32_t)p.b_bytes;
+  ChainPatchBars* bars = reinterpret_cast<ChainPatchBars*>(smem_aligned + (size_t)p.b_bytes + (size_t)p.nslots * p.slot_bytes);
+  const int n_issuers = p.mma_warps == 2 ? 2 : 1;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int total_tiles = cp.nconv * p.total_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int k = 0; k < cp.nconv; ++k) {
+      ptx::prefetch_tmap(&maps.a[k]); ptx::prefetch_tmap(&maps.b[k][0]); ptx::prefetch_tmap(&maps.b[k][1]);
+    }
+    ptx::mbar_init(ptx::smem_u32(&bars->b_full), 1);
+    ptx::mbar_init(ptx::smem_u32(&bars->b_empty), (uint32_t)n_issuers);
+    for (int i = 0; i < p.nslots; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[i]), 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128u);
+    }
+    for (int i = 0; i < kChainRing; ++i) {
+      ptx::mbar_init(ptx::smem_u32(&bars->ring.full[i]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->ring.empty[i]), 1u + (uint32_t)n_issuers + 256u);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+  const long long t_begin = cp.dbg ? clock64() : 0;
+
+  // bytes of one conv's resident weight set
+  uint32_t btx = 0;
+  for (int j = 0; j < p.nchunks; ++j) btx += 9u * (uint32_t)(p.Cout * p.bkc[j] * 2);
+
+  if (warp == 1) {
+    // ===================================================================== scheduler
+    ptx::pdl_wait();
+    if (ptx::elect_one()) {
+      RingWriter rw; rw.init(&bars->ring);
+      long long dbg_dep = 0; int dbg_tiles = 0;
+      unsigned next = atomicAdd(&cp.ctrl[0], 1u);
+      for (;;) {
+        const unsigned t = next;
+        rw.acquire_slot();
+        if (t >= (unsigned)total_tiles) { rw.publish(kChainDone); break; }
+        next = atomicAdd(&cp.ctrl[0], 1u);
+        const int k = (int)t / p.total_tiles;
+        const int tile = (int)t - k * p.total_tiles;
+        if (k > 0) {
+          // the 10 x 18 input patch of an 8 x 16 tile touches the 3 x 3 neighbouring tiles of the same image: tile rows
+          // th-1 .. th+1 of that image must be complete (tiles_w arrivals each)
+          const long long tq = cp.dbg ? clock64() : 0;
+          const int img = tile / tiles_per_img;
+          const int th = (tile - img * tiles_per_img) / p.tiles_w;
+          chain_wait_units(cp.counters + (size_t)(k - 1) * cp.unit_stride + img * p.tiles_h, max(th - 1, 0),
+                           min(th + 1, p.tiles_h - 1), (unsigned)p.tiles_w);
+          if (cp.dbg) dbg_dep += clock64() - tq;
+        }
+        rw.publish(((uint32_t)k << 28) | (uint32_t)tile);
+        ++dbg_tiles;
+      }
+      if (cp.dbg) { cp.dbg[blockIdx.x * 8 + 0] = dbg_dep; cp.dbg[blockIdx.x * 8 + 1] = dbg_tiles; }
+    }
+    __syncwarp();
+  } else if (warp == 0) {
+    // ===================================================================== TMA producer
+    // Also owns the resident weights: conv 0's before the grid dependency resolves (constants), then a reload whenever
+    // the ticket stream of this CTA moves on to another conv.
+    if (ptx::elect_one()) {
+      const uint32_t bfull = ptx::smem_u32(&bars->b_full);
+      const uint32_t bempty = ptx::smem_u32(&bars->b_empty);
+      auto load_weights = [&](int k) {
+        ptx::mbar_expect_tx(bfull, btx);
+        for (int j = 0; j < p.nchunks; ++j)
+          for (int t = 0; t < 9; ++t)
+            ptx::tma_load_2d(b_base + (uint32_t)(p.boff[j] + t * p.bblk[j]), &maps.b[k][p.mapi[j] ? 1 : 0], bfull,
+                             t * p.Cin + p.c0[j], 0);
+      };
+      // The first conv this CTA works on is not known before its first ticket; conv 0 is the common case (always true
+      // for the first gridDim tickets), so its weights are requested ahead of the grid dependency.
+      int cur_k = 0;
+      int nswitch = 0;                      // weight reloads so far
+      load_weights(0);
+      ptx::pdl_wait();
+      RingReader rr; rr.init(&bars->ring);
+      // Two issuers: tiles of parity w run through pipeline w (issuer w, epilogue warpgroup w, slots [w * ring, (w+1) * ring)).
+      const int nw = n_issuers;
+      const int ring = nw == 2 ? p.nslots / 2 : p.nslots;
+      int L0 = 0, L1 = 0;                   // chunk loads issued into each pipeline's slot ring
+      for (int it = 0;; ++it) {
+        const uint32_t info = rr.next();
+        if (info == kChainDone) break;
+        const int k = (int)(info >> 28);
+        const int tile = (int)(info & 0x0fffffffu);
+        if (k != cur_k) {
+          cur_k = k;
+          // the MMAs of every earlier tile of this CTA (all issuers) must have retired before the overwrite
+          ptx::mbar_wait(bempty, (uint32_t)(nswitch & 1));
+          load_weights(k);
+          ++nswitch;
+        }
+        const int w = nw == 2 ? (it & 1) : 0;
+        const int sbase = w * ring;
+        const int img = tile / tiles_per_img;
+        const int rem = tile - img * tiles_per_img;
+        const int th = rem / p.tiles_w;
+        const int tw = rem - th * p.tiles_w;
+        fence_proxy_async_all();       // the scheduler's acquire (generic proxy) before this tile's TMA reads
+        for (int j = 0; j < p.nchunks; ++j) {
+          const int L = w ? L1++ : L0++;
+          const int slot = sbase + L % ring;
+          const uint32_t phase = (uint32_t)((L / ring) & 1);
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[slot]), phase ^ 1u);
+          const uint32_t full = ptx::smem_u32(&bars->a_full[slot]);
+          ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 128));
+          ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a[k], full, p.c0[j], tw * kPatchTW - 1,
+                           th * kPatchTH - 1, img);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2 || (warp == 3 && n_issuers == 2)) {
+    // ===================================================================== MMA issuer(s)
+    const int mw = warp - 2;
+    if (ptx::elect_one()) {
+      RingReader rr; rr.init(&bars->ring);
+      const uint32_t idesc = ptx::umma_idesc_f16(128, p.Cout);
+      const uint32_t bfull = ptx::smem_u32(&bars->b_full);
+      const uint32_t bempty = ptx::smem_u32(&bars->b_empty);
+      const int nw = n_issuers;
+      const int ring = nw == 2 ? p.nslots / 2 : p.nslots;
+      const int sbase = nw == 2 ? mw * ring : 0;
+      int slot = 0;
+      uint32_t phase = 0;
+      bool ready = false;
+      int cur_k = 0;
+      int nswitch = 0;
+      ptx::mbar_wait(bfull, 0);               // conv 0's weights
+      for (int it = 0;; ++it) {
+        const uint32_t info = rr.next();
+        if (info == kChainDone) break;
+        const int k = (int)(info >> 28);
+        if (k != cur_k) {
+          // every issuer walks every ring entry, so both see every conv switch of this CTA, in order: retire the
+          // MMAs that read the old weights, then wait for the new set (each b_full phase is waited exactly once)
+          cur_k = k;
+          ptx::mma_commit(bempty);
+          ++nswitch;
+          ptx::mbar_wait(bfull, (uint32_t)(nswitch & 1));
+          ptx::tc_fence_after_sync();
+        }
+        if (nw == 2 && (it & 1) != mw) continue;
+        const int acc = it & (p.nacc - 1);
+        const uint32_t acc_phase = (uint32_t)((it >> p.nacc_log2) & 1);
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+        for (int j = 0; j < p.nchunks; ++j) {
+          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->a_full[sbase + slot]), phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_slot = a_base + (uint32_t)((sbase + slot) * p.slot_bytes);
+          const uint32_t brow = (uint32_t)p.bkc[j] * 2u;
+          const int nk = p.kreal[j] / 16;
+          int nslot = slot + 1;
+          uint32_t nphase = phase;
+          if (nslot == ring) { nslot = 0; nphase ^= 1u; }
+          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->a_full[sbase + nslot]), nphase);
+          const uint64_t a0 = ptx::umma_desc_kmajor(a_slot, 128u, (uint32_t)kPatchPW * 128u);
+          const uint64_t b0 = ptx::umma_desc_kmajor(b_base + (uint32_t)p.boff[j], brow, 8u * brow);
+          const uint32_t bstep = (uint32_t)p.bblk[j] >> 4;
+          const uint32_t first = (uint32_t)(j != 0);
+          switch (nk) {
+            case 4: issue_taps<4, false>(d_tmem, a0, b0, bstep, idesc, first); break;
+            case 3: issue_taps<3, false>(d_tmem, a0, b0, bstep, idesc, first); break;
+            case 2: issue_taps<2, false>(d_tmem, a0, b0, bstep, idesc, first); break;
+            default: issue_taps<1, false>(d_tmem, a0, b0, bstep, idesc, first); break;
+          }
+          ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sbase + slot]));
+          slot = nslot; phase = nphase; ready = nready;
+        }
+        ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue (two warpgroups, alternating tiles)
+    const int g = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int dh = row >> 3, dw = row & 7;
+    const bool leader = (q == 0) && (lane == 0);
+    ptx::pdl_wait();
+    RingReader rr; rr.init(&bars->ring);
+    for (int it = 0;; ++it) {
+      const uint32_t info = rr.next();
+      if (info == kChainDone) break;
+      if ((it & 1) != g) continue;
+      const int k = (int)(info >> 28);
+      const int tile = (int)(info & 0x0fffffffu);
+      const ChainConv& cv = cp.conv[k];
+      const int acc = it & (p.nacc - 1);
+      const uint32_t acc_phase = (uint32_t)((it >> p.nacc_log2) & 1);
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int th = rem / p.tiles_w;
+      const int tw = rem - th * p.tiles_w;
+      const int oh = th * kPatchTH + dh, ow = tw * kPatchTW + dw;
+      EpiRow e;
+      e.s_scale = cv.scale; e.s_bias = cv.bias; e.residual = cv.residual; e.out = cv.out;
+      e.row_off = (((size_t)img * p.H + oh) * p.W + ow) * p.Cout;
+      e.ch0 = 0; e.ncols = p.Cout; e.relu = cv.relu; e.out_f32 = 0; e.valid = oh < p.H && ow < p.W;
+      uint4 rres[8];
+      chain_load_residual(rres, e, 0);
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
+      ptx::tc_fence_after_sync();
+      chain_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout));
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
+      chain_publish_tile(cp.counters + (size_t)k * cp.unit_stride + img * p.tiles_h + th, 1 + g, leader);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+  if (cp.dbg && threadIdx.x == 0) cp.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin;
+  chain_exit(cp.ctrl, cp.counters, cp.nconv, p.N * p.tiles_h, cp.unit_stride, &bars->pad);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+cudaError_t conv_chain_set_attributes(int max_smem) {
+  cudaError_t e = cudaFuncSetAttribute(conv_chain_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_chain_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  return e;
+}
+
+static bool chain_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("HRNET_B200_NO_PDL") ? 0 : 1;
+  return v == 1;
+}
+
+template <typename K, typename M, typename P>
+static cudaError_t launch_chain(K kernel, const M& maps, const P& p, int threads, int smem_bytes, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  int na = 0;
+  if (chain_pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = (unsigned)na;
+  return cudaLaunchKernelEx(&cfg, kernel, maps, p);
+}
+
+cudaError_t launch_chain_igemm(const ChainIgemmMaps& maps, const ChainIgemmParams& p, int smem_bytes, int grid, cudaStream_t st) {
+  return launch_chain(conv_chain_igemm_kernel, maps, p, kCIThreads, smem_bytes, grid, st);
+}
+cudaError_t launch_chain_patch(const ChainPatchMaps& maps, const ChainPatchParams& p, int smem_bytes, int grid, cudaStream_t st) {
+  return launch_chain(conv_chain_patch_kernel, maps, p, kCPThreads, smem_bytes, grid, st);
+}
+
+}  // namespace hrnet

@@ -119,6 +119,46 @@ struct ConvSimtParams {
   void* out;
 };
 
+// ---- branch chains (conv_chain.cu): the eight 3x3 convs of one StageModule branch in ONE persistent kernel ----------
+// Tiles of all convs form one ordered ticket sequence (conv-major); a CTA draws tickets from a global counter and a tile
+// of conv k starts once the tiles of conv k-1 covering its 3x3 halo carry this launch's epoch stamp.
+constexpr int kChainMaxConv = 8;
+struct ChainConv {
+  const float* scale;
+  const float* bias;
+  const __half* residual;    // nullptr or NHWC fp16 (written earlier in the same launch: read with ld.global.cg)
+  __half* out;
+  int relu;
+  int pad_;
+};
+// control words of one chain in global memory: [0] ticket counter, [1] exited-CTA counter.
+// counters[conv * unit_stride + unit] = finished tiles of that unit (a row of 8x16 tiles of one image / a 128-pixel
+// M-tile); the last CTA of a launch clears what the launch used.
+struct ChainIgemmParams {
+  int nconv;
+  int M_total, OH, OW, OHW, C;
+  int cpt, nkb, bps, n_tile, n_tiles, m_tiles, stages, tmem_cols, a_blk_bytes, b_blk_bytes;
+  int unit_stride;           // counters per conv (M-tiles at max batch)
+  unsigned* ctrl;
+  unsigned* counters;
+  long long* dbg;            // optional per-CTA counters (8 x int64 per CTA)
+  ChainConv conv[kChainMaxConv];
+};
+struct ChainIgemmMaps { CUtensorMap a[kChainMaxConv], b[kChainMaxConv]; };
+struct ChainPatchParams {
+  int nconv;
+  ConvPatchParams pp;        // geometry / shared-memory layout common to all convs of the chain (scale .. out unused)
+  int unit_stride;           // counters per conv (tile rows at max batch)
+  unsigned* ctrl;
+  unsigned* counters;
+  long long* dbg;
+  ChainConv conv[kChainMaxConv];
+};
+struct ChainPatchMaps { CUtensorMap a[kChainMaxConv]; CUtensorMap b[kChainMaxConv][2]; };
+cudaError_t launch_chain_igemm(const ChainIgemmMaps& maps, const ChainIgemmParams& p, int smem_bytes, int grid, cudaStream_t st);
+cudaError_t launch_chain_patch(const ChainPatchMaps& maps, const ChainPatchParams& p, int smem_bytes, int grid, cudaStream_t st);
+cudaError_t conv_chain_set_attributes(int max_smem);
+
 struct FuseParams {
   int N, H, W, C, nsrc, relu;
   const void* src[4];
@@ -146,6 +186,7 @@ struct Op {
   double work = 0;             // estimated SM-cycles (CTA split of grouped launches)
   float sm_frac = 1.f;         // share of the SMs this op's persistent grid may occupy (branch-level SM partitioning)
   int group = -1;              // ops with the same group id run concurrently on different streams and split the SMs
+  int chain = -1, chain_pos = 0;   // branch chain (conv_chain.cu) this conv belongs to / its position in it
   // tcgen05 path
   bool use_tc = false;
   ConvTcCfg tc;

@@ -36,12 +36,30 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 using namespace hrnet;
 
+// One branch chain (conv_chain.cu): the eight 3x3 convs of a StageModule branch issued as one persistent kernel.
+struct ChainInfo {
+  std::vector<int> ops;            // member convs, in execution order
+  int module = -1, branch = 0;
+  bool enabled = false;            // eligible and not disabled by a flag
+  bool patch = false;              // halo-patch kernel (else im2col kernel)
+  int smem = 0;
+  int share = 0;                   // per mille of the SMs inside the forward: a module's chains run side by side
+  int grid = 0;                    // ... resolved to CTAs by hrnet_plan_bind
+  double cost = 0;                 // estimated SM-cycles of the whole chain (grid split)
+  int flag_stride = 0;             // unit counters per conv (at max batch)
+  size_t ctrl_off = 0, flags_off = 0;   // bytes into the activation workspace
+  ChainIgemmMaps imaps;            // filled by hrnet_plan_bind
+  ChainPatchMaps pmaps;
+};
+
 struct HrnetPlan {
   HrnetDesc desc{};
   std::vector<TensorInfo> tensors;
   std::vector<ParamInfo> params;
   std::vector<int> param_kind, param_a, param_b;  // deconv sub-pixel phases
   std::vector<Op> ops;
+  std::vector<ChainInfo> chains;
+  size_t sync_off = 0, sync_bytes = 0;   // chain control words + tile flags (zeroed by hrnet_plan_bind)
   size_t act_bytes = 0, weight_bytes = 0;
   int t_input = -1, t_heatmaps = -1;
   int Hh = 0, Wh = 0;
@@ -147,7 +165,7 @@ struct Builder {
   }
 };
 
-void choose_tc_cfg(Op& op, uint32_t flags) {
+void choose_tc_cfg(Op& op, uint32_t flags, int max_nt = 256) {
   op.use_tc = false;
   if (flags & HRNET_FLAG_FORCE_SIMT) return;
   if (op.kind != OP_CONV) return;
@@ -156,9 +174,9 @@ void choose_tc_cfg(Op& op, uint32_t flags) {
   ConvTcCfg c;
   c.kc = 64;   // 128-byte swizzled k-blocks; a channel tail is zero-filled by TMA and skipped by the MMA loop
   int nt = op.cout;
-  if (nt > 256) {
+  if (nt > max_nt) {
     int d = 2;
-    while (op.cout % d || (op.cout / d) > 256 || (op.cout / d) % 16) ++d;
+    while (op.cout % d || (op.cout / d) > max_nt || (op.cout / d) % 16) ++d;
     nt = op.cout / d;
   }
   c.n_tile = nt;
@@ -414,6 +432,11 @@ int build_hrnet(HrnetPlan& P) {
         ybuf[i] = {b.new_tensor(arena, ti.C, ti.H, ti.W), b.new_tensor(arena, ti.C, ti.H, ti.W)};
         cur[i] = xs[i];
       }
+      const int chain_base = (int)P.chains.size();
+      for (int i = 0; i < S; ++i) {
+        ChainInfo ci; ci.module = module_idx; ci.branch = i;
+        P.chains.push_back(ci);
+      }
       for (int k = 0; k < 4; ++k) {
         for (int half = 0; half < 2; ++half) {
           const int grp = grp_counter++;
@@ -426,6 +449,9 @@ int build_hrnet(HrnetPlan& P) {
               b.conv(p + ".conv2", p + ".conv2", p + ".bn2", tbuf[i], C, 3, 1, true, cur[i], ybuf[i][k & 1], arena, i);
             P.ops.back().group = module_idx;
             P.ops.back().grp = grp;
+            P.ops.back().chain = chain_base + i;
+            P.ops.back().chain_pos = 2 * k + half;
+            P.chains[chain_base + i].ops.push_back((int)P.ops.size() - 1);
           }
         }
         for (int i = 0; i < S; ++i) cur[i] = ybuf[i][k & 1];
@@ -584,11 +610,85 @@ int build_poseresnet(HrnetPlan& P) {
   return 0;
 }
 
+// Branch chains: which chains run as one kernel, their shared-memory needs, the tile-flag region in the workspace, the
+// "all chains of a module start together" dependencies and each chain's share of the SMs.
+void plan_chains(HrnetPlan& P) {
+  const uint32_t off_flags = HRNET_FLAG_NO_CHAIN | HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_GROUP | HRNET_FLAG_PARTITION;
+  const bool want = !(P.desc.flags & off_flags);
+  size_t cur = (P.act_bytes + 1023) / 1024 * 1024;
+  P.sync_off = cur;
+  for (auto& ch : P.chains) {
+    ch.enabled = false;
+    if (!want || ch.ops.empty() || (int)ch.ops.size() > kChainMaxConv) continue;
+    const Op& o0 = P.ops[ch.ops[0]];
+    bool ok = o0.use_tc && o0.k == 3 && o0.stride == 1 && o0.pad == 1 && o0.cin == o0.cout;
+    for (int i : ch.ops) {
+      const Op& o = P.ops[i];
+      ok = ok && o.use_tc && o.use_patch == o0.use_patch && o.cin == o0.cin && o.cout == o0.cout && o.k == 3 &&
+           o.stride == 1 && P.tensors[o.in].H == P.tensors[o0.in].H && P.tensors[o.in].W == P.tensors[o0.in].W &&
+           P.tensors[o.out].dtype == DT_F16;
+      if (o.use_patch) ok = ok && o.pp.cs == 1 && !o.pp.b_stream && o.pp.epi_tma == 0;
+      else ok = ok && o.tc.cs == 1 && o.tc.epi == 0 && o.tc.n_tile <= 256 && o.cout / o.tc.n_tile <= 15;
+    }
+    if (!ok) continue;
+    ch.enabled = true;
+    ch.patch = o0.use_patch;
+    const TensorInfo& ti = P.tensors[o0.in];
+    const double k16 = 9.0 * ((o0.cin + 15) / 16);
+    if (ch.patch) {
+      ch.smem = o0.patch_smem;
+      ch.flag_stride = P.desc.max_batch * o0.pp.tiles_h;             // one counter per row of tiles of an image
+      ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * o0.work;
+    } else {
+      for (int i : ch.ops) P.ops[i].tc.mma_warps = 1;
+      ch.smem = o0.tc.smem_bytes;
+      const int n_tiles = o0.cout / o0.tc.n_tile;
+      const int m_tiles = (P.desc.max_batch * ti.H * ti.W + 127) / 128;
+      ch.flag_stride = m_tiles;                                      // one counter per M-tile (n_tiles arrivals)
+      // measured inside the per-conv kernels: ~200 clk per K16 step of a 128 x 192 tile (profiles/r01_exp_gridcap_pair_sweep.log)
+      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * (200.0 * o0.tc.n_tile / 192.0);
+    }
+    ch.ctrl_off = cur; cur += 256;
+    ch.flags_off = cur; cur += ((size_t)ch.ops.size() * ch.flag_stride * 4 + 255) / 256 * 256;
+  }
+  P.sync_bytes = cur - P.sync_off;
+  P.act_bytes = cur;
+  for (auto& ch : P.chains)
+    if (!ch.enabled) for (int i : ch.ops) { P.ops[i].chain = -1; P.ops[i].chain_pos = 0; }
+  // The chains of a module share the SMs (grids sum to the SM count), so they must start together: while some of them
+  // still waited for the previous module's exchange unit, that unit's ordinary persistent kernels would only find the
+  // SMs the early chains left over.  Every chain's first conv therefore depends on everything any of them depends on.
+  std::map<int, std::vector<int>> by_module;
+  for (size_t c = 0; c < P.chains.size(); ++c) if (P.chains[c].enabled) by_module[P.chains[c].module].push_back((int)c);
+  for (auto& kv : by_module) {
+    std::vector<int> deps;
+    for (int c : kv.second)
+      for (int dpi : P.ops[P.chains[c].ops[0]].deps)
+        if (std::find(deps.begin(), deps.end(), dpi) == deps.end()) deps.push_back(dpi);
+    for (int c : kv.second) P.ops[P.chains[c].ops[0]].deps = deps;
+    // grid split: proportional to the estimated cost (HRNET_TUNE_CHAIN_SHARE* overrides, per mille of the SM count);
+    // resolved to CTA counts at bind time, when the SM count is known
+    double tot = 0;
+    for (int c : kv.second) tot += P.chains[c].cost;
+    double tsum = 0;
+    bool tuned = true;
+    for (int c : kv.second) { const int t = P.desc.tune[HRNET_TUNE_CHAIN_SHARE0 + std::min(P.chains[c].branch, 3)]; if (t <= 0) tuned = false; tsum += t; }
+    for (int c : kv.second) {
+      ChainInfo& ch = P.chains[c];
+      const double share = tuned ? P.desc.tune[HRNET_TUNE_CHAIN_SHARE0 + std::min(ch.branch, 3)] / tsum : ch.cost / tot;
+      ch.share = std::max(1, (int)std::lround(share * 1000.0));
+    }
+  }
+}
+
 void finalize_schedule(HrnetPlan& P) {
+  const bool chain_cfg = !(P.desc.flags & (HRNET_FLAG_NO_CHAIN | HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_GROUP | HRNET_FLAG_PARTITION));
   for (auto& op : P.ops) {
-    choose_tc_cfg(op, P.desc.flags);
+    // chain members keep N tiles <= 192 wide (two accumulators in TMEM, direct epilogue) and the direct epilogue
+    const bool cand = chain_cfg && op.chain >= 0;
+    choose_tc_cfg(op, P.desc.flags, cand ? 192 : 256);
     if (op.use_tc && op.in >= 0) choose_patch_cfg(op, P.tensors[op.in].H, P.tensors[op.in].W, P.desc.flags);
-    if (op.use_tc && op.out >= 0 && !(P.desc.flags & HRNET_FLAG_GROUP))
+    if (op.use_tc && op.out >= 0 && !(P.desc.flags & HRNET_FLAG_GROUP) && !cand)
       choose_epi(op, P.tensors[op.out].dtype == DT_F32, op.pad >= 100, op.res >= 0);
   }
   // (Opt-in, HRNET_FLAG_PARTITION; measured SLOWER than letting every kernel use all SMs: 12.85 vs 9.9 ms per
@@ -652,6 +752,7 @@ void finalize_schedule(HrnetPlan& P) {
       }
     }
   }
+  plan_chains(P);
   // every stream's last op must be joined back into stream 0 before the head runs
   int head = -1;
   for (size_t i = 0; i < P.ops.size(); ++i) if (P.ops[i].kind == OP_HEAD) head = (int)i;
@@ -664,8 +765,10 @@ void finalize_schedule(HrnetPlan& P) {
     for (int dpi : op.deps)
       if (P.ops[dpi].stream != op.stream) P.ops[dpi].needs_event = true;
   P.launch_count = 0;
-  for (size_t i = 0; i < P.ops.size(); ++i)
+  for (size_t i = 0; i < P.ops.size(); ++i) {
+    if (P.ops[i].chain >= 0) { if (P.ops[i].chain_pos == 0) ++P.launch_count; continue; }   // one kernel per chain
     if (P.ops[i].grp < 0 || i == 0 || P.ops[i - 1].grp != P.ops[i].grp) ++P.launch_count;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -909,7 +1012,7 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     o << "{\"kind\":" << op.kind << ",\"name\":\"" << op.name << "\",\"in\":" << op.in << ",\"out\":" << op.out
       << ",\"res\":" << op.res << ",\"param\":" << op.param << ",\"cin\":" << op.cin << ",\"cout\":" << op.cout
       << ",\"k\":" << op.k << ",\"stride\":" << op.stride << ",\"pad\":" << op.pad << ",\"relu\":" << op.relu
-      << ",\"stream\":" << op.stream << ",\"grp\":" << op.grp << ",\"sm_frac\":" << op.sm_frac << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
+      << ",\"stream\":" << op.stream << ",\"chain\":" << op.chain << ",\"chain_pos\":" << op.chain_pos << ",\"grp\":" << op.grp << ",\"sm_frac\":" << op.sm_frac << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
       << op.src[0] << "," << op.src[1] << "," << op.src[2] << "," << op.src[3] << "],\"shift\":[" << op.shift[0] << ","
       << op.shift[1] << "," << op.shift[2] << "," << op.shift[3] << "],\"deps\":[";
     for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
@@ -919,7 +1022,19 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
       << ",\"patch_cs\":" << (op.use_patch ? op.pp.cs : 0) << ",\"patch_slots\":" << (op.use_patch ? op.pp.nslots : 0)
       << ",\"mma_warps\":" << (op.use_patch ? op.pp.mma_warps : op.tc.mma_warps) << "}}";
   }
-  o << "]}";
+  o << "],\"chains\":[";
+  bool first_chain = true;
+  for (const auto& ch : P->chains) {
+    if (!ch.enabled) continue;
+    if (!first_chain) o << ",";
+    first_chain = false;
+    o << "{\"module\":" << ch.module << ",\"branch\":" << ch.branch << ",\"patch\":" << (ch.patch ? 1 : 0) << ",\"smem\":" << ch.smem
+      << ",\"share_permille\":" << ch.share << ",\"grid\":" << ch.grid << ",\"flag_stride\":" << ch.flag_stride << ",\"ctrl_off\":" << ch.ctrl_off
+      << ",\"flags_off\":" << ch.flags_off << ",\"ops\":[";
+    for (size_t k = 0; k < ch.ops.size(); ++k) o << (k ? "," : "") << ch.ops[k];
+    o << "]}";
+  }
+  o << "],\"sync_off\":" << P->sync_off << ",\"sync_bytes\":" << P->sync_bytes << "}";
   const std::string s = o.str();
   if (needed) *needed = s.size() + 1;
   if (buf && cap) {
@@ -969,6 +1084,50 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
       rc = encode_epi_maps(op, P->abase + to.offset, op.res >= 0 ? P->abase + P->tensors[op.res].offset : nullptr,
                            P->desc.max_batch, to.H, to.W);
       if (rc) return rc;
+    }
+  }
+  // branch chains: tensor maps of the member convs side by side, grid split of each module's chains, cleared flags
+  {
+    std::map<int, std::vector<int>> by_module;
+    for (size_t c = 0; c < P->chains.size(); ++c) {
+      ChainInfo& ch = P->chains[c];
+      if (!ch.enabled) continue;
+      by_module[ch.module].push_back((int)c);
+      for (size_t k = 0; k < ch.ops.size(); ++k) {
+        const Op& op = P->ops[ch.ops[k]];
+        if (ch.patch) {
+          int tail = 0;
+          for (int j = 0; j < op.pp.nchunks; ++j) if (op.pp.mapi[j]) tail = op.pp.mapi[j];
+          ch.pmaps.a[k] = op.tmPA[0];
+          ch.pmaps.b[k][0] = op.tmPB[0];
+          ch.pmaps.b[k][1] = op.tmPB[tail];
+        } else {
+          ch.imaps.a[k] = op.tmA;
+          ch.imaps.b[k] = op.tmB;
+        }
+      }
+      for (size_t k = ch.ops.size(); k < (size_t)kChainMaxConv; ++k) {   // unused slots: any valid descriptor
+        if (ch.patch) { ch.pmaps.a[k] = ch.pmaps.a[0]; ch.pmaps.b[k][0] = ch.pmaps.b[0][0]; ch.pmaps.b[k][1] = ch.pmaps.b[0][1]; }
+        else { ch.imaps.a[k] = ch.imaps.a[0]; ch.imaps.b[k] = ch.imaps.b[0]; }
+      }
+    }
+    const int cap = P->desc.tune[HRNET_TUNE_CHAIN_GRID_CAP] > 0 ? P->desc.tune[HRNET_TUNE_CHAIN_GRID_CAP] : P->num_sms;
+    for (auto& kv : by_module) {
+      int left = P->num_sms, big = kv.second[0];
+      for (int c : kv.second) {
+        ChainInfo& ch = P->chains[c];
+        ch.grid = std::max(1, (int)std::lround(ch.share * 0.001 * P->num_sms));
+        left -= ch.grid;
+        if (ch.share > P->chains[big].share) big = c;
+      }
+      P->chains[big].grid = std::max(1, P->chains[big].grid + left);    // rounding remainder to the largest chain
+      for (int c : kv.second) P->chains[c].grid = std::min(P->chains[c].grid, cap);
+    }
+    if (P->sync_bytes) {
+      cudaError_t e = cudaMemset(P->abase + P->sync_off, 0, P->sync_bytes);
+      if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaMemset(chain flags): ") + cudaGetErrorString(e));
+      e = conv_chain_set_attributes(kMaxDynSmem);
+      if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute(chain): ") + cudaGetErrorString(e));
     }
   }
   {
@@ -1122,6 +1281,55 @@ int launch_group(HrnetPlan* P, int first, int last, int n, cudaStream_t st, std:
   return 0;
 }
 
+// One launch for the whole branch chain `c` at batch n on `grid` CTAs (<= 0: the chain's share inside the forward).
+int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st) {
+  const ChainInfo& ch = P->chains[c];
+  const Op& o0 = P->ops[ch.ops[0]];
+  if (grid <= 0) grid = ch.grid;
+  auto fill_convs = [&](ChainConv* cv) {
+    for (size_t k = 0; k < ch.ops.size(); ++k) {
+      const Op& op = P->ops[ch.ops[k]];
+      const ParamInfo& pi = P->params[op.param];
+      cv[k].scale = (const float*)(P->wbase + pi.scale_offset);
+      cv[k].bias = (const float*)(P->wbase + pi.bias_offset);
+      cv[k].residual = op.res >= 0 ? (const __half*)(P->abase + P->tensors[op.res].offset) : nullptr;
+      cv[k].out = (__half*)(P->abase + P->tensors[op.out].offset);
+      cv[k].relu = op.relu;
+      cv[k].pad_ = 0;
+    }
+  };
+  if (ch.patch) {
+    ChainPatchParams p{};
+    p.nconv = (int)ch.ops.size();
+    p.pp = o0.pp;
+    p.pp.N = n; p.pp.total_tiles = n * p.pp.tiles_w * p.pp.tiles_h;
+    p.unit_stride = ch.flag_stride;
+    p.ctrl = (unsigned*)(P->abase + ch.ctrl_off);
+    p.counters = (unsigned*)(P->abase + ch.flags_off);
+    p.dbg = nullptr;
+    fill_convs(p.conv);
+    if (p.pp.total_tiles == 0) return 0;
+    grid = std::max(1, std::min(grid, p.pp.total_tiles));
+    CK(launch_chain_patch(ch.pmaps, p, ch.smem, grid, st));
+  } else {
+    const ConvTcParams t = fill_tc_params(P, o0, n);
+    ChainIgemmParams p{};
+    p.nconv = (int)ch.ops.size();
+    p.M_total = t.M_total; p.OH = t.OH; p.OW = t.OW; p.OHW = t.OHW; p.C = o0.cin;
+    p.cpt = t.cpt; p.nkb = t.nkb; p.bps = t.bps; p.n_tile = t.n_tile; p.n_tiles = t.n_tiles; p.m_tiles = t.m_tiles;
+    p.stages = t.stages; p.tmem_cols = t.tmem_cols; p.a_blk_bytes = t.a_blk_bytes; p.b_blk_bytes = t.b_blk_bytes;
+    p.unit_stride = ch.flag_stride;
+    p.ctrl = (unsigned*)(P->abase + ch.ctrl_off);
+    p.counters = (unsigned*)(P->abase + ch.flags_off);
+    p.dbg = nullptr;
+    fill_convs(p.conv);
+    if (p.m_tiles * p.n_tiles == 0) return 0;
+    grid = std::max(1, std::min(grid, p.m_tiles * p.n_tiles));
+    CK(launch_chain_igemm(ch.imaps, p, ch.smem, grid, st));
+  }
+  return 0;
+}
+
 int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_ext, float* joints, int32_t* idx,
               const float* boxes, cudaStream_t st) {
   auto tptr = [&](int t) -> uint8_t* { return P->abase + P->tensors[t].offset; };
@@ -1234,6 +1442,19 @@ int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, flo
   for (int i = first; i < last; ++i) {
     const Op& op = P->ops[i];
     cudaStream_t st = stream_of(op.stream);
+    if (op.chain >= 0) {
+      // the whole branch chain is issued where its first conv stands; the other members are part of that launch
+      if (op.chain_pos != 0) continue;
+      const ChainInfo& ch = P->chains[op.chain];
+      for (int m : ch.ops)
+        for (int dpi : P->ops[m].deps)
+          if (P->ops[dpi].stream != op.stream) CK(cudaStreamWaitEvent(st, P->events[dpi], 0));
+      int rc = launch_chain_op(P, op.chain, n, (P->desc.flags & HRNET_FLAG_SERIAL) ? P->num_sms : 0, st);
+      if (rc) return rc;
+      for (int m : ch.ops)
+        if (P->ops[m].needs_event) CK(cudaEventRecord(P->events[m], st));
+      continue;
+    }
     if (op.grp >= 0) {
       int j = i;
       while (j < last && P->ops[j].grp == op.grp) ++j;
@@ -1388,12 +1609,27 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
   std::vector<cudaEvent_t> ev(nops + 1);
   for (auto& e : ev) CK(cudaEventCreate(&e));
   std::vector<std::vector<float>> t(nops, std::vector<float>(iters));
+  std::vector<cudaEvent_t> chain_ev(2 * P->chains.size(), nullptr);
+  for (size_t c = 0; c < P->chains.size(); ++c)
+    if (P->chains[c].enabled) { CK(cudaEventCreate(&chain_ev[2 * c])); CK(cudaEventCreate(&chain_ev[2 * c + 1])); }
   for (int it = -1; it < iters; ++it) {   // iteration -1 = warm-up
     CK(cudaEventRecord(ev[0], s0));
     std::vector<std::pair<int, int>> spans;          // grouped launches: [first, last)
     std::vector<std::vector<double>> span_cost;
     for (int i = 0; i < nops; ++i) {
       const Op& op = P->ops[i];
+      if (op.chain >= 0) {
+        // a branch chain is one kernel: timed alone on the whole GPU where its first conv stands, its time is split
+        // evenly between the member convs (equal FLOPs) below
+        if (op.chain_pos == 0) {
+          CK(cudaEventRecord(chain_ev[2 * op.chain], s0));
+          int rc = launch_chain_op(P, op.chain, n, P->num_sms, s0);
+          if (rc) return rc;
+          CK(cudaEventRecord(chain_ev[2 * op.chain + 1], s0));
+        }
+        CK(cudaEventRecord(ev[i + 1], s0));
+        continue;
+      }
       if (op.grp >= 0) {
         int j = i;
         while (j < nops && P->ops[j].grp == op.grp) ++j;
@@ -1412,6 +1648,13 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
     CK(cudaStreamSynchronize(s0));
     if (it >= 0) {
       for (int i = 0; i < nops; ++i) { CK(cudaEventElapsedTime(&t[i][it], ev[i], ev[i + 1])); }
+      for (size_t c = 0; c < P->chains.size(); ++c) {
+        const ChainInfo& ch = P->chains[c];
+        if (!ch.enabled) continue;
+        float total = 0.f;
+        CK(cudaEventElapsedTime(&total, chain_ev[2 * c], chain_ev[2 * c + 1]));
+        for (int m : ch.ops) t[m][it] = total / (float)ch.ops.size();
+      }
       for (size_t gi = 0; gi < spans.size(); ++gi) {   // one kernel for the whole span: split its time by estimated cost
         float total = 0.f;
         CK(cudaEventElapsedTime(&total, ev[spans[gi].first], ev[spans[gi].second]));
@@ -1427,6 +1670,7 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
     usec_per_op[i] = t[i][iters / 2] * 1000.f;
   }
   for (auto& e : ev) cudaEventDestroy(e);
+  for (auto& e : chain_ev) if (e) cudaEventDestroy(e);
   return HRNET_OK;
 }
 

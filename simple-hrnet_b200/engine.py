@@ -91,10 +91,20 @@ def pack_state_dict(state_dict, infos, weight_bytes):
     return buf
 
 
+def _aligned_empty(nbytes, device, zero=False, align=1024):
+    """(base, view): a uint8 device buffer whose view starts on an `align`-byte boundary.  The torch caching allocator
+    only guarantees 512-byte granularity (a block split off a cached segment can start at an odd 512 multiple), while
+    hrnet_plan_bind wants 1024 (swizzle-atom aligned TMA boxes): over-allocate and bind the aligned slice; `base`
+    keeps the allocation alive."""
+    base = (torch.zeros if zero else torch.empty)(nbytes + align, dtype=torch.uint8, device=device)
+    off = (-base.data_ptr()) % align
+    return base, base[off:off + nbytes]
+
+
 class Plan:
     """Host-only view of a plan (no CUDA needed): layer inventory, workspace sizes, op list."""
 
-    def __init__(self, arch, c, nof_joints, resolution, max_batch, flags=0):
+    def __init__(self, arch, c, nof_joints, resolution, max_batch, flags=0, tune=None):
         self.lib = load_library()
         self.arch = {"hrnet": _lib.ARCH_HRNET, "poseresnet": _lib.ARCH_POSERESNET}.get(str(arch).lower())
         if self.arch is None:
@@ -104,7 +114,10 @@ class Plan:
         self.max_batch = int(max_batch)
         self.flags = int(flags)
         self._plan = ctypes.c_void_p()
+        self.tune = dict(tune or {})                     # {HRNET_TUNE_* index: value}; speed knobs, never results
         desc = HrnetDesc(self.arch, self.c, self.J, self.H, self.W, self.max_batch, int(flags))
+        for k, v in self.tune.items():
+            desc.tune[int(k)] = int(v)
         check(self.lib.hrnet_plan_create(ctypes.byref(desc), ctypes.byref(self._plan)), self.lib)
         a, w = ctypes.c_size_t(), ctypes.c_size_t()
         check(self.lib.hrnet_plan_workspace_bytes(self._plan, ctypes.byref(a), ctypes.byref(w)), self.lib)
@@ -141,7 +154,7 @@ class B200Engine(Plan):
     engine.forward_decode(images, ...)  -> (joints [n,J,3] (y,x,conf), argmax idx [n,J], heat-maps or None)
     """
 
-    def __init__(self, arch, c, nof_joints, resolution, max_batch, device, flags=0):
+    def __init__(self, arch, c, nof_joints, resolution, max_batch, device, flags=0, tune=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise HrnetError("B200Engine is CUDA-only (sm_100a); there is no CPU fallback")
@@ -149,7 +162,7 @@ class B200Engine(Plan):
             raise HrnetError("no CUDA device available: the B200 engine cannot run (no CPU fallback)")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        super().__init__(arch, c, nof_joints, resolution, max_batch, flags)
+        super().__init__(arch, c, nof_joints, resolution, max_batch, flags, tune)
         self._weights = None
         self._workspace = None
 
@@ -157,12 +170,14 @@ class B200Engine(Plan):
     def load_state_dict(self, state_dict):
         host = pack_state_dict(state_dict, self.infos, self.weight_bytes)
         with torch.cuda.device(self.device):
-            self._weights = torch.from_numpy(host).to(self.device)
+            self._weights_base, self._weights = _aligned_empty(self.weight_bytes, self.device)
+            self._weights.copy_(torch.from_numpy(host))
             if self._workspace is None:
-                self._workspace = torch.zeros(self.act_bytes, dtype=torch.uint8, device=self.device)
-            assert self._weights.data_ptr() % 1024 == 0 and self._workspace.data_ptr() % 1024 == 0
+                self._workspace_base, self._workspace = _aligned_empty(self.act_bytes, self.device, zero=True)
             check(self.lib.hrnet_plan_bind(self._plan, self._weights.data_ptr(), self.weight_bytes,
                                            self._workspace.data_ptr(), self.act_bytes), self.lib)
+            # the zero fill ran on the current stream; other streams (HostPipeline) may use the plan right away
+            torch.cuda.current_stream(self.device).synchronize()
         return self
 
     def clone_shared(self):
@@ -171,12 +186,13 @@ class B200Engine(Plan):
         if self._weights is None:
             raise HrnetError("load_state_dict must be called before clone_shared")
         other = B200Engine("hrnet" if self.arch == _lib.ARCH_HRNET else "poseresnet", self.c, self.J, (self.H, self.W),
-                           self.max_batch, self.device, flags=self.flags)
+                           self.max_batch, self.device, flags=self.flags, tune=self.tune)
         with torch.cuda.device(self.device):
-            other._weights = self._weights
-            other._workspace = torch.zeros(other.act_bytes, dtype=torch.uint8, device=self.device)
+            other._weights_base, other._weights = self._weights_base, self._weights
+            other._workspace_base, other._workspace = _aligned_empty(other.act_bytes, self.device, zero=True)
             check(other.lib.hrnet_plan_bind(other._plan, other._weights.data_ptr(), other.weight_bytes,
                                             other._workspace.data_ptr(), other.act_bytes), other.lib)
+            torch.cuda.current_stream(self.device).synchronize()
         return other
 
     # -- execution --------------------------------------------------------------------------

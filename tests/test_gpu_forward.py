@@ -65,6 +65,28 @@ def test_forward_matches_reference_fixture(golden_dir, name, tol_scale):
     assert np.array_equal(joints.cpu().numpy().view(np.uint32), pts.view(np.uint32))
 
 
+def test_w48_four_person_summary_fixture(golden_dir):
+    """Reference-generated summary of HRNet-W48 384x288 on 4 persons (tests/golden/make_golden.py ran the live reference
+    class): flat argmax, (y, x, conf) and top-1 / top-2 gaps for all 68 joints, min / mean / max of the heat-maps."""
+    g = np.load(os.path.join(golden_dir, "w48_384x288_n4_default_summary.npz"))
+    c, n, h, w = int(g["c"]), int(g["n"]), int(g["h"]), int(g["w"])
+    sd = O.make_state_dict(O.hrnet_param_spec(c, 17), seed=int(g["wseed"]), bn=str(g["bn"]))
+    x = torch.randn(n, 3, h, w, generator=torch.Generator().manual_seed(int(g["xseed"])))
+    e = _engine("hrnet", c, (h, w), n, sd)
+    joints, idx, hm = e.forward_decode(x.cuda(), return_heatmaps=True)
+    hm = hm.cpu().numpy(); idx = idx.cpu().numpy(); joints = joints.cpu().numpy()
+    stats = np.asarray([hm.min(), hm.mean(), hm.max()])
+    assert np.abs(stats - g["hm_stats"]).max() <= 1e-3
+    err = 1e-3                                       # the heat-map bar: joints whose gap exceeds 2 x bar must agree exactly
+    robust = g["gaps"] > 2 * err
+    flips = int((idx != g["argmax"]).sum())
+    _report(f"w48_384x288_n4_default_summary: end-to-end argmax flips {flips} of {idx.size} "
+            f"(joints with gap <= 2e-3: {int((~robust).sum())})")
+    assert np.array_equal(idx[robust], g["argmax"][robust])
+    assert np.array_equal(joints[..., :2][robust], g["pts"][..., :2][robust])
+    assert np.abs(joints[..., 2] - g["pts"][..., 2]).max() <= 1e-3
+
+
 def test_forward_variants_agree():
     """graph vs direct launch vs serial streams are bit-identical; the SIMT cross-check path agrees to
     accumulation-order noise; fp32 exchange terms (opt-in) and the default fp16 ones both stay inside the bar."""
@@ -121,11 +143,15 @@ def test_batch_invariance_and_chunking_full_size():
         for _ in range(2):
             _, _, hk = e.forward_decode(x[:k], return_heatmaps=True)
             assert torch.equal(hk, h64[:k]), f"n={k}"
-    # against the oracle on a 2-person slice (CPU fp32 takes ~1 s)
-    ref = O.hrnet_forward(sd, x[:2].cpu()).numpy()
-    err = float(np.abs(h64[:2].cpu().numpy() - ref).max())
-    _report(f"w48_384x288 N=64 (persons 0-1 vs oracle): heat-map max-abs err {err:.3e}")
+    # against the oracle on 8 persons spread over the batch (CPU fp32, a few seconds)
+    sel = [0, 9, 18, 27, 36, 45, 54, 63]
+    ref = O.hrnet_forward(sd, x[sel].cpu()).numpy()
+    got = h64[sel].cpu().numpy()
+    err = float(np.abs(got - ref).max())
+    _report(f"w48_384x288 N=64 (persons {sel} vs oracle): heat-map max-abs err {err:.3e}")
     assert err <= 1e-3
+    flips, fragile = _check_argmax(ref, i64[sel].cpu().numpy(), err)
+    _report(f"w48_384x288 N=64 (8 persons): end-to-end argmax flips {flips} of {8 * 17} (joints with gap <= 2*err: {fragile})")
 
 
 @pytest.mark.parametrize("arch,c,B,ks", [("hrnet", 32, 32, (3, 8, 16)), ("poseresnet", 50, 64, (3, 8, 33))])

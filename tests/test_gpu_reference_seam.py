@@ -1,0 +1,70 @@
+"""`-m gpu`: the INTEGRATION.md section 2 stub exercised against the REAL reference class.
+
+The unmodified `SimpleHRNet` of stefanopini/simple-HRNet (installed into oracle/_ref/ by oracle/install_ref.py; it cannot
+be imported from /root/reference on the GPU box) is constructed on the GPU, its `.model` is replaced by a `B200Engine`
+exactly where the reference swaps in a TensorRT module (SimpleHRNet.py:143-147), and its own unmodified `predict()`
+(resize, cvtColor, transform, chunked `self.model(images)`, numpy argmax decode: SimpleHRNet.py:212-343, 345-496) runs on
+top of the B200 engine.  The result is compared with the same class running the reference network on the CPU."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hrnet_oracle as O
+from oracle.install_ref import import_reference
+from simple_hrnet_b200 import B200Engine
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = import_reference()
+    if r is None:
+        pytest.skip("reference not installed (oracle/_ref missing: run __graft_entry__.build() where /root/reference exists)")
+    return r
+
+
+def _swap_in_engine(model, arch, c, res, max_batch):
+    """what the `enable_b200` branch next to SimpleHRNet.py:143-147 does."""
+    sd = model.model.module.state_dict() if hasattr(model.model, "module") else model.model.state_dict()
+    eng = B200Engine(arch, c, model.nof_joints, res, max_batch, model.device)
+    eng.load_state_dict({k: v.cpu() for k, v in sd.items()})
+    model.model = eng.cuda().eval()
+    return eng
+
+
+@pytest.mark.parametrize("arch,c,res,batch", [("hrnet", 32, (256, 192), 6), ("hrnet", 48, (384, 288), 5),
+                                                ("poseresnet", 50, (256, 192), 3)])
+def test_reference_predict_runs_on_the_b200_engine(ref, arch, c, res, batch):
+    RefSimpleHRNet, _, _ = ref
+    spec = O.hrnet_param_spec(c, 17) if arch == "hrnet" else O.poseresnet_param_spec(c, 17)
+    sd = O.make_state_dict(spec, seed=0, bn="default")
+    with tempfile.TemporaryDirectory() as td:
+        ckpt = os.path.join(td, "w.pth")
+        torch.save(sd, ckpt)                                   # the reference needs a checkpoint file (SimpleHRNet.py:117)
+        name = "HRNet" if arch == "hrnet" else "PoseResNet"
+        kw = dict(model_name=name, resolution=res, multiperson=False, return_heatmaps=True, return_bounding_boxes=True,
+                  max_batch_size=4)
+        cpu = RefSimpleHRNet(c, 17, ckpt, device=torch.device("cpu"), **kw)
+        gpu = RefSimpleHRNet(c, 17, ckpt, device=torch.device("cuda:0"), **kw)
+    _swap_in_engine(gpu, arch, c, res, 4)
+    rng = np.random.default_rng(7)
+    # one image at another resolution (the reference resizes it, SimpleHRNet.py:216-220) and a stack (chunked by 4)
+    img = rng.integers(0, 256, (300, 210, 3), dtype=np.uint8)
+    stack = rng.integers(0, 256, (batch, res[0], res[1], 3), dtype=np.uint8)
+    for inp in (img, stack):
+        hm_c, box_c, pts_c = cpu.predict(inp)
+        hm_g, box_g, pts_g = gpu.predict(inp)
+        assert hm_g.shape == hm_c.shape and pts_g.shape == pts_c.shape and pts_g.dtype == pts_c.dtype
+        assert np.array_equal(np.asarray(box_g), np.asarray(box_c))
+        err = float(np.abs(hm_g - hm_c).max())
+        assert err <= 1e-3, err
+        flat = hm_c.reshape(hm_c.shape[0], hm_c.shape[1], -1)
+        top2 = np.sort(flat, axis=2)[..., -2:]
+        robust = (top2[..., 1] - top2[..., 0]) > 2 * err
+        pc, pg = pts_c.reshape(-1, 17, 3), pts_g.reshape(-1, 17, 3)
+        assert np.array_equal(pg[..., :2][robust], pc[..., :2][robust])
+        assert np.abs(pg[..., 2] - pc[..., 2]).max() <= 1e-3
