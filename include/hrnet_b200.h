@@ -49,11 +49,31 @@ extern "C" {
 #define HRNET_FLAG_NO_CHAIN 128u   /* debug / cross-check: launch the eight convs of a StageModule branch one by one
                                       instead of as one persistent branch-chain kernel (bit-identical results)     */
 
-/* Tuning knobs of a plan (HrnetDesc.tune[]); 0 = the library's default.  They change speed only, never results. */
+/* Tuning / diagnostic knobs of a plan (HrnetDesc.tune[]); 0 = the library's default.  They select between kernel
+ * variants that compute the same function (results agree to accumulation-order noise at most; the default set is what
+ * the parity tests pin).  Nothing in the library reads the process environment. */
 #define HRNET_TUNE_CHAIN_SHARE0 0  /* [0..3] per-mille share of the SMs given to the branch-0..3 chain kernel of a
                                       StageModule with four branches (three / two branches: renormalised)          */
 #define HRNET_TUNE_CHAIN_GRID_CAP 4 /* upper bound on any chain kernel's grid (experiments)                         */
-#define HRNET_TUNE_COUNT 8
+#define HRNET_TUNE_CHAIN_DEBUG 5    /* != 0: hrnet_profile_ops also runs every chain once with per-CTA role timers and
+                                      prints their averages to stderr (development aid; allocates a scratch buffer)  */
+#define HRNET_TUNE_IGEMM_PAIR 6     /* 2: im2col kernel in CTA-pair mode (tcgen05 cta_group::2)                      */
+#define HRNET_TUNE_IGEMM_PAIR_MIN_K 7 /* ... only for convs with at least this GEMM K                                */
+#define HRNET_TUNE_PATCH_PAIR_MIN_COUT 8  /* > 0: halo-patch kernel in CTA-pair mode for convs with Cout in            */
+#define HRNET_TUNE_PATCH_PAIR_MAX_COUT 9  /*      [MIN_COUT, MAX_COUT] (MAX 0 = no upper bound)                        */
+#define HRNET_TUNE_EPILOGUE 10      /* 0 auto, 1 direct, 2 staged TMA wherever eligible, 3 warp-staged coalesced wherever
+                                      it fits, 4 TMA on every halo-patch conv, 5 TMA on every im2col conv, 6 batched
+                                      TMEM loads on tiles <= 64 channels                                              */
+#define HRNET_TUNE_BPS 11           /* k-blocks per pipeline stage of the im2col kernel: 1 or 2                       */
+#define HRNET_TUNE_IGEMM_MMA2 12    /* two MMA-issuing warps for N tiles up to this width (default 96); -1 never, 1 always */
+#define HRNET_TUNE_PATCH_MMA2 13    /* halo-patch kernel: 1 one MMA issuer, 2 two issuers (default: two when each keeps two slots) */
+#define HRNET_TUNE_PATCH_NACC 14    /* 2: only two TMEM accumulator buffers in the halo-patch kernel                  */
+#define HRNET_TUNE_NO_PDL 15        /* != 0: launch without programmatic dependent launch                             */
+#define HRNET_TUNE_DEBUG 16         /* bit 0: per-CTA role timers on the single-op entry points (stderr); bit 1: per-op
+                                      output checksums with HRNET_FLAG_NO_GRAPH (stderr); bit 2: finish times of grouped
+                                      launches; bit 3: single-op halo-patch conv without global stores (timing only)  */
+#define HRNET_TUNE_GRID_CAP 17      /* single-op entry points: cap on the persistent grid (experiments)              */
+#define HRNET_TUNE_COUNT 24
 
 typedef struct HrnetPlan HrnetPlan;
 
@@ -142,6 +162,9 @@ int hrnet_profile_ops(HrnetPlan* plan, const float* in_nchw_f32, int n, float* u
 int hrnet_plan_launch_count(const HrnetPlan* plan);
 
 /* ---- single-op entry points (tests, ncu) ------------------------------------------------------ */
+/* The single-op entry points below have no HrnetDesc: they use this process-wide copy of the tuning knobs
+ * (HRNET_TUNE_COUNT int32 values, NULL = all defaults).  Plans never look at it. */
+void hrnet_debug_set_tune(const int32_t* tune);
 /* kxk conv + BN(scale,bias) (+residual) (+ReLU) on NHWC fp16; weights [cout][k][k][cin] fp16.
  * use_tc: 0 = SIMT cross-check kernel, 1 = tcgen05 implicit GEMM (TMA im2col), 2 = tcgen05 halo-patch
  * kernel (3x3 stride 1 with shared-memory-resident weights).  out_f32 selects fp32 output. */

@@ -15,7 +15,7 @@ class HrnetError(RuntimeError):
 class HrnetDesc(ctypes.Structure):
     _fields_ = [("arch", ctypes.c_int32), ("c", ctypes.c_int32), ("nof_joints", ctypes.c_int32),
                 ("height", ctypes.c_int32), ("width", ctypes.c_int32), ("max_batch", ctypes.c_int32),
-                ("flags", ctypes.c_uint32), ("tune", ctypes.c_int32 * 8)]
+                ("flags", ctypes.c_uint32), ("tune", ctypes.c_int32 * 24)]
 
 
 class HrnetParamInfo(ctypes.Structure):
@@ -29,7 +29,11 @@ class HrnetParamInfo(ctypes.Structure):
 ARCH_HRNET, ARCH_POSERESNET = 0, 1
 FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F32, FLAG_SERIAL, FLAG_NO_PATCH, FLAG_PARTITION, FLAG_GROUP = 1, 2, 4, 8, 16, 32, 64
 FLAG_NO_CHAIN = 128
-TUNE_CHAIN_SHARE0, TUNE_CHAIN_GRID_CAP, TUNE_COUNT = 0, 4, 8
+TUNE_CHAIN_SHARE0, TUNE_CHAIN_GRID_CAP, TUNE_CHAIN_DEBUG = 0, 4, 5
+TUNE_IGEMM_PAIR, TUNE_IGEMM_PAIR_MIN_K, TUNE_PATCH_PAIR_MIN_COUT, TUNE_PATCH_PAIR_MAX_COUT = 6, 7, 8, 9
+TUNE_EPILOGUE, TUNE_BPS, TUNE_IGEMM_MMA2, TUNE_PATCH_MMA2, TUNE_PATCH_NACC, TUNE_NO_PDL, TUNE_DEBUG, TUNE_GRID_CAP = 10, 11, 12, 13, 14, 15, 16, 17
+TUNE_COUNT = 24
+EPI_AUTO, EPI_DIRECT, EPI_TMA, EPI_COAL, EPI_TMA_PATCH, EPI_TMA_IGEMM, EPI_BATCH = 0, 1, 2, 3, 4, 5, 6
 
 # every symbol include/hrnet_b200.h declares: (name, restype, argtypes)
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
@@ -49,6 +53,7 @@ SYMBOLS = {
     "hrnet_forward_host_u8_async": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "hrnet_plan_launch_count": (_i, [_vp]),
     "hrnet_profile_ops": (_i, [_vp, _vp, _i, ctypes.POINTER(ctypes.c_float), _i, _vp]),
+    "hrnet_debug_set_tune": (None, [ctypes.POINTER(ctypes.c_int32)]),
     "hrnet_conv_bn_act": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "hrnet_fuse": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "hrnet_argmax": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -84,6 +89,18 @@ def load_library(build_if_missing=True):
             fn.argtypes = args
         _LIB = lib
         return lib
+
+
+def set_debug_tune(tune=None):
+    """Tuning knobs of the single-op entry points ({HRNET_TUNE_* index: value}; None = defaults)."""
+    lib = load_library()
+    if not tune:
+        lib.hrnet_debug_set_tune(None)
+        return
+    arr = (ctypes.c_int32 * TUNE_COUNT)()
+    for k, v in tune.items():
+        arr[int(k)] = int(v)
+    lib.hrnet_debug_set_tune(arr)
 
 
 def check(rc, lib=None):

@@ -1,6 +1,5 @@
 // Single-problem launch of the halo-patch 3x3 conv (body and documentation: conv3x3_patch_body.cuh).
 #include <algorithm>
-#include <cstdlib>
 
 #include "conv3x3_patch_body.cuh"
 
@@ -68,9 +67,7 @@ cudaError_t launch_conv_patch(const CUtensorMap* tmA3, const CUtensorMap* tmB3, 
     at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
     ++na;
   }
-  static int pdl = -1;
-  if (pdl < 0) pdl = getenv("HRNET_B200_NO_PDL") ? 0 : 1;
-  if (pdl) {   // resident-weight loads and the rest of the prologue overlap the previous kernel's tail
+  if (p.pdl) {   // resident-weight loads and the rest of the prologue overlap the previous kernel's tail
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

@@ -9,13 +9,14 @@
 //   * a CTA draws tickets from a global counter (dynamic scheduling: a CTA only ever waits for tiles with a LOWER
 //     ticket, which are owned by CTAs that are already running -> no deadlock whatever subset of the grid is resident,
 //     e.g. when two forwards or the four branch chains of a module share the SMs);
-//   * tile (conv k, position t) may start when the tiles of conv k-1 that cover its 3x3 halo are stored.  Finished
-//     tiles are counted per UNIT of the output map -- a row of 8x16 tiles of one image (halo-patch kernel) or a
-//     128-pixel M-tile (im2col kernel; one arrival per N-tile): after the epilogue warpgroup's stores a
-//     __threadfence + red.add on `counters[k][unit]`.  The scheduler warp reads the three units u-1, u, u+1 of conv
-//     k-1 with relaxed loads followed by one acquire fence.  The last CTA to exit clears the counters and the ticket
-//     (every other CTA is gone by then), so nothing has to be cleared between forwards or graph replays and any batch
-//     size can follow any other;
+//   * tile (conv k, position t) may start when the tiles of conv k-1 that cover its 3x3 halo are stored.  The output
+//     map is cut into UNITS -- a row of 8x16 tiles of one image (halo-patch kernel) or a 128-pixel M-tile (im2col
+//     kernel) -- and `counters[k][u]` counts the finished tiles of units u-1, u, u+1 of conv k: after its stores
+//     (+ __threadfence) an epilogue warpgroup adds 1 to the (up to) three counters its tile belongs to (red.add, fire
+//     and forget).  A ticket is a CHUNK of tiles of one unit (three neighbouring patch tiles / all N-tiles of an
+//     M-tile); the scheduler warp needs ONE ld.acquire.gpu of counters[k-1][u] per chunk.  The last CTA to exit clears
+//     the counters and the ticket (every other CTA is gone by then), so nothing has to be cleared between forwards or
+//     graph replays and any batch size can follow any other;
 //   * write-after-read hazards on the rotating t / y0 / y1 buffers are covered by the same chain of dependencies (a
 //     tile of conv k+1 depends on every tile of conv k that read the region it overwrites);
 //   * data written earlier in the same launch is read through TMA (L2) or ld.global.cg -- never through L1 / ld.nc.
@@ -25,32 +26,79 @@
 // asserts), plus a scheduler (warp 3 of the im2col kernel, warp 1 of the halo-patch kernel) that feeds a small ring of
 // tile descriptors to the producer / MMA / epilogue roles.
 #include <algorithm>
-#include <cstdlib>
 
 #include "conv3x3_patch_body.cuh"
 #include "conv_igemm_body.cuh"
 
 namespace hrnet {
 
-constexpr int kChainRing = 4;
+constexpr int kChainRing = 8;
 constexpr uint32_t kChainDone = 0xffffffffu;
 
 struct ChainRing {
   uint64_t full[kChainRing];
   uint64_t empty[kChainRing];
-  uint32_t info[kChainRing];
-  uint32_t pad[4];
+  uint32_t info[kChainRing];     // conv | tile (kChainDone after the last one)
+  uint32_t coord[kChainRing];    // the tile's coordinates, decoded once by the scheduler (no divisions in the other roles)
 };
 
-__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void red_add_relaxed_gpu(unsigned* p, unsigned v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// 256-bit global accesses (sm_100: LDG / STG.E.256).  The thread-per-row epilogue is bound by the load/store unit's sector
+// rate -- every lane touches its own 32-byte sector, ~1 sector per clock per SM (profiles/r02_s2_chain_sched_v2_roles.log:
+// four epilogue warpgroups took exactly as long per tile as two) -- so moving a whole sector per access instead of half
+// of one halves the epilogue's load/store time.  The load is GPU-coherent (.cg: L2, never a stale L1 line).
+struct __align__(32) U256 { uint32_t w[8]; };
+__device__ __forceinline__ U256 ldg256_cg(const void* p) {
+  U256 v;
+  asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
+               : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg256(void* p, const U256& v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7]) : "memory");
+}
+// 16 accumulator columns starting at tile column c: the arithmetic of epi_cols16 (epilogue.cuh) with the residual arriving
+// as and the result leaving as ONE 32-byte access.  fp16 outputs only.
+__device__ __forceinline__ void chain_cols16(const uint32_t (&v)[16], const U256& r, const EpiRow& e, int c) {
+  float y[16];
+  const float4* sc = reinterpret_cast<const float4*>(e.s_scale + e.ch0 + c);
+  const float4* bi = reinterpret_cast<const float4*>(e.s_bias + e.ch0 + c);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 s4 = sc[i], b4 = bi[i];
+    y[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), s4.x, b4.x);
+    y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), s4.y, b4.y);
+    y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), s4.z, b4.z);
+    y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), s4.w, b4.w);
+  }
+  if (e.residual != nullptr) {
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __half22float2(h[i]);
+      y[2 * i] += f.x; y[2 * i + 1] += f.y;
+    }
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+  }
+  U256 o;
+  __half2* oh2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oh2[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+  stg256(reinterpret_cast<__half*>(e.out) + e.row_off + c, o);
+}
+
 // generic-proxy accesses before / async-proxy (TMA) accesses after, all state spaces
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t addr) {
@@ -65,51 +113,48 @@ __device__ __forceinline__ void sts_volatile_u32(uint32_t addr, uint32_t v) {
 // A dependency that never arrives would hang the GPU: after ~2 s of polling the CTA traps (launch failure on the host).
 static __device__ __noinline__ void chain_wait_counter_slow(const unsigned* c, unsigned want) {
   const long long t0 = clock64();
-  while (ld_relaxed_gpu(c) < want) {
-    __nanosleep(64);
+  while (ld_acquire_gpu(c) < want) {
+    __nanosleep(32);
     if (clock64() - t0 > 4000000000ll) {
       printf("hrnet_b200: chain dependency timeout (block %d counter %p want %u have %u)\n", (int)blockIdx.x, (const void*)c,
-             want, ld_relaxed_gpu(c));
+             want, ld_acquire_gpu(c));
       __trap();
     }
   }
 }
-// Units lo .. hi (at most three) of one conv have all `want` arrivals.  The loads are issued back to back (one L2 round
-// trip); the acquire fence orders everything the caller does afterwards behind the arrivals it has observed.
-__device__ __forceinline__ void chain_wait_units(const unsigned* c, int lo, int hi, unsigned want) {
-  const unsigned v0 = ld_relaxed_gpu(c + lo);
-  const unsigned v1 = lo + 1 <= hi ? ld_relaxed_gpu(c + lo + 1) : want;
-  const unsigned v2 = lo + 2 <= hi ? ld_relaxed_gpu(c + lo + 2) : want;
-  if (v0 < want) chain_wait_counter_slow(c + lo, want);
-  if (v1 < want) chain_wait_counter_slow(c + lo + 1, want);
-  if (v2 < want) chain_wait_counter_slow(c + lo + 2, want);
-  fence_acq_rel_gpu();
+// counters[k-1][u] has reached `want`: every tile of units u-1 .. u+1 of the previous conv is stored and visible
+__device__ __forceinline__ void chain_wait_counter(const unsigned* c, unsigned want) {
+  if (ld_acquire_gpu(c) < want) chain_wait_counter_slow(c, want);
 }
 // Ring consumer: every consuming thread walks every entry (tile descriptor or kChainDone), in order.
 struct RingReader {
-  uint32_t full0, empty0, info0;
+  uint32_t full0, empty0, info0, coord0;
   int i;
   __device__ __forceinline__ void init(ChainRing* r) {
     full0 = ptx::smem_u32(&r->full[0]); empty0 = ptx::smem_u32(&r->empty[0]); info0 = ptx::smem_u32(&r->info[0]);
+    coord0 = ptx::smem_u32(&r->coord[0]);
     i = 0;
   }
-  __device__ __forceinline__ uint32_t next() {
+  __device__ __forceinline__ uint32_t next(uint32_t& coord) {
     const uint32_t slot = (uint32_t)(i % kChainRing);
     const uint32_t ph = (uint32_t)((i / kChainRing) & 1);
     ptx::mbar_wait(full0 + 8u * slot, ph);
     const uint32_t v = lds_volatile_u32(info0 + 4u * slot);
+    coord = lds_volatile_u32(coord0 + 4u * slot);
     ptx::mbar_arrive(empty0 + 8u * slot);
     ++i;
     return v;
   }
+  __device__ __forceinline__ uint32_t next() { uint32_t c; return next(c); }
 };
 
 // Ring producer side of the scheduler thread.
 struct RingWriter {
-  uint32_t full0, empty0, info0;
+  uint32_t full0, empty0, info0, coord0;
   int i;
   __device__ __forceinline__ void init(ChainRing* r) {
     full0 = ptx::smem_u32(&r->full[0]); empty0 = ptx::smem_u32(&r->empty[0]); info0 = ptx::smem_u32(&r->info[0]);
+    coord0 = ptx::smem_u32(&r->coord[0]);
     i = 0;
   }
   __device__ __forceinline__ void acquire_slot() {
@@ -117,9 +162,10 @@ struct RingWriter {
     const uint32_t ph = (uint32_t)((i / kChainRing) & 1);
     ptx::mbar_wait(empty0 + 8u * slot, ph ^ 1u);
   }
-  __device__ __forceinline__ void publish(uint32_t v) {
+  __device__ __forceinline__ void publish(uint32_t v, uint32_t coord = 0u) {
     const uint32_t slot = (uint32_t)(i % kChainRing);
     sts_volatile_u32(info0 + 4u * slot, v);
+    sts_volatile_u32(coord0 + 4u * slot, coord);
     ptx::mbar_arrive(full0 + 8u * slot);     // release at CTA scope: the descriptor is visible to the waiters
     ++i;
   }
@@ -140,20 +186,20 @@ __device__ __forceinline__ void chain_exit(unsigned* ctrl, unsigned* counters, i
   if (threadIdx.x == 0) { ctrl[0] = 0u; ctrl[1] = 0u; }
 }
 
-// Epilogue of one row with coherent residual loads (ld.global.cg: the residual was written earlier in this launch by
-// another SM; .nc / L1-cached loads could return a stale line).  Arithmetic identical to epi_store_row.
-__device__ __forceinline__ void chain_load_residual(uint4 (&r)[8], const EpiRow& e, int c_begin) {
+// Epilogue of one row of the im2col chain: the residual of the next 64 channels is in flight while the current 64 are
+// converted (4 x 256-bit loads; written earlier in this launch by another SM, hence the coherent loads).
+__device__ __forceinline__ void chain_load_residual(U256 (&r)[4], const EpiRow& e, int c_begin) {
   if (e.residual == nullptr || !e.valid) return;
-  const uint4* rp = reinterpret_cast<const uint4*>(e.residual + e.row_off + c_begin);
+  const __half* rp = e.residual + e.row_off + c_begin;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (c_begin + 8 * i < e.ncols) r[i] = __ldcg(rp + i);
+  for (int i = 0; i < 4; ++i)
+    if (c_begin + 16 * i < e.ncols) r[i] = ldg256_cg(rp + 16 * i);
 }
-__device__ __forceinline__ void chain_store_row(uint4 (&r)[8], const EpiRow& e, uint32_t t_row) {
+__device__ __forceinline__ void chain_store_row(U256 (&r)[4], const EpiRow& e, uint32_t t_row) {
   for (int c64 = 0; c64 < e.ncols; c64 += 64) {
-    uint4 cur[8];
+    U256 cur[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) cur[i] = r[i];
+    for (int i = 0; i < 4; ++i) cur[i] = r[i];
     if (c64 + 64 < e.ncols) chain_load_residual(r, e, c64 + 64);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -165,21 +211,41 @@ __device__ __forceinline__ void chain_store_row(uint4 (&r)[8], const EpiRow& e, 
         if (two) ptx::tmem_ld16(t_row + (uint32_t)(c + 16), v1);
         ptx::tmem_ld_wait();
         if (e.valid) {
-          epi_cols16(v0, cur[4 * h], cur[4 * h + 1], e, c);
-          if (two) epi_cols16(v1, cur[4 * h + 2], cur[4 * h + 3], e, c + 16);
+          chain_cols16(v0, cur[2 * h], e, c);
+          if (two) chain_cols16(v1, cur[2 * h + 1], e, c + 16);
         }
       }
     }
   }
 }
 
-// After a warpgroup has stored its tile: make the stores visible GPU-wide and count the tile in its unit.
-__device__ __forceinline__ void chain_publish_tile(unsigned* counter, int bar_id, bool leader) {
+// Register-lean variant for the 20-warp halo-patch chain (96 registers per thread): 16 columns per step, the residual of
+// the next 16 columns in flight while the current ones are converted.  r0 = residual of columns [0, 16), loaded before
+// the wait on the accumulator barrier.  Same arithmetic as epi_cols16, so results do not change.
+__device__ __forceinline__ void chain_store_row_lean(const EpiRow& e, uint32_t t_row, U256 r0) {
+  const bool has_res = e.residual != nullptr && e.valid;
+  const __half* rp = e.residual + e.row_off;
+  for (int c = 0; c < e.ncols; c += 16) {
+    U256 n0 = r0;
+    if (has_res && c + 16 < e.ncols) n0 = ldg256_cg(rp + c + 16);
+    uint32_t v[16];
+    ptx::tmem_ld16(t_row + (uint32_t)c, v);
+    ptx::tmem_ld_wait();
+    if (e.valid) chain_cols16(v, r0, e, c);
+    r0 = n0;
+  }
+}
+
+// After a warpgroup has stored its tile of unit u: make the stores visible GPU-wide and count the tile in the
+// neighbourhood counters of units u-1 (if has_lo), u and u+1 (if has_hi).
+__device__ __forceinline__ void chain_publish_tile(unsigned* counter_u, bool has_lo, bool has_hi, int bar_id, bool leader) {
   ptx::bar_sync(bar_id, 128);                  // all four warps of the warpgroup have issued their stores
   if (leader) {
     fence_proxy_async_all();                   // generic-proxy stores before later async-proxy (TMA) reads
     __threadfence();
-    red_add_relaxed_gpu(counter, 1u);
+    red_add_relaxed_gpu(counter_u, 1u);
+    if (has_lo) red_add_relaxed_gpu(counter_u - 1, 1u);
+    if (has_hi) red_add_relaxed_gpu(counter_u + 1, 1u);
   }
 }
 
@@ -213,8 +279,6 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
   const int stage_bytes = a_stage_bytes + b_stage_bytes;
   ChainIgemmBars* bars = reinterpret_cast<ChainIgemmBars*>(smem_aligned + (size_t)p.stages * stage_bytes);
   const int nstages_k = (p.nkb + p.bps - 1) / p.bps;
-  const int tiles_per_conv = p.m_tiles * p.n_tiles;
-  const int total_tiles = p.nconv * tiles_per_conv;
 
   if (warp == 0 && lane == 0) {
     for (int k = 0; k < p.nconv; ++k) { ptx::prefetch_tmap(&maps.a[k]); ptx::prefetch_tmap(&maps.b[k]); }
@@ -255,27 +319,35 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
     if (ptx::elect_one()) {
       RingWriter rw; rw.init(&bars->ring);
       long long dbg_dep = 0; int dbg_tiles = 0;
+      // one ticket = one M-tile (all of its N-tiles: same dependencies, same A operand)
+      const unsigned total_chunks = (unsigned)(p.nconv * p.m_tiles);
       unsigned next = atomicAdd(&p.ctrl[0], 1u);
       for (;;) {
         const unsigned t = next;
-        rw.acquire_slot();
-        if (t >= (unsigned)total_tiles) { rw.publish(kChainDone); break; }
-        next = atomicAdd(&p.ctrl[0], 1u);            // in flight while this tile's dependencies are polled
-        const int k = (int)t / tiles_per_conv;
-        const int r = (int)t - k * tiles_per_conv;
-        const int mt = r / p.n_tiles;
-        const int nt = r - mt * p.n_tiles;
+        if (t >= total_chunks) { rw.acquire_slot(); rw.publish(kChainDone); break; }
+        next = atomicAdd(&p.ctrl[0], 1u);            // in flight while this chunk's dependency is polled
+        const int k = (int)t / p.m_tiles;
+        const int mt = (int)t - k * p.m_tiles;
         if (k > 0) {
           // rows [m0 - (OW + 1), m0 + 127 + OW + 1] of conv k-1: OW + 1 < 128, so M-tiles mt-1 .. mt+1 (all N-tiles)
           const long long tq = p.dbg ? clock64() : 0;
-          chain_wait_units(p.counters + (size_t)(k - 1) * p.unit_stride, max(mt - 1, 0), min(mt + 1, p.m_tiles - 1),
-                           (unsigned)p.n_tiles);
+          const int nb = 1 + (mt > 0 ? 1 : 0) + (mt < p.m_tiles - 1 ? 1 : 0);
+          chain_wait_counter(p.counters + (size_t)(k - 1) * p.unit_stride + mt, (unsigned)(nb * p.n_tiles));
+          fence_proxy_async_all();   // the acquired generic-proxy stores before the TMA (async-proxy) reads issued downstream
           if (p.dbg) dbg_dep += clock64() - tq;
         }
-        rw.publish(((uint32_t)k << 28) | ((uint32_t)nt << 24) | (uint32_t)mt);
-        ++dbg_tiles;
+        const int m0 = mt * kTileM;
+        const int img = m0 / p.OHW;
+        const int rem = m0 - img * p.OHW;
+        const int oh0 = rem / p.OW;
+        const uint32_t coord = ((uint32_t)img << 16) | ((uint32_t)oh0 << 8) | (uint32_t)(rem - oh0 * p.OW);
+        for (int nt = 0; nt < p.n_tiles; ++nt) {
+          rw.acquire_slot();
+          rw.publish(((uint32_t)k << 28) | ((uint32_t)nt << 24) | (uint32_t)mt, coord);
+          ++dbg_tiles;
+        }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = dbg_dep; p.dbg[blockIdx.x * 8 + 1] = dbg_tiles; }
+      if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = dbg_dep; p.dbg[blockIdx.x * 16 + 1] = dbg_tiles; }
     }
     __syncwarp();
   } else if (warp < 2) {
@@ -286,17 +358,13 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
       int stage = warp;
       uint32_t phase = 0;
       for (;;) {
-        const uint32_t info = rr.next();
+        uint32_t coord;
+        const uint32_t info = rr.next(coord);
         if (info == kChainDone) break;
-        const int k = (int)(info >> 28), nt = (int)((info >> 24) & 15u), mt = (int)(info & 0xffffffu);
-        const int m0 = mt * kTileM;
-        const int img = m0 / p.OHW;
-        const int rem = m0 - img * p.OHW;
-        const int oh0 = rem / p.OW;
-        const int ow0 = rem - oh0 * p.OW;
-        const int bw = ow0 - 1, bh = oh0 - 1;
+        const int k = (int)(info >> 28), nt = (int)((info >> 24) & 15u);
+        const int img = (int)(coord >> 16);
+        const int bw = (int)(coord & 255u) - 1, bh = (int)((coord >> 8) & 255u) - 1;
         const int n0 = nt * p.n_tile;
-        fence_proxy_async_all();       // the scheduler's acquire (generic proxy) before this tile's TMA reads
         for (int ks = 0; ks < nstages_k; ++ks, ++L) {
           if ((L & 1) != warp) continue;
           const int kb0 = ks * p.bps;
@@ -388,14 +456,14 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
       e.s_scale = cv.scale; e.s_bias = cv.bias; e.residual = cv.residual; e.out = cv.out;
       e.row_off = (size_t)m * p.C + n0;
       e.ch0 = n0; e.ncols = p.n_tile; e.relu = cv.relu; e.out_f32 = 0; e.valid = m < p.M_total;
-      uint4 rres[8];
+      U256 rres[4];
       chain_load_residual(rres, e, 0);
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
       ptx::tc_fence_after_sync();
       chain_store_row(rres, e, t_row);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
-      chain_publish_tile(p.counters + (size_t)k * p.unit_stride + mt, 1 + g, leader);
+      chain_publish_tile(p.counters + (size_t)k * p.unit_stride + mt, mt > 0, mt < p.m_tiles - 1, 1 + g, leader);
     }
   }
 
@@ -405,7 +473,7 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
-  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin;
+  if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 2] = clock64() - t_begin;
   chain_exit(p.ctrl, p.counters, p.nconv, p.m_tiles, p.unit_stride, &bars->pad);
 }
 
@@ -413,9 +481,14 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
 // halo-patch chain (C = 48, 96 at W48; C = 32, 64 at W32): resident weights are swapped at every conv boundary
 // =====================================================================================================================
 // Warp 0 producer (one TMA per channel chunk of a tile: a single issuing thread keeps up, unlike the im2col kernel's
-// per-k-block loads), warp 1 scheduler, warps 2-3 MMA issuers (3 only when pp.mma_warps == 2), warps 4-11 epilogue.
-// (A 13th warp would put four warps on one scheduler partition and cap every thread at 128 registers.)
-constexpr int kCPThreads = 384;
+// per-k-block loads), warp 1 scheduler, warps 2-3 MMA issuers (3 only when pp.mma_warps == 2), warps 4-19 epilogue:
+// FOUR epilogue warpgroups, warpgroup g drains accumulator buffer g (tile it -> buffer it & 3).  The thread-per-row
+// epilogue of a narrow tile is latency-bound (profiles/r01_exp_epilogue_cost.log: one or two warps per scheduler
+// partition expose every TMEM-load / shared-load / FMA -> MAX -> CVT chain) and paced the C = 48 convs at 2,150 clk per
+// tile where the MMAs need 1,190; four warps per partition hide those latencies behind each other.  20 warps cap a
+// thread at 96 registers (5 warps on a partition share its 16 K registers).
+constexpr int kCPThreads = 640;
+constexpr int kCPEpiGroups = 4;
 
 struct __align__(8) ChainPatchBars {
   uint64_t b_full;          // resident weights of the current conv have landed (one phase per conv of this CTA)
@@ -443,8 +516,6 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
   const uint32_t a_base = smem_base + (uint32_t)p.b_bytes;
   ChainPatchBars* bars = reinterpret_cast<ChainPatchBars*>(smem_aligned + (size_t)p.b_bytes + (size_t)p.nslots * p.slot_bytes);
   const int n_issuers = p.mma_warps == 2 ? 2 : 1;
-  const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const int total_tiles = cp.nconv * p.total_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int k = 0; k < cp.nconv; ++k) {
@@ -462,11 +533,20 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
     }
     for (int i = 0; i < kChainRing; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->ring.full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->ring.empty[i]), 1u + (uint32_t)n_issuers + 256u);
+      ptx::mbar_init(ptx::smem_u32(&bars->ring.empty[i]), 1u + (uint32_t)n_issuers + 128u * kCPEpiGroups);
     }
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), (uint32_t)p.tmem_cols);
+  // BN scale / bias of EVERY conv of the chain (constants): [conv][scale | bias][Cout] behind the barriers
+  float* s_sb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
+  if (warp >= 4) {
+    for (int k = 0; k < cp.nconv; ++k)
+      for (int i = threadIdx.x - 128; i < p.Cout; i += 128 * kCPEpiGroups) {
+        s_sb[(2 * k) * p.Cout + i] = cp.conv[k].scale[i];
+        s_sb[(2 * k + 1) * p.Cout + i] = cp.conv[k].bias[i];
+      }
+  }
   ptx::tc_fence_before_sync();
   __syncthreads();
   ptx::tc_fence_after_sync();
@@ -483,28 +563,39 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
     if (ptx::elect_one()) {
       RingWriter rw; rw.init(&bars->ring);
       long long dbg_dep = 0; int dbg_tiles = 0;
+      // one ticket = one tile row of one image (tiles_w neighbouring tiles: same dependencies, overlapping input patches)
+      const int units = p.N * p.tiles_h;                         // tile rows of this launch
+      const unsigned total_chunks = (unsigned)(cp.nconv * units);
+      long long dbg_tk = 0, dbg_ring = 0;
       unsigned next = atomicAdd(&cp.ctrl[0], 1u);
       for (;;) {
-        const unsigned t = next;
-        rw.acquire_slot();
-        if (t >= (unsigned)total_tiles) { rw.publish(kChainDone); break; }
+        long long tq = cp.dbg ? clock64() : 0;
+        const unsigned t = next;                                 // (first use of the atomic's result: waits for it)
+        if (t >= total_chunks) { rw.acquire_slot(); rw.publish(kChainDone); break; }
         next = atomicAdd(&cp.ctrl[0], 1u);
-        const int k = (int)t / p.total_tiles;
-        const int tile = (int)t - k * p.total_tiles;
+        const int k = (int)t / units;
+        const int u = (int)t - k * units;                        // unit = img * tiles_h + th
+        const int img = u / p.tiles_h;
+        const int th = u - img * p.tiles_h;
+        if (cp.dbg) { const long long tn = clock64(); dbg_tk += tn - tq; tq = tn; }
         if (k > 0) {
           // the 10 x 18 input patch of an 8 x 16 tile touches the 3 x 3 neighbouring tiles of the same image: tile rows
-          // th-1 .. th+1 of that image must be complete (tiles_w arrivals each)
-          const long long tq = cp.dbg ? clock64() : 0;
-          const int img = tile / tiles_per_img;
-          const int th = (tile - img * tiles_per_img) / p.tiles_w;
-          chain_wait_units(cp.counters + (size_t)(k - 1) * cp.unit_stride + img * p.tiles_h, max(th - 1, 0),
-                           min(th + 1, p.tiles_h - 1), (unsigned)p.tiles_w);
-          if (cp.dbg) dbg_dep += clock64() - tq;
+          // th-1 .. th+1 of that image must be complete
+          const int nb = 1 + (th > 0 ? 1 : 0) + (th < p.tiles_h - 1 ? 1 : 0);
+          chain_wait_counter(cp.counters + (size_t)(k - 1) * cp.unit_stride + u, (unsigned)(nb * p.tiles_w));
+          fence_proxy_async_all();   // the acquired generic-proxy stores before the TMA (async-proxy) reads issued downstream
+          if (cp.dbg) { const long long tn = clock64(); dbg_dep += tn - tq; tq = tn; }
         }
-        rw.publish(((uint32_t)k << 28) | (uint32_t)tile);
-        ++dbg_tiles;
+        const uint32_t c0 = ((uint32_t)img << 16) | ((uint32_t)th << 8);
+        for (int tw = 0; tw < p.tiles_w; ++tw) {
+          rw.acquire_slot();
+          rw.publish(((uint32_t)k << 28) | (uint32_t)(u * p.tiles_w + tw), c0 | (uint32_t)tw);
+          ++dbg_tiles;
+        }
+        if (cp.dbg) dbg_ring += clock64() - tq;
       }
-      if (cp.dbg) { cp.dbg[blockIdx.x * 8 + 0] = dbg_dep; cp.dbg[blockIdx.x * 8 + 1] = dbg_tiles; }
+      if (cp.dbg) { cp.dbg[blockIdx.x * 16 + 8] = dbg_tk; cp.dbg[blockIdx.x * 16 + 9] = dbg_ring; }
+      if (cp.dbg) { cp.dbg[blockIdx.x * 16 + 0] = dbg_dep; cp.dbg[blockIdx.x * 16 + 1] = dbg_tiles; }
     }
     __syncwarp();
   } else if (warp == 0) {
@@ -532,11 +623,14 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
       const int nw = n_issuers;
       const int ring = nw == 2 ? p.nslots / 2 : p.nslots;
       int L0 = 0, L1 = 0;                   // chunk loads issued into each pipeline's slot ring
+      long long dbg_pring = 0, dbg_pslot = 0;
       for (int it = 0;; ++it) {
-        const uint32_t info = rr.next();
+        long long tq = cp.dbg ? clock64() : 0;
+        uint32_t coord;
+        const uint32_t info = rr.next(coord);
+        if (cp.dbg) dbg_pring += clock64() - tq;
         if (info == kChainDone) break;
         const int k = (int)(info >> 28);
-        const int tile = (int)(info & 0x0fffffffu);
         if (k != cur_k) {
           cur_k = k;
           // the MMAs of every earlier tile of this CTA (all issuers) must have retired before the overwrite
@@ -546,22 +640,21 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
         }
         const int w = nw == 2 ? (it & 1) : 0;
         const int sbase = w * ring;
-        const int img = tile / tiles_per_img;
-        const int rem = tile - img * tiles_per_img;
-        const int th = rem / p.tiles_w;
-        const int tw = rem - th * p.tiles_w;
-        fence_proxy_async_all();       // the scheduler's acquire (generic proxy) before this tile's TMA reads
+        const int img = (int)(coord >> 16), th = (int)((coord >> 8) & 255u), tw = (int)(coord & 255u);
         for (int j = 0; j < p.nchunks; ++j) {
           const int L = w ? L1++ : L0++;
           const int slot = sbase + L % ring;
           const uint32_t phase = (uint32_t)((L / ring) & 1);
+          if (cp.dbg) tq = clock64();
           ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[slot]), phase ^ 1u);
+          if (cp.dbg) dbg_pslot += clock64() - tq;
           const uint32_t full = ptx::smem_u32(&bars->a_full[slot]);
           ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 128));
           ptx::tma_load_4d(a_base + (uint32_t)(slot * p.slot_bytes), &maps.a[k], full, p.c0[j], tw * kPatchTW - 1,
                            th * kPatchTH - 1, img);
         }
       }
+      if (cp.dbg) { cp.dbg[blockIdx.x * 16 + 10] = dbg_pring; cp.dbg[blockIdx.x * 16 + 11] = dbg_pslot; }
     }
     __syncwarp();
   } else if (warp == 2 || (warp == 3 && n_issuers == 2)) {
@@ -580,12 +673,18 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
       bool ready = false;
       int cur_k = 0;
       int nswitch = 0;
+      const bool dbg_on = cp.dbg != nullptr && mw == 0;
+      long long dbg_wfull = 0, dbg_wtm = 0, dbg_wsw = 0;
       ptx::mbar_wait(bfull, 0);               // conv 0's weights
       for (int it = 0;; ++it) {
         const uint32_t info = rr.next();
-        if (info == kChainDone) break;
+        if (info == kChainDone) {
+          if (dbg_on) { cp.dbg[blockIdx.x * 16 + 5] = dbg_wfull; cp.dbg[blockIdx.x * 16 + 6] = dbg_wtm; cp.dbg[blockIdx.x * 16 + 7] = dbg_wsw; }
+          break;
+        }
         const int k = (int)(info >> 28);
         if (k != cur_k) {
+          const long long tsw = dbg_on ? clock64() : 0;
           // every issuer walks every ring entry, so both see every conv switch of this CTA, in order: retire the
           // MMAs that read the old weights, then wait for the new set (each b_full phase is waited exactly once)
           cur_k = k;
@@ -593,15 +692,20 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
           ++nswitch;
           ptx::mbar_wait(bfull, (uint32_t)(nswitch & 1));
           ptx::tc_fence_after_sync();
+          if (dbg_on) dbg_wsw += clock64() - tsw;
         }
         if (nw == 2 && (it & 1) != mw) continue;
         const int acc = it & (p.nacc - 1);
         const uint32_t acc_phase = (uint32_t)((it >> p.nacc_log2) & 1);
+        long long tq = dbg_on ? clock64() : 0;
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        if (dbg_on) { const long long t = clock64(); dbg_wtm += t - tq; }
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
         for (int j = 0; j < p.nchunks; ++j) {
+          if (dbg_on) tq = clock64();
           if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->a_full[sbase + slot]), phase);
+          if (dbg_on) dbg_wfull += clock64() - tq;
           ptx::tc_fence_after_sync();
           const uint32_t a_slot = a_base + (uint32_t)((sbase + slot) * p.slot_bytes);
           const uint32_t brow = (uint32_t)p.bkc[j] * 2u;
@@ -628,7 +732,7 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================================================================== epilogue (two warpgroups, alternating tiles)
+    // ===================================================================== epilogue (four warpgroups, tile it -> it & 3)
     const int g = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -636,33 +740,37 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
     const bool leader = (q == 0) && (lane == 0);
     ptx::pdl_wait();
     RingReader rr; rr.init(&bars->ring);
+    long long dbg_work = 0, dbg_wait = 0;
     for (int it = 0;; ++it) {
-      const uint32_t info = rr.next();
+      uint32_t coord;
+      const uint32_t info = rr.next(coord);
       if (info == kChainDone) break;
-      if ((it & 1) != g) continue;
+      if ((it & (kCPEpiGroups - 1)) != g) continue;
       const int k = (int)(info >> 28);
-      const int tile = (int)(info & 0x0fffffffu);
       const ChainConv& cv = cp.conv[k];
       const int acc = it & (p.nacc - 1);
       const uint32_t acc_phase = (uint32_t)((it >> p.nacc_log2) & 1);
-      const int img = tile / tiles_per_img;
-      const int rem = tile - img * tiles_per_img;
-      const int th = rem / p.tiles_w;
-      const int tw = rem - th * p.tiles_w;
+      const int img = (int)(coord >> 16), th = (int)((coord >> 8) & 255u), tw = (int)(coord & 255u);
       const int oh = th * kPatchTH + dh, ow = tw * kPatchTW + dw;
       EpiRow e;
-      e.s_scale = cv.scale; e.s_bias = cv.bias; e.residual = cv.residual; e.out = cv.out;
+      e.s_scale = s_sb + (2 * k) * p.Cout; e.s_bias = e.s_scale + p.Cout; e.residual = cv.residual; e.out = cv.out;
       e.row_off = (((size_t)img * p.H + oh) * p.W + ow) * p.Cout;
       e.ch0 = 0; e.ncols = p.Cout; e.relu = cv.relu; e.out_f32 = 0; e.valid = oh < p.H && ow < p.W;
-      uint4 rres[8];
-      chain_load_residual(rres, e, 0);
+      U256 r0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r0.w[i] = 0u;
+      if (e.residual != nullptr && e.valid) r0 = ldg256_cg(e.residual + e.row_off);   // in flight while the MMAs of this tile finish
+      long long tq = cp.dbg ? clock64() : 0;
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
+      if (cp.dbg) { const long long t = clock64(); dbg_wait += t - tq; tq = t; }
       ptx::tc_fence_after_sync();
-      chain_store_row(rres, e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout));
+      chain_store_row_lean(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout), r0);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
-      chain_publish_tile(cp.counters + (size_t)k * cp.unit_stride + img * p.tiles_h + th, 1 + g, leader);
+      chain_publish_tile(cp.counters + (size_t)k * cp.unit_stride + img * p.tiles_h + th, th > 0, th < p.tiles_h - 1, 1 + g, leader);
+      if (cp.dbg) dbg_work += clock64() - tq;
     }
+    if (cp.dbg && threadIdx.x == 128) { cp.dbg[blockIdx.x * 16 + 3] = dbg_wait; cp.dbg[blockIdx.x * 16 + 4] = dbg_work; }
   }
 
   ptx::tc_fence_before_sync();
@@ -671,7 +779,7 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
-  if (cp.dbg && threadIdx.x == 0) cp.dbg[blockIdx.x * 8 + 2] = clock64() - t_begin;
+  if (cp.dbg && threadIdx.x == 0) cp.dbg[blockIdx.x * 16 + 2] = clock64() - t_begin;
   chain_exit(cp.ctrl, cp.counters, cp.nconv, p.N * p.tiles_h, cp.unit_stride, &bars->pad);
 }
 
@@ -680,12 +788,6 @@ cudaError_t conv_chain_set_attributes(int max_smem) {
   cudaError_t e = cudaFuncSetAttribute(conv_chain_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_chain_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   return e;
-}
-
-static bool chain_pdl_enabled() {
-  static int v = -1;
-  if (v < 0) v = getenv("HRNET_B200_NO_PDL") ? 0 : 1;
-  return v == 1;
 }
 
 template <typename K, typename M, typename P>
@@ -697,7 +799,7 @@ static cudaError_t launch_chain(K kernel, const M& maps, const P& p, int threads
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   int na = 0;
-  if (chain_pdl_enabled()) {
+  if (p.pdl) {
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

@@ -73,9 +73,7 @@ cudaError_t launch_conv_group(const GroupLaunch& g, cudaStream_t st) {
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   int na = 0;
-  static int pdl = -1;
-  if (pdl < 0) pdl = getenv("HRNET_B200_NO_PDL") ? 0 : 1;
-  if (pdl) {
+  if (g.pdl) {
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

@@ -1,6 +1,5 @@
 // Single-problem launches of the TMA-im2col implicit-GEMM conv (body and documentation: conv_igemm_body.cuh).
 #include <algorithm>
-#include <cstdlib>
 
 #include "conv_igemm_body.cuh"
 
@@ -57,12 +56,6 @@ int conv_tc_grid(const ConvTcParams& p, int smem_bytes, int num_sms) {
   return std::min(need, max_clusters) * cs;
 }
 
-static bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) v = getenv("HRNET_B200_NO_PDL") ? 0 : 1;
-  return v == 1;
-}
-
 cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmOR, const ConvTcParams& p,
                            int smem_bytes, int grid, cudaStream_t st) {
   // without the staged epilogue the two extra maps are never dereferenced: pass any valid descriptor
@@ -80,7 +73,7 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     at[na].val.clusterDim.x = (unsigned)p.cs; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl_enabled()) {   // prologue overlaps the tail of the previous kernel in the stream (ptx::pdl_wait)
+  if (p.pdl) {   // prologue overlaps the tail of the previous kernel in the stream (ptx::pdl_wait)
     at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

@@ -74,6 +74,7 @@ struct ConvTcParams {
   int tmem_cols;
   int a_blk_bytes, b_blk_bytes;
   int epi_tma, epi_bytes;   // epilogue (epilogue.cuh): 0 direct, 1 staged TMA stores, 2 warp-staged coalesced; staging follows the stages
+  int pdl;                  // host side: launch with programmatic stream serialization
   const float* scale;
   const float* bias;
   const __half* residual;
@@ -101,6 +102,7 @@ struct ConvPatchParams {
   int cs;                      // 2: CTA-pair mode (cta_group::2), each CTA keeps Cout / 2 weight rows; else 1
   int relu, out_f32, tmem_cols;
   int epi_tma, epi_bytes;      // epilogue: 0 direct, 1 staged TMA stores, 2 warp-staged coalesced; staging follows the patch slots
+  int pdl;                     // host side: launch with programmatic stream serialization
   const float* scale;
   const float* bias;
   const __half* residual;
@@ -139,6 +141,7 @@ struct ChainIgemmParams {
   int M_total, OH, OW, OHW, C;
   int cpt, nkb, bps, n_tile, n_tiles, m_tiles, stages, tmem_cols, a_blk_bytes, b_blk_bytes;
   int unit_stride;           // counters per conv (M-tiles at max batch)
+  int pdl;                   // host side: launch with programmatic stream serialization
   unsigned* ctrl;
   unsigned* counters;
   long long* dbg;            // optional per-CTA counters (8 x int64 per CTA)
@@ -149,6 +152,8 @@ struct ChainPatchParams {
   int nconv;
   ConvPatchParams pp;        // geometry / shared-memory layout common to all convs of the chain (scale .. out unused)
   int unit_stride;           // counters per conv (tile rows at max batch)
+  int chunk;                 // tiles per ticket: a divisor of pp.tiles_w (neighbouring tiles of one tile row)
+  int pdl;                   // host side: launch with programmatic stream serialization
   unsigned* ctrl;
   unsigned* counters;
   long long* dbg;
@@ -210,6 +215,7 @@ struct GroupLaunch {
   CUtensorMap igemm_map_a[2], igemm_map_b[2];
   ConvTcParams ip[2];
   int smem_bytes = 0;
+  int pdl = 1;
 };
 cudaError_t launch_conv_group(const GroupLaunch& g, cudaStream_t st);
 cudaError_t conv_group_set_attributes(int max_smem);

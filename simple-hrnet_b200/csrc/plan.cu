@@ -32,6 +32,9 @@ int fail(int code, const std::string& msg) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// tuning knobs of the single-op entry points (hrnet_debug_set_tune); plans carry their own copy in HrnetDesc::tune
+int32_t g_single_op_tune[HRNET_TUNE_COUNT] = {0};
+
 }  // namespace hrnet
 
 using namespace hrnet;
@@ -76,7 +79,6 @@ struct HrnetPlan {
   cudaEvent_t fork_ev = nullptr;
   std::map<int, cudaGraphExec_t> graphs;
   int launch_count = 0;
-  bool input_u8 = false;   // current call feeds NHWC BGR uint8 images (hrnet_forward_u8)
 };
 
 namespace {
@@ -165,7 +167,7 @@ struct Builder {
   }
 };
 
-void choose_tc_cfg(Op& op, uint32_t flags, int max_nt = 256) {
+void choose_tc_cfg(Op& op, uint32_t flags, const int32_t* tune, int max_nt = 256) {
   op.use_tc = false;
   if (flags & HRNET_FLAG_FORCE_SIMT) return;
   if (op.kind != OP_CONV) return;
@@ -182,21 +184,15 @@ void choose_tc_cfg(Op& op, uint32_t flags, int max_nt = 256) {
   c.n_tile = nt;
   // k-blocks per pipeline stage: every stage costs the issuing threads a barrier wait, an expect_tx and a commit
   // (~300 clk, conv_igemm_body.cuh); with narrow tiles that is more than the stage's MMAs, so two k-blocks share a
-  // stage when four such stages still fit (HRNET_B200_BPS overrides).
+  // stage when four such stages still fit (HRNET_TUNE_BPS overrides).
   c.bps = (nt <= 64 && op.k * op.k * ((op.cin + 63) / 64) >= 4) ? 2 : 1;
-  if (const char* e = getenv("HRNET_B200_BPS")) { const int v = atoi(e); if (v == 1 || v == 2) c.bps = v; }
+  if (tune[HRNET_TUNE_BPS] == 1 || tune[HRNET_TUNE_BPS] == 2) c.bps = tune[HRNET_TUNE_BPS];
   // CTA-pair mode (tcgen05 cta_group::2): each CTA stages half of the weight tile.  Measured on B200 it makes the
   // large-N kernels faster in isolation (stage-4 C=192/384 convs 46 -> 42.7 us, 2.3x fewer clk per GEMM row) but the
   // whole W48/64 forward slower (9.76 vs 9.46 ms: pair clusters co-schedule worse with the other branches' kernels,
-  // profiles/r01_exp_pair_mode_scope.log), so it is opt-in: HRNET_B200_CS=2 (optionally HRNET_B200_CS_MINK=<K>).
-  c.cs = 1;
-  if (const char* e = getenv("HRNET_B200_CS")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2) c.cs = v;
-  }
-  if (const char* e = getenv("HRNET_B200_CS_MINK")) {   // experiments: pair mode only for convs with at least this K
-    if (op.k * op.k * op.cin < atoi(e)) c.cs = 1;
-  }
+  // profiles/r01_exp_pair_mode_scope.log), so it is opt-in: HRNET_TUNE_IGEMM_PAIR = 2 (optionally _PAIR_MIN_K).
+  c.cs = tune[HRNET_TUNE_IGEMM_PAIR] == 2 ? 2 : 1;
+  if (op.k * op.k * op.cin < tune[HRNET_TUNE_IGEMM_PAIR_MIN_K]) c.cs = 1;   // pair mode only for convs with at least this K
   if (nt % 16 || (nt / 2) % 8) c.cs = 1;
   // two MMA-issuing warps on alternate tiles (conv_igemm_body.cuh): HRNET_B200_IGEMM_MMA2=1 (all convs) or =<max N>
   // (only tiles at most that wide, where the issue side rather than shared-memory bandwidth sets the pace)
@@ -212,9 +208,9 @@ void choose_tc_cfg(Op& op, uint32_t flags, int max_nt = 256) {
   // two MMA-issuing warps on alternate tiles, each with half of the stage ring (conv_igemm_body.cuh): on for tiles at
   // most 96 channels wide, where per-tile barrier / commit latencies rather than shared-memory bandwidth set the pace
   // (forward 7.81 -> 7.71 ms); wider tiles lose more from the halved ring (C = 384 branch conv 35 -> 52 us).
-  // HRNET_B200_IGEMM_MMA2=0 (off) / 1 (all convs) / <max N> overrides.
+  // HRNET_TUNE_IGEMM_MMA2 = -1 (off) / 1 (all convs) / <max N> overrides.
   int mma2_max_n = 96;
-  if (const char* e = getenv("HRNET_B200_IGEMM_MMA2")) { const int v = atoi(e); mma2_max_n = v == 1 ? 1 << 30 : v; }
+  if (tune[HRNET_TUNE_IGEMM_MMA2]) { const int v = tune[HRNET_TUNE_IGEMM_MMA2]; mma2_max_n = v == 1 ? 1 << 30 : v; }
   c.mma_warps = nt <= mma2_max_n ? 2 : 1;
   if (c.cs == 2 || c.stages < 4) c.mma_warps = 1;
   c.smem_bytes = fixed + c.stages * stage;
@@ -228,7 +224,7 @@ void choose_tc_cfg(Op& op, uint32_t flags, int max_nt = 256) {
 // Halo-patch path: 3x3 stride-1 convs whose 9-tap weights fit in shared memory next to >= 2 patch slots and
 // whose map tiles into 8x16 output tiles with little waste.
 constexpr int kMaxDynSmem = 226 * 1024;
-bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
+bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags, const int32_t* tune) {
   op.use_patch = false;
   if (flags & (HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_NO_PATCH)) return false;
   if (op.kind != OP_CONV || op.k != 3 || op.stride != 1 || op.pad != 1) return false;
@@ -237,13 +233,12 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
   if ((double)(H * W) / (double)(tw * kPatchTW * th * kPatchTH) < 0.85) return false;
   ConvPatchParams p{};
   p.H = H; p.W = W; p.Cin = op.cin; p.Cout = op.cout; p.tiles_w = tw; p.tiles_h = th;
-  // CTA-pair mode (conv3x3_patch_body.cuh): HRNET_B200_PATCH_PAIR=<min Cout> enables it for convs with at least that
-  // many (and at most HRNET_B200_PATCH_PAIR_MAX) output channels; each CTA then keeps Cout / 2 weight rows.
+  // CTA-pair mode (conv3x3_patch_body.cuh): HRNET_TUNE_PATCH_PAIR_MIN_COUT enables it for convs with at least that
+  // many (and at most HRNET_TUNE_PATCH_PAIR_MAX_COUT) output channels; each CTA then keeps Cout / 2 weight rows.
   p.cs = 1;
   if (!(flags & HRNET_FLAG_GROUP)) {
-    int pair_min = 0, pair_max = 1 << 30;
-    if (const char* e = getenv("HRNET_B200_PATCH_PAIR")) pair_min = atoi(e);
-    if (const char* m = getenv("HRNET_B200_PATCH_PAIR_MAX")) pair_max = atoi(m);
+    const int pair_min = tune[HRNET_TUNE_PATCH_PAIR_MIN_COUT];
+    const int pair_max = tune[HRNET_TUNE_PATCH_PAIR_MAX_COUT] > 0 ? tune[HRNET_TUNE_PATCH_PAIR_MAX_COUT] : 1 << 30;
     if (pair_min > 0 && op.cout >= pair_min && op.cout <= pair_max && op.cout % 16 == 0) p.cs = 2;
   }
   const int b_rows = op.cout / p.cs;
@@ -278,16 +273,16 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
     if (avail < 2 * p.slot_bytes) return false;
   }
   p.nslots = std::min(8, avail / p.slot_bytes) & ~1;   // two producer warps alternate slots
-  // accumulator buffers: 4 when they fit the 512 TMEM columns (HRNET_B200_PATCH_NACC=2 forces double buffering)
+  // accumulator buffers: 4 when they fit the 512 TMEM columns (HRNET_TUNE_PATCH_NACC = 2 forces double buffering)
   p.nacc = 4 * op.cout <= 512 ? 4 : 2;
-  if (const char* e = getenv("HRNET_B200_PATCH_NACC")) { if (atoi(e) == 2) p.nacc = 2; }
+  if (tune[HRNET_TUNE_PATCH_NACC] == 2) p.nacc = 2;
   p.nacc_log2 = p.nacc == 4 ? 2 : 1;
   // two MMA-issuing warps on alternate tiles, each with half of the slot ring (conv3x3_patch_body.cuh): on when every
   // ring keeps two slots (C = 48 branch convs 39.7 -> 33.9 us, layer1 conv2 47.8 -> 44.8; with one slot per ring the
   // C = 96 convs and the streamed-weight transition conv get slower, profiles/r01_exp_mma2_issuers.log).
-  // HRNET_B200_PATCH_MMA2=0/1 overrides.
+  // HRNET_TUNE_PATCH_MMA2 = 1 (one issuer) / 2 (two) overrides.
   p.mma_warps = p.nslots >= 4 ? 2 : 1;
-  if (const char* e = getenv("HRNET_B200_PATCH_MMA2")) p.mma_warps = atoi(e) ? 2 : 1;
+  if (tune[HRNET_TUNE_PATCH_MMA2] == 1 || tune[HRNET_TUNE_PATCH_MMA2] == 2) p.mma_warps = tune[HRNET_TUNE_PATCH_MMA2];
   if (p.cs == 2) p.mma_warps = 1;
   int cols = 32;
   while (cols < p.nacc * op.cout) cols *= 2;
@@ -303,38 +298,31 @@ bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags) {
 //   1 staged TMA stores        : tiles at least 256 channels wide (layer1 conv3 / downsample: 136 -> 104 us)
 //   2 warp-staged coalesced    : everything else, when the 36 KB of staging fit next to the pipeline
 //   0 direct row-per-thread    : fp32 outputs, sub-pixel phases, or no shared memory left (C = 96 halo-patch conv)
-// HRNET_B200_EPI = auto (default) | direct | tma (TMA wherever eligible) | coal (coalesced wherever it fits) |
-// batch (kind 3: direct stores with batched TMEM loads on tiles <= 64 channels, not yet run on hardware); read at
-// plan time.  The staging tiles are carved out of the pipeline's shared memory.
-int epi_policy() {
-  const char* e = getenv("HRNET_B200_EPI");
-  if (!e || !strcmp(e, "auto")) return 0;
-  if (!strcmp(e, "direct")) return 1;
-  if (!strcmp(e, "tma")) return 2;
-  if (!strcmp(e, "coal")) return 3;
-  if (!strcmp(e, "tma_patch")) return 4;    // experiments: TMA epilogue on every halo-patch conv, auto elsewhere
-  if (!strcmp(e, "tma_igemm")) return 5;    // experiments: TMA epilogue on every im2col conv, auto elsewhere
-  if (!strcmp(e, "batch")) return 6;        // experiments: batched TMEM loads (kind 3) on tiles <= 64 channels, auto elsewhere
-  return 0;
+// HRNET_TUNE_EPILOGUE = 0 auto | 1 direct | 2 tma (TMA wherever eligible) | 3 coal (coalesced wherever it fits) |
+// 4 / 5 TMA on every halo-patch / im2col conv | 6 batch (kind 3: direct stores with batched TMEM loads on tiles <= 64
+// channels); read at plan time.  The staging tiles are carved out of the pipeline's shared memory.
+int epi_policy(const int32_t* tune) {
+  const int v = tune[HRNET_TUNE_EPILOGUE];
+  return v >= 0 && v <= 6 ? v : 0;
 }
 // The epilogue staging tiles are carved out of the pipeline's shared memory: re-check that every issuer's ring keeps its
 // minimum depth once the final slot / stage counts are known.
-void finalize_mma_warps(Op& op) {
+void finalize_mma_warps(Op& op, const int32_t* tune) {
   if (!op.use_tc) return;
   if (op.use_patch) {
-    if (op.pp.mma_warps == 2 && op.pp.nslots < 4 && !getenv("HRNET_B200_PATCH_MMA2")) op.pp.mma_warps = 1;
+    if (op.pp.mma_warps == 2 && op.pp.nslots < 4 && !tune[HRNET_TUNE_PATCH_MMA2]) op.pp.mma_warps = 1;
   } else if (op.tc.mma_warps == 2 && op.tc.stages < 4) {
     op.tc.mma_warps = 1;
   }
 }
 
-void choose_epi_impl(Op& op, bool out_f32, bool sub, bool has_res);
-void choose_epi(Op& op, bool out_f32, bool sub, bool has_res) {
-  choose_epi_impl(op, out_f32, sub, has_res);
-  finalize_mma_warps(op);
+void choose_epi_impl(Op& op, bool out_f32, bool sub, bool has_res, const int32_t* tune);
+void choose_epi(Op& op, bool out_f32, bool sub, bool has_res, const int32_t* tune) {
+  choose_epi_impl(op, out_f32, sub, has_res, tune);
+  finalize_mma_warps(op, tune);
 }
-void choose_epi_impl(Op& op, bool out_f32, bool sub, bool has_res) {
-  const int policy = epi_policy();
+void choose_epi_impl(Op& op, bool out_f32, bool sub, bool has_res, const int32_t* tune) {
+  const int policy = epi_policy(tune);
   if (!op.use_tc || policy == 1 || out_f32 || sub) return;
   const int width = op.use_patch ? op.pp.Cout : op.tc.n_tile;
   if (policy == 6 && width <= 64 && (op.use_patch ? op.pp.cs : op.tc.cs) == 1) {   // no staging memory needed
@@ -627,7 +615,7 @@ void plan_chains(HrnetPlan& P) {
       ok = ok && o.use_tc && o.use_patch == o0.use_patch && o.cin == o0.cin && o.cout == o0.cout && o.k == 3 &&
            o.stride == 1 && P.tensors[o.in].H == P.tensors[o0.in].H && P.tensors[o.in].W == P.tensors[o0.in].W &&
            P.tensors[o.out].dtype == DT_F16;
-      if (o.use_patch) ok = ok && o.pp.cs == 1 && !o.pp.b_stream && o.pp.epi_tma == 0;
+      if (o.use_patch) ok = ok && o.pp.cs == 1 && !o.pp.b_stream && o.pp.epi_tma == 0 && o.pp.nacc == 4;
       else ok = ok && o.tc.cs == 1 && o.tc.epi == 0 && o.tc.n_tile <= 256 && o.cout / o.tc.n_tile <= 15;
     }
     if (!ok) continue;
@@ -636,7 +624,8 @@ void plan_chains(HrnetPlan& P) {
     const TensorInfo& ti = P.tensors[o0.in];
     const double k16 = 9.0 * ((o0.cin + 15) / 16);
     if (ch.patch) {
-      ch.smem = o0.patch_smem;
+      ch.smem = o0.patch_smem + (int)(ch.ops.size() - 1) * 2 * o0.cout * 4;   // BN constants of every conv stay in shared memory
+      if (ch.smem > kMaxDynSmem) { ch.enabled = false; continue; }
       ch.flag_stride = P.desc.max_batch * o0.pp.tiles_h;             // one counter per row of tiles of an image
       ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * o0.work;
     } else {
@@ -686,10 +675,10 @@ void finalize_schedule(HrnetPlan& P) {
   for (auto& op : P.ops) {
     // chain members keep N tiles <= 192 wide (two accumulators in TMEM, direct epilogue) and the direct epilogue
     const bool cand = chain_cfg && op.chain >= 0;
-    choose_tc_cfg(op, P.desc.flags, cand ? 192 : 256);
-    if (op.use_tc && op.in >= 0) choose_patch_cfg(op, P.tensors[op.in].H, P.tensors[op.in].W, P.desc.flags);
+    choose_tc_cfg(op, P.desc.flags, P.desc.tune, cand ? 192 : 256);
+    if (op.use_tc && op.in >= 0) choose_patch_cfg(op, P.tensors[op.in].H, P.tensors[op.in].W, P.desc.flags, P.desc.tune);
     if (op.use_tc && op.out >= 0 && !(P.desc.flags & HRNET_FLAG_GROUP) && !cand)
-      choose_epi(op, P.tensors[op.out].dtype == DT_F32, op.pad >= 100, op.res >= 0);
+      choose_epi(op, P.tensors[op.out].dtype == DT_F32, op.pad >= 100, op.res >= 0, P.desc.tune);
   }
   // (Opt-in, HRNET_FLAG_PARTITION; measured SLOWER than letting every kernel use all SMs: 12.85 vs 9.9 ms per
   // W48/64 forward, profiles/r01_exp_variants_partition_pdl.log -- total work is unchanged and the low-resolution
@@ -934,6 +923,10 @@ extern "C" {
 
 const char* hrnet_last_error(void) { return g_last_error.c_str(); }
 
+void hrnet_debug_set_tune(const int32_t* tune) {
+  for (int i = 0; i < HRNET_TUNE_COUNT; ++i) g_single_op_tune[i] = tune ? tune[i] : 0;
+}
+
 int hrnet_plan_create(const HrnetDesc* desc, HrnetPlan** out) {
   if (!desc || !out) return fail(HRNET_E_INVALID, "null argument");
   if (desc->height <= 0 || desc->width <= 0 || desc->height % 32 || desc->width % 32)
@@ -1176,6 +1169,7 @@ ConvPatchParams fill_patch_params(HrnetPlan* P, const Op& op, int n) {
   p.bias = (const float*)(P->wbase + pi.bias_offset);
   p.residual = op.res >= 0 ? (const __half*)(P->abase + P->tensors[op.res].offset) : nullptr;
   p.out = P->abase + to.offset;
+  p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
   return p;
 }
 
@@ -1202,6 +1196,7 @@ ConvTcParams fill_tc_params(HrnetPlan* P, const Op& op, int n) {
   p.residual = op.res >= 0 ? (const __half*)(P->abase + P->tensors[op.res].offset) : nullptr;
   p.out = P->abase + to.offset;
   p.epi_tma = op.tc.epi; p.epi_bytes = op.tc.epi_bytes;
+  p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
   return p;
 }
 
@@ -1246,7 +1241,8 @@ int launch_group(HrnetPlan* P, int first, int last, int n, cudaStream_t st, std:
   }
   for (int k = 0; k < np; ++k) *slot[k] = c[k];
   if (cost_out) { cost_out->clear(); for (int k = 0; k < np; ++k) cost_out->push_back(units[k] * ucost[k]); }
-  if (getenv("HRNET_B200_DBG_GROUP")) {   // debug: per-problem finish times of one grouped launch
+  g.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
+  if (P->desc.tune[HRNET_TUNE_DEBUG] & 4) {   // debug: per-problem finish times of one grouped launch
     long long* dev = nullptr;
     const int grid = P->num_sms;
     if (cudaMalloc(&dev, (size_t)grid * 32 * sizeof(long long)) == cudaSuccess) {
@@ -1282,7 +1278,7 @@ int launch_group(HrnetPlan* P, int first, int last, int n, cudaStream_t st, std:
 }
 
 // One launch for the whole branch chain `c` at batch n on `grid` CTAs (<= 0: the chain's share inside the forward).
-int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st) {
+int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st, long long* dbg = nullptr) {
   const ChainInfo& ch = P->chains[c];
   const Op& o0 = P->ops[ch.ops[0]];
   if (grid <= 0) grid = ch.grid;
@@ -1304,9 +1300,11 @@ int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st) {
     p.pp = o0.pp;
     p.pp.N = n; p.pp.total_tiles = n * p.pp.tiles_w * p.pp.tiles_h;
     p.unit_stride = ch.flag_stride;
+    p.chunk = p.pp.tiles_w;   // one ticket = one tile row
+    p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
     p.ctrl = (unsigned*)(P->abase + ch.ctrl_off);
     p.counters = (unsigned*)(P->abase + ch.flags_off);
-    p.dbg = nullptr;
+    p.dbg = dbg;
     fill_convs(p.conv);
     if (p.pp.total_tiles == 0) return 0;
     grid = std::max(1, std::min(grid, p.pp.total_tiles));
@@ -1318,10 +1316,11 @@ int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st) {
     p.M_total = t.M_total; p.OH = t.OH; p.OW = t.OW; p.OHW = t.OHW; p.C = o0.cin;
     p.cpt = t.cpt; p.nkb = t.nkb; p.bps = t.bps; p.n_tile = t.n_tile; p.n_tiles = t.n_tiles; p.m_tiles = t.m_tiles;
     p.stages = t.stages; p.tmem_cols = t.tmem_cols; p.a_blk_bytes = t.a_blk_bytes; p.b_blk_bytes = t.b_blk_bytes;
+    p.pdl = t.pdl;
     p.unit_stride = ch.flag_stride;
     p.ctrl = (unsigned*)(P->abase + ch.ctrl_off);
     p.counters = (unsigned*)(P->abase + ch.flags_off);
-    p.dbg = nullptr;
+    p.dbg = dbg;
     fill_convs(p.conv);
     if (p.m_tiles * p.n_tiles == 0) return 0;
     grid = std::max(1, std::min(grid, p.m_tiles * p.n_tiles));
@@ -1330,15 +1329,16 @@ int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st) {
   return 0;
 }
 
+// in_u8: `in_ext` holds NHWC BGR uint8 images (hrnet_forward_u8) instead of the NCHW fp32 network input
 int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_ext, float* joints, int32_t* idx,
-              const float* boxes, cudaStream_t st) {
+              const float* boxes, cudaStream_t st, bool in_u8 = false) {
   auto tptr = [&](int t) -> uint8_t* { return P->abase + P->tensors[t].offset; };
   switch (op.kind) {
     case OP_STEM:
     case OP_STEM7: {
       const ParamInfo& pi = P->params[op.param];
       // conv1 runs on the tensor cores unless the SIMT cross-check path is forced
-      if (P->input_u8) {
+      if (in_u8) {
         if (op.kind != OP_STEM) return fail(HRNET_E_INVALID, "uint8 image input is implemented for the HRNet stem only");
         CK(launch_stem_tc_u8((const uint8_t*)in_ext, (const float*)(P->wbase + pi.w_offset),
                              (const float*)(P->wbase + pi.scale_offset), (const float*)(P->wbase + pi.bias_offset),
@@ -1370,6 +1370,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.bias = (const float*)(P->wbase + pi.bias_offset);
         p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
         p.out = tptr(op.out);
+        p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
         if (p.total_tiles == 0) return 0;
         const int cap = std::max(1, (int)std::lround(op.sm_frac * P->num_sms));
         CK(launch_conv_patch(op.tmPA, op.tmPB, op.tmOR, p, op.patch_smem, std::min(std::max(p.cs, cap / p.cs * p.cs), conv_patch_grid(p, P->num_sms)), st));
@@ -1390,6 +1391,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         p.residual = op.res >= 0 ? (const __half*)tptr(op.res) : nullptr;
         p.out = tptr(op.out);
         p.epi_tma = op.tc.epi; p.epi_bytes = op.tc.epi_bytes;
+        p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
         const int tiles = p.m_tiles * p.n_tiles;
         if (tiles == 0) return 0;
         const int cap = std::max(p.cs, (int)std::lround(op.sm_frac * P->num_sms) / p.cs * p.cs);
@@ -1437,7 +1439,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
 
 // launches ops [first, last) with stream fork/join according to the dependency lists
 int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, float* hm_ext, float* joints,
-              int32_t* idx, const float* boxes, cudaStream_t s0) {
+              int32_t* idx, const float* boxes, cudaStream_t s0, bool in_u8 = false) {
   auto stream_of = [&](int s) { return s == 0 ? s0 : P->side[s - 1]; };
   for (int i = first; i < last; ++i) {
     const Op& op = P->ops[i];
@@ -1470,14 +1472,13 @@ int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, flo
     }
     for (int dpi : op.deps)
       if (P->ops[dpi].stream != op.stream) CK(cudaStreamWaitEvent(st, P->events[dpi], 0));
-    int rc = launch_op(P, op, n, in_ext, hm_ext, joints, idx, boxes, st);
+    int rc = launch_op(P, op, n, in_ext, hm_ext, joints, idx, boxes, st, in_u8);
     if (rc) return rc;
     if (op.needs_event) CK(cudaEventRecord(P->events[i], st));
     // debug (HRNET_FLAG_NO_GRAPH only): synchronise after every op and print a hash of the n images of its output, so
     // two runs can be diffed op by op (tools/dbg_invariance.py)
     if ((P->desc.flags & HRNET_FLAG_NO_GRAPH) && op.out >= 0 && P->tensors[op.out].offset != (size_t)-1) {
-      static const bool on = getenv("HRNET_B200_DBG_CHECKSUM") != nullptr;
-      if (on) {
+      if (P->desc.tune[HRNET_TUNE_DEBUG] & 2) {
         CK(cudaStreamSynchronize(st));
         const size_t bytes = P->tensors[op.out].bytes(n);
         std::vector<uint8_t> h(bytes);
@@ -1494,10 +1495,8 @@ int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, flo
 
 }  // namespace
 
-extern "C" {
-
-int hrnet_forward(HrnetPlan* P, const float* in, int n, float* heatmaps, float* joints, int32_t* argmax_idx,
-                  const float* boxes, void* stream) {
+static int forward_impl(HrnetPlan* P, const float* in, int n, float* heatmaps, float* joints, int32_t* argmax_idx,
+                        const float* boxes, void* stream, bool in_u8) {
   if (!P) return fail(HRNET_E_INVALID, "null plan");
   if (!P->bound) return fail(HRNET_E_STATE, "hrnet_plan_bind must be called before hrnet_forward");
   if (n < 0 || n > P->desc.max_batch) return fail(HRNET_E_INVALID, "n out of range [0, max_batch]");
@@ -1507,7 +1506,7 @@ int hrnet_forward(HrnetPlan* P, const float* in, int n, float* heatmaps, float* 
   const int nops = (int)P->ops.size();
   // ops touching caller pointers stay outside the graph: first (stem) and the last two (head, argmax)
   const int g_first = 1, g_last = nops - 2;
-  int rc = run_range(P, 0, g_first, n, in, heatmaps, joints, argmax_idx, boxes, s0);
+  int rc = run_range(P, 0, g_first, n, in, heatmaps, joints, argmax_idx, boxes, s0, in_u8);
   if (rc) return rc;
   if (P->desc.flags & HRNET_FLAG_NO_GRAPH) {
     rc = run_range(P, g_first, g_last, n, in, heatmaps, joints, argmax_idx, boxes, s0);
@@ -1552,14 +1551,18 @@ int hrnet_forward(HrnetPlan* P, const float* in, int n, float* heatmaps, float* 
   return HRNET_OK;
 }
 
+extern "C" {
+
+int hrnet_forward(HrnetPlan* P, const float* in, int n, float* heatmaps, float* joints, int32_t* argmax_idx,
+                  const float* boxes, void* stream) {
+  return forward_impl(P, in, n, heatmaps, joints, argmax_idx, boxes, stream, false);
+}
+
 int hrnet_forward_u8(HrnetPlan* P, const uint8_t* images_nhwc_bgr, int n, float* heatmaps, float* joints,
                      int32_t* argmax_idx, const float* boxes, void* stream) {
   if (!P) return fail(HRNET_E_INVALID, "null plan");
   if (P->desc.arch != HRNET_ARCH_HRNET) return fail(HRNET_E_INVALID, "uint8 image input is implemented for HRNet only");
-  P->input_u8 = true;
-  const int rc = hrnet_forward(P, reinterpret_cast<const float*>(images_nhwc_bgr), n, heatmaps, joints, argmax_idx, boxes, stream);
-  P->input_u8 = false;
-  return rc;
+  return forward_impl(P, reinterpret_cast<const float*>(images_nhwc_bgr), n, heatmaps, joints, argmax_idx, boxes, stream, true);
 }
 
 static int forward_host_u8_impl(HrnetPlan* P, const uint8_t* images_h, int n, float* heatmaps_h, float* joints_h,
@@ -1669,6 +1672,41 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
     std::sort(t[i].begin(), t[i].end());
     usec_per_op[i] = t[i][iters / 2] * 1000.f;
   }
+  if (P->desc.tune[HRNET_TUNE_CHAIN_DEBUG]) {
+    // development aid: every chain once more with per-CTA role timers, alone on the whole GPU and on its in-forward grid
+    long long* dev = nullptr;
+    const int maxg = P->num_sms;
+    if (cudaMalloc(&dev, (size_t)maxg * 16 * sizeof(long long)) == cudaSuccess) {
+      for (size_t c = 0; c < P->chains.size(); ++c) {
+        const ChainInfo& ch = P->chains[c];
+        if (!ch.enabled) continue;
+        for (int g : {P->num_sms, ch.grid}) {
+          cudaMemset(dev, 0, (size_t)maxg * 16 * sizeof(long long));
+          cudaEvent_t a, b;
+          cudaEventCreate(&a); cudaEventCreate(&b);
+          cudaEventRecord(a, s0);
+          int rc = launch_chain_op(P, (int)c, n, g, s0, dev);
+          cudaEventRecord(b, s0);
+          if (rc || cudaStreamSynchronize(s0) != cudaSuccess) { cudaFree(dev); return fail(HRNET_E_CUDA, "chain debug launch failed"); }
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, a, b);
+          std::vector<long long> h((size_t)maxg * 16);
+          cudaMemcpy(h.data(), dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+          double avg[16] = {0};
+          int act = 0;
+          for (int bb = 0; bb < maxg; ++bb) if (h[(size_t)bb * 16 + 2]) { ++act; for (int k = 0; k < 16; ++k) avg[k] += (double)h[(size_t)bb * 16 + k]; }
+          for (double& v : avg) v /= std::max(1, act);
+          fprintf(stderr, "[chain-dbg] %s %s grid=%d (ctas seen %d) %.1f us | per CTA: tiles %.1f, cta clk %.0f, sched: ticket %.0f dep-wait %.0f "
+                  "ring %.0f | producer: ring-wait %.0f slot-wait %.0f | epi(wg0) wait_acc %.0f work %.0f | mma0 wait_full %.0f wait_tmem %.0f "
+                  "wait_weights %.0f\n",
+                  P->ops[ch.ops[0]].name.c_str(), ch.patch ? "patch" : "im2col", g, act, ms * 1000.f, avg[1], avg[2], avg[8], avg[0], avg[9],
+                  avg[10], avg[11], avg[3], avg[4], avg[5], avg[6], avg[7]);
+          cudaEventDestroy(a); cudaEventDestroy(b);
+        }
+      }
+      cudaFree(dev);
+    }
+  }
   for (auto& e : ev) cudaEventDestroy(e);
   for (auto& e : chain_ev) if (e) cudaEventDestroy(e);
   return HRNET_OK;
@@ -1707,7 +1745,7 @@ struct DbgTimers {
   int grid = 0;
   bool on() const { return dev != nullptr; }
   void begin(int g) {
-    if (!getenv("HRNET_B200_DBG")) return;
+    if (!(g_single_op_tune[HRNET_TUNE_DEBUG] & 1)) return;
     grid = g;
     if (cudaMalloc(&dev, (size_t)g * 32 * sizeof(long long)) != cudaSuccess) { dev = nullptr; return; }
     cudaMemset(dev, 0, (size_t)g * 32 * sizeof(long long));
@@ -1749,13 +1787,13 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
   const int OH = ih / stride, OW = iw / stride;
   if (use_tc == 2) {
     op.use_tc = true;
-    if (!choose_patch_cfg(op, ih, iw, 0))
+    if (!choose_patch_cfg(op, ih, iw, 0, g_single_op_tune))
       return fail(HRNET_E_INVALID, "shape not eligible for the halo-patch path (3x3 s1, cin/cout % 16, weights must fit in smem, map must tile 8x16)");
     int rc = load_driver_fns();
     if (rc) return rc;
     rc = encode_patch_maps(op, in, w, n);
     if (rc) return rc;
-    choose_epi(op, out_f32 != 0, false, residual != nullptr);
+    choose_epi(op, out_f32 != 0, false, residual != nullptr, g_single_op_tune);
     rc = encode_epi_maps(op, out, residual, n, OH, OW);
     if (rc) return rc;
     CK(conv_patch_set_attributes(kMaxDynSmem));
@@ -1766,8 +1804,9 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.N = n; p.total_tiles = n * p.tiles_w * p.tiles_h; p.relu = relu; p.out_f32 = out_f32;
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
     if (p.total_tiles == 0) return HRNET_OK;
-    if (getenv("HRNET_B200_DBG_NOSTORE")) p.H = 0;   // experiments: every output row invalid -> epilogue without global traffic
-    if (const char* e = getenv("HRNET_B200_GRID_CAP")) sms = std::max(1, std::min(sms, atoi(e)));   // experiments
+    p.pdl = g_single_op_tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
+    if (g_single_op_tune[HRNET_TUNE_DEBUG] & 8) p.H = 0;   // experiments: every output row invalid -> epilogue without global traffic
+    if (g_single_op_tune[HRNET_TUNE_GRID_CAP] > 0) sms = std::max(1, std::min(sms, (int)g_single_op_tune[HRNET_TUNE_GRID_CAP]));   // experiments
     const int pgrid = conv_patch_grid(p, sms);
     DbgTimers dt; dt.begin(pgrid); p.dbg = dt.dev;
     CK(launch_conv_patch(op.tmPA, op.tmPB, op.tmOR, p, op.patch_smem, pgrid, st));
@@ -1775,11 +1814,11 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     return HRNET_OK;
   }
   if (use_tc) {
-    choose_tc_cfg(op, 0);
+    choose_tc_cfg(op, 0, g_single_op_tune);
     if (!op.use_tc) return fail(HRNET_E_INVALID, "shape not supported by the tcgen05 path (cin, cout must be multiples of 16)");
     int rc = load_driver_fns();
     if (rc) return rc;
-    choose_epi(op, out_f32 != 0, false, residual != nullptr);
+    choose_epi(op, out_f32 != 0, false, residual != nullptr, g_single_op_tune);
     rc = encode_epi_maps(op, out, residual, n, OH, OW);
     if (rc) return rc;
     rc = encode_im2col(&op.tmA, in, n, ih, iw, cin, op.tc.kc, ksize, stride, op.pad, op.pad, op.pad, op.pad);
@@ -1790,7 +1829,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (const char* e = getenv("HRNET_B200_GRID_CAP")) sms = std::max(2, std::min(sms, atoi(e)));   // experiments
+    if (g_single_op_tune[HRNET_TUNE_GRID_CAP] > 0) sms = std::max(2, std::min(sms, (int)g_single_op_tune[HRNET_TUNE_GRID_CAP]));   // experiments
     ConvTcParams p{};
     p.M_total = n * OH * OW; p.OH = OH; p.OW = OW; p.OHW = OH * OW;
     p.ksize = ksize; p.stride = stride; p.pad_h = op.pad; p.pad_w = op.pad; p.Cin = cin; p.Cout = cout;
@@ -1802,6 +1841,7 @@ static int conv_single(const void* in, const void* w, const float* scale, const 
     p.b_blk_bytes = (int)align_up((size_t)(p.n_tile / p.cs) * p.kc * 2, 1024);
     p.scale = scale; p.bias = bias; p.residual = (const __half*)residual; p.out = out;
     p.epi_tma = op.tc.epi; p.epi_bytes = op.tc.epi_bytes;
+    p.pdl = g_single_op_tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
     const int tiles = p.m_tiles * p.n_tiles;
     if (tiles == 0) return HRNET_OK;
     DbgTimers dt; dt.begin(conv_tc_grid(p, op.tc.smem_bytes, sms)); p.dbg = dt.dev;

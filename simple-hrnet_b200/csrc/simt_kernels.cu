@@ -298,10 +298,9 @@ cudaError_t launch_head(const __half* in, const float* w, const float* bias, flo
   if (total == 0) return cudaSuccess;
   if (J > kHeadMaxJ) return cudaErrorInvalidValue;
   const int smem = (J * Cin + J) * 4;
-  static int attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaFuncSetAttribute(head_conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr = smem;
+  if (smem > 48 * 1024) {   // (17 joints x 2048 channels is 139 KB; per device, so no cached state)
+    cudaError_t e = cudaFuncSetAttribute(head_conv1x1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
   }
   head_conv1x1_kernel<<<(unsigned)((total + 127) / 128), 128, smem, st>>>(in, w, bias, out_nchw, N, HW, Cin, J);
   return cudaGetLastError();
@@ -327,8 +326,9 @@ argmax_decode_kernel(const float* __restrict__ hm, int J, int Hh, int Wh, const 
   const float* p = hm + (size_t)pj * HW;
   float best = 0.f;
   int bi = 0x7fffffff;
-  // vectorised scan when the map is 16B-aligned (HW % 4 == 0 holds for every supported resolution)
-  if ((HW & 3) == 0) {
+  // vectorised scan when every map is 16-byte aligned (HW % 4 == 0 holds for every supported resolution; the base
+  // pointer of hrnet_argmax / hrnet_forward(heatmaps=...) is the caller's and may be a view at any 4-byte offset)
+  if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(hm) & 15u) == 0) {
     const float4* p4 = reinterpret_cast<const float4*>(p);
     for (int i = threadIdx.x; i < HW / 4; i += 256) {
       float4 v = __ldg(p4 + i);

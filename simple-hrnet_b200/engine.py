@@ -207,6 +207,24 @@ class B200Engine(Plan):
             raise ValueError(f"input on {images.device}, engine on {self.device}")
         return images.to(torch.float32).contiguous()
 
+    def _outputs(self, n, boxes, return_heatmaps, joints_out):
+        """Joints / idx / heat-map buffers and the device copy of the boxes, validated the same way for every entry point."""
+        if joints_out is not None:
+            if not (joints_out.is_cuda and joints_out.device == self.device and joints_out.is_contiguous()
+                    and joints_out.dtype == torch.float32 and joints_out.numel() == n * self.J * 3):
+                raise ValueError(f"joints_out must be a contiguous float32 cuda tensor with {n * self.J * 3} elements on {self.device}")
+            joints = joints_out
+        else:
+            joints = torch.empty(n, self.J, 3, dtype=torch.float32, device=self.device)
+        idx = torch.empty(n, self.J, dtype=torch.int32, device=self.device)
+        hm = torch.empty(n, self.J, self.H // 4, self.W // 4, dtype=torch.float32, device=self.device) if return_heatmaps else None
+        bx = None
+        if boxes is not None:
+            bx = torch.as_tensor(boxes, dtype=torch.float32).to(self.device).contiguous()
+            if tuple(bx.shape) != (n, 4):
+                raise ValueError(f"boxes must have shape ({n}, 4), got {tuple(bx.shape)}")
+        return joints, idx, hm, bx
+
     def forward_decode(self, images, boxes=None, return_heatmaps=False, joints_out=None):
         """images [n,3,H,W] fp32 cuda -> joints [n,J,3] fp32 (y,x,conf), idx [n,J] int32, heat-maps|None.
         `joints_out` lets the caller have the decode write straight into a slice of a larger
@@ -214,14 +232,7 @@ class B200Engine(Plan):
         x = self._check_input(images)
         n = x.shape[0]
         with torch.cuda.device(self.device):
-            joints = joints_out if joints_out is not None else torch.empty(n, self.J, 3, dtype=torch.float32, device=self.device)
-            assert joints.is_contiguous() and joints.dtype == torch.float32 and joints.numel() == n * self.J * 3
-            idx = torch.empty(n, self.J, dtype=torch.int32, device=self.device)
-            hm = torch.empty(n, self.J, self.H // 4, self.W // 4, dtype=torch.float32, device=self.device) if return_heatmaps else None
-            bx = None
-            if boxes is not None:
-                bx = torch.as_tensor(boxes, dtype=torch.float32).to(self.device).contiguous()
-                assert bx.shape == (n, 4)
+            joints, idx, hm, bx = self._outputs(n, boxes, return_heatmaps, joints_out)
             stream = torch.cuda.current_stream(self.device).cuda_stream
             check(self.lib.hrnet_forward(self._plan, x.data_ptr(), n, hm.data_ptr() if hm is not None else None,
                                          joints.data_ptr(), idx.data_ptr(), bx.data_ptr() if bx is not None else None,
@@ -244,12 +255,7 @@ class B200Engine(Plan):
         x = x.contiguous()
         n = x.shape[0]
         with torch.cuda.device(self.device):
-            joints = joints_out if joints_out is not None else torch.empty(n, self.J, 3, dtype=torch.float32, device=self.device)
-            idx = torch.empty(n, self.J, dtype=torch.int32, device=self.device)
-            hm = torch.empty(n, self.J, self.H // 4, self.W // 4, dtype=torch.float32, device=self.device) if return_heatmaps else None
-            bx = None
-            if boxes is not None:
-                bx = torch.as_tensor(boxes, dtype=torch.float32).to(self.device).contiguous()
+            joints, idx, hm, bx = self._outputs(n, boxes, return_heatmaps, joints_out)
             stream = torch.cuda.current_stream(self.device).cuda_stream
             check(self.lib.hrnet_forward_u8(self._plan, x.data_ptr(), n, hm.data_ptr() if hm is not None else None,
                                             joints.data_ptr(), idx.data_ptr(), bx.data_ptr() if bx is not None else None,
@@ -261,8 +267,10 @@ class B200Engine(Plan):
         if self._weights is None:
             raise HrnetError("load_state_dict must be called before running the engine")
         x = np.ascontiguousarray(images_u8_host, dtype=np.uint8)
-        assert x.ndim == 4 and x.shape[1:] == (self.H, self.W, 3)
+        if x.ndim != 4 or x.shape[1:] != (self.H, self.W, 3):
+            raise ValueError(f"expected uint8 [n,{self.H},{self.W},3], got {x.shape}")
         n = x.shape[0]
+        self._check_host(n, boxes_host)
         joints = np.empty((n, self.J, 3), dtype=np.float32)
         idx = np.empty((n, self.J), dtype=np.int32)
         hm = np.empty((n, self.J, self.H // 4, self.W // 4), dtype=np.float32) if want_heatmaps else None
@@ -273,6 +281,12 @@ class B200Engine(Plan):
                                                  joints.ctypes.data, idx.ctypes.data,
                                                  bx.ctypes.data if bx is not None else None, stream), self.lib)
         return joints, idx, hm
+
+    def _check_host(self, n, boxes_host):
+        if n > self.max_batch:
+            raise ValueError(f"batch {n} > max_batch {self.max_batch}")
+        if boxes_host is not None and np.asarray(boxes_host).shape != (n, 4):
+            raise ValueError(f"boxes must have shape ({n}, 4), got {np.asarray(boxes_host).shape}")
 
     def profile_ops(self, images, iters=5):
         """[(op name, op dict, usec)] with one CUDA-event pair per kernel (serial execution, no graph)."""
@@ -293,7 +307,10 @@ class B200Engine(Plan):
         if self._weights is None:
             raise HrnetError("load_state_dict must be called before running the engine")
         x = np.ascontiguousarray(images_host, dtype=np.float32)
+        if x.ndim != 4 or x.shape[1:] != (3, self.H, self.W):     # the C side copies n*3*H*W*4 bytes from this pointer
+            raise ValueError(f"expected float32 [n,3,{self.H},{self.W}], got {x.shape}")
         n = x.shape[0]
+        self._check_host(n, boxes_host)
         joints = np.empty((n, self.J, 3), dtype=np.float32)
         idx = np.empty((n, self.J), dtype=np.int32)
         hm = np.empty((n, self.J, self.H // 4, self.W // 4), dtype=np.float32) if want_heatmaps else None

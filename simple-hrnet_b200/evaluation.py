@@ -30,35 +30,46 @@ def _stream(t):
     return _vp(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-def _get_3rd_point(a, b):
-    d = a - b
-    return b + np.array([-d[1], d[0]], dtype=np.float32)
+def crop_to_image_affines(center, scale, pixel_std, heatmap_size):
+    """[n,2,3] float64 matrices that map heat-map pixels back to image pixels -- what the reference obtains per person
+    from `get_affine_transform(center, scale, pixel_std, 0, [Wh, Hh], inv=1)` (misc/utils.py:46-79; the evaluation
+    path never rotates).
 
-
-def get_affine_transform(center, scale, pixel_std, rot, output_size, shift=np.array([0, 0], dtype=np.float32), inv=0):
-    """misc/utils.py:46-79: crop <-> image affine from three point pairs (cv2.getAffineTransform, float64 2x3)."""
+    An axis-aligned box of `scale * pixel_std` pixels around `center` corresponds to the heat-map; the reference pins the
+    map with three point pairs (box centre, the point half a box width above it, and that offset turned by 90 degrees),
+    stores them as float32 and lets `cv2.getAffineTransform` solve for the matrix in double precision.  The same three
+    pairs are built here for all persons at once, with the same float32 / float64 roundings (the arithmetic keeps the
+    caller's dtype of `scale` exactly as NumPy does in the reference), so the matrices agree bit for bit
+    (tests/test_eval_cpu.py)."""
     import cv2
-    if not isinstance(scale, np.ndarray) and not isinstance(scale, list):
+    center = np.asarray(center)
+    scale = np.asarray(scale)
+    n = center.shape[0]
+    box = scale * 1.0 * pixel_std                         # [n,2] box size in image pixels (dtype of `scale`)
+    up_img = box[:, 0] * -0.5                             # half a box WIDTH, upwards
+    wm, hm = heatmap_size[0], heatmap_size[1]
+    img = np.zeros((n, 3, 2), dtype=np.float32)
+    img[:, 0] = center
+    img[:, 1, 0] = center[:, 0] + np.zeros(n)             # float64 sums, rounded once when stored (as in the reference)
+    img[:, 1, 1] = center[:, 1] + up_img.astype(np.float64)
+    d = img[:, 0] - img[:, 1]                             # float32
+    img[:, 2, 0] = img[:, 1, 0] - d[:, 1]
+    img[:, 2, 1] = img[:, 1, 1] + d[:, 0]
+    hmp = np.zeros((3, 2), dtype=np.float32)
+    hmp[0] = [wm * 0.5, hm * 0.5]
+    hmp[1] = np.array([wm * 0.5, hm * 0.5]) + np.array([0, wm * -0.5], np.float32)
+    dh = hmp[0] - hmp[1]
+    hmp[2] = hmp[1] + np.array([-dh[1], dh[0]], dtype=np.float32)
+    return np.stack([cv2.getAffineTransform(hmp, img[i]) for i in range(n)]) if n else np.zeros((0, 2, 3))
+
+
+def get_affine_transform(center, scale, pixel_std, rot, output_size, shift=None, inv=0):
+    """Reference signature (misc/utils.py:46) for the one case the evaluation decode uses: rot = 0, no shift, inv = 1."""
+    if rot != 0 or not inv or (shift is not None and np.any(np.asarray(shift) != 0)):
+        raise NotImplementedError("only the inverse, unrotated, unshifted crop affine of the evaluation decode is provided")
+    if not isinstance(scale, (np.ndarray, list)):
         scale = np.array([scale, scale])
-    scale_tmp = scale * 1.0 * pixel_std
-    src_w = scale_tmp[0]
-    dst_w, dst_h = output_size[0], output_size[1]
-    rot_rad = np.pi * rot / 180
-    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
-    p0, p1 = 0, src_w * -0.5
-    src_dir = [p0 * cs - p1 * sn, p0 * sn + p1 * cs]
-    dst_dir = np.array([0, dst_w * -0.5], np.float32)
-    src = np.zeros((3, 2), dtype=np.float32)
-    dst = np.zeros((3, 2), dtype=np.float32)
-    src[0, :] = center + scale_tmp * shift
-    src[1, :] = center + src_dir + scale_tmp * shift
-    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
-    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5]) + dst_dir
-    src[2:, :] = _get_3rd_point(src[0, :], src[1, :])
-    dst[2:, :] = _get_3rd_point(dst[0, :], dst[1, :])
-    if inv:
-        return cv2.getAffineTransform(np.float32(dst), np.float32(src))
-    return cv2.getAffineTransform(np.float32(src), np.float32(dst))
+    return crop_to_image_affines(np.asarray(center)[None], np.asarray(scale)[None], pixel_std, output_size)[0]
 
 
 def _decode(batch_heatmaps, post_processing, trans):
@@ -87,9 +98,7 @@ def get_max_preds(batch_heatmaps):
 def get_final_preds(post_processing, batch_heatmaps, center, scale, pixel_std):
     """Quarter-pixel refined joints transformed back to image coordinates; center / scale: [n,2] numpy arrays."""
     n, _, Hh, Wh = batch_heatmaps.shape
-    trans = np.stack([get_affine_transform(center[i], scale[i], pixel_std, 0, [Wh, Hh], inv=1) for i in range(n)]) \
-        if n else np.zeros((0, 2, 3))
-    return _decode(batch_heatmaps, post_processing, trans)
+    return _decode(batch_heatmaps, post_processing, crop_to_image_affines(center, scale, pixel_std, [Wh, Hh]))
 
 
 def _perm(matched_parts, J):

@@ -80,12 +80,15 @@ def test_conv_patch_equals_im2col_kernel_bitwise_f32():
 
 @pytest.mark.parametrize("shape", [(3, 24, 18, 192, 192, 3, 1), (5, 12, 9, 384, 384, 3, 1), (2, 24, 18, 192, 384, 3, 2),
                                    (1, 16, 12, 256, 512, 1, 2), (2, 48, 36, 96, 96, 3, 1)], ids=lambda s: "x".join(map(str, s)))
-def test_conv_tc_pair_mode_matches_cpu(shape, monkeypatch):
-    """CTA-pair mode (tcgen05 cta_group::2, opt-in via HRNET_B200_CS=2): M=256 MMAs over a 2-CTA cluster, half weight
-    tile per CTA, odd tile counts (ghost CTA), N split."""
-    monkeypatch.setenv("HRNET_B200_CS", "2")
+def test_conv_tc_pair_mode_matches_cpu(shape):
+    """CTA-pair mode (tcgen05 cta_group::2, opt-in via HRNET_TUNE_IGEMM_PAIR=2): M=256 MMAs over a 2-CTA cluster, half
+    weight tile per CTA, odd tile counts (ghost CTA), N split."""
     case = G.conv_case(*shape, relu=True, residual=(shape[6] == 1 and shape[3] == shape[4]), out_f32=False, seed=8)
-    out = G.run_conv(case, use_tc=1)
+    _lib.set_debug_tune({_lib.TUNE_IGEMM_PAIR: 2})
+    try:
+        out = G.run_conv(case, use_tc=1)
+    finally:
+        _lib.set_debug_tune(None)
     err = (out - case["ref"]).abs().max().item()
     assert err <= G.conv_tolerance(case), f"max abs err {err}"
 
@@ -93,15 +96,34 @@ def test_conv_tc_pair_mode_matches_cpu(shape, monkeypatch):
 @pytest.mark.parametrize("shape", [(2, 96, 72, 48, 48), (3, 48, 36, 96, 96), (1, 16, 8, 64, 64), (5, 48, 24, 48, 96),
                                    (1, 32, 16, 128, 128)], ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("epi", ["direct", "tma", "coal"])
-def test_conv_patch_pair_mode_matches_cpu(shape, epi, monkeypatch):
-    """Halo-patch kernel in CTA-pair mode (opt-in via HRNET_B200_PATCH_PAIR=<min Cout>): M=256 MMAs over two tiles, half of
+def test_conv_patch_pair_mode_matches_cpu(shape, epi):
+    """Halo-patch kernel in CTA-pair mode (opt-in via HRNET_TUNE_PATCH_PAIR_MIN_COUT): M=256 MMAs over two tiles, half of
     the resident weight rows per CTA, odd tile counts (ghost CTA: (1,16,8) has one tile, (5,48,24) has 45), with the
     direct, the TMA-store and the warp-staged coalesced epilogue."""
-    monkeypatch.setenv("HRNET_B200_PATCH_PAIR", "16")
-    monkeypatch.setenv("HRNET_B200_EPI", epi)
     n, h, w, cin, cout = shape
     case = G.conv_case(n, h, w, cin, cout, 3, 1, relu=True, residual=(cin == cout), out_f32=False, seed=9)
-    out = G.run_conv(case, use_tc=2)
+    _lib.set_debug_tune({_lib.TUNE_PATCH_PAIR_MIN_COUT: 16,
+                         _lib.TUNE_EPILOGUE: {"direct": _lib.EPI_DIRECT, "tma": _lib.EPI_TMA, "coal": _lib.EPI_COAL}[epi]})
+    try:
+        out = G.run_conv(case, use_tc=2)
+    finally:
+        _lib.set_debug_tune(None)
+    err = (out - case["ref"]).abs().max().item()
+    assert err <= G.conv_tolerance(case), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("epi", ["coal", "batch"])
+@pytest.mark.parametrize("shape,kind", [((3, 96, 72, 48, 48, 3, 1), 2), ((2, 48, 36, 64, 64, 3, 1), 2), ((3, 24, 18, 48, 64, 1, 1), 1),
+                                        ((2, 48, 36, 48, 48, 3, 2), 1)], ids=str)
+def test_opt_in_epilogues_match_cpu(shape, kind, epi):
+    """The opt-in epilogue variants (HRNET_TUNE_EPILOGUE = coal: warp-staged coalesced stores; batch: all TMEM loads of a
+    <= 64-channel tile before one wait) run on hardware here, so selecting them never executes unvalidated code."""
+    case = G.conv_case(*shape, relu=True, residual=(shape[6] == 1 and shape[3] == shape[4]), out_f32=False, seed=12)
+    _lib.set_debug_tune({_lib.TUNE_EPILOGUE: _lib.EPI_COAL if epi == "coal" else _lib.EPI_BATCH})
+    try:
+        out = G.run_conv(case, use_tc=kind)
+    finally:
+        _lib.set_debug_tune(None)
     err = (out - case["ref"]).abs().max().item()
     assert err <= G.conv_tolerance(case), f"max abs err {err}"
 

@@ -1,0 +1,55 @@
+"""Branch-chain diagnostics on the headline config (W48 384x288, 64 crops):
+  1. per-chain role timers (HRNET_TUNE_CHAIN_DEBUG) alone on the GPU and on the in-forward grid  -> stderr
+  2. per-class serial times from hrnet_profile_ops
+  3. forward time for several SM splits between the chains of a module (HRNET_TUNE_CHAIN_SHARE*) and without chains
+Usage: python tools/chain_probe.py [debug] [shares "a,b,c,d" ...]"""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import hrnet_oracle as O
+from simple_hrnet_b200 import B200Engine, _lib
+
+sd = O.make_state_dict(O.hrnet_param_spec(48, 17), seed=0, bn="default")
+x = torch.randn(64, 3, 384, 288, generator=torch.Generator().manual_seed(1)).cuda()
+
+
+def fwd_ms(eng, reps=10):
+    for _ in range(3):
+        eng.forward_decode(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eng.forward_decode(x)
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+args = sys.argv[1:]
+if "debug" in args:
+    eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), tune={_lib.TUNE_CHAIN_DEBUG: 1})
+    eng.load_state_dict(sd)
+    ops, desc = eng.profile_ops(x, iters=3)
+    cls = {}
+    for name, op, us in ops:
+        if op["kind"] == 1 and ".branches." in name:
+            key = (name.split(".")[0], op["cin"])
+            cls.setdefault(key, []).append(us)
+    for k, v in sorted(cls.items()):
+        print(f"{k[0]} C={k[1]:3d}: {len(v):3d} convs, {sum(v) / len(v):6.1f} us per conv (chain alone on the GPU)")
+    print(f"forward (default split): {fwd_ms(eng):.3f} ms")
+    eng.close()
+splits = [a for a in args if "," in a]
+for sp in splits:
+    t = {i: int(v) for i, v in enumerate(sp.split(","))}
+    eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), tune=t)
+    eng.load_state_dict(sd)
+    d = eng.describe()
+    grids = [(c["module"], c["branch"], c["grid"]) for c in d["chains"] if c["module"] in (1, 2, 6)]
+    print(f"split {sp}: {fwd_ms(eng):.3f} ms/forward   grids (module, branch, ctas): {grids}", flush=True)
+    eng.close()
+if "nochain" in args:
+    eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), flags=_lib.FLAG_NO_CHAIN)
+    eng.load_state_dict(sd)
+    print(f"no chains: {fwd_ms(eng):.3f} ms/forward")
