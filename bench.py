@@ -139,7 +139,9 @@ def run_cpu_child(key, threads, n, warm, steps, timeout=900):
 def cpu_arm(key, warm, steps, n):
     """Best thread count at the TIMED batch (one warm-up + one timed rep per candidate), then the timed run."""
     ncpu = os.cpu_count() or 1
-    cands = sorted({t for t in (16, 32, 64, ncpu // 2, ncpu) if 1 <= t <= ncpu})
+    # 16 / 32 / 64 threads (a socket's worth at most): every hardware thread of a big host is far slower (oneDNN
+    # oversubscribed: 123 s for a 4-person forward on 128 threads in round 1), so it is not even tried
+    cands = sorted({min(t, ncpu) for t in (16, 32, 64)})
     calib = {}
     for t in cands:
         r = run_cpu_child(key, t, n, 1, 1, timeout=300)
@@ -375,16 +377,28 @@ def main():
     xs, gen = make_inputs(rank)
     pred = ShardedPredictor(lambda imgs, out: eng.forward_decode(imgs, joints_out=out), J, dev)
 
-    def step(i):
-        return pred.predict_joints(B, xs[i % 3])
+    def run_steps(first, count):
+        """`count` steps; returns the joints [B,17,3] of the last one.  Multi-GPU: pipelined form -- step i's all-gather
+        runs on a side stream while step i+1's forward computes; every step's result is consumed one step later."""
+        if world == 1:
+            out = None
+            for i in range(first, first + count):
+                out = pred.predict_joints(B, xs[i % 3])
+            return out
+        prev = None
+        for i in range(first, first + count):
+            h = pred.submit(B, xs[i % 3])
+            if prev is not None:
+                pred.result(prev)
+            prev = h
+        return pred.result(prev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
+    run_steps(0, args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -393,8 +407,7 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        joints = step(i)
+    joints = run_steps(0, args.steps)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -562,7 +575,9 @@ def main():
                                       f"with fp32 accumulate, random-init weights (seed 0), torch.randn inputs ({cfg['baseline']})",
                           "global_batch": B, "per_gpu_batch": PB, "parallelism": f"dp{world}",
                           "l2": "3 rotating input buffers; a step streams far more activation bytes through HBM than the 126 MB L2 holds",
-                          "collective": "one NCCL all_gather_into_tensor of joints [B,17,3] f32 per step" if world > 1 else "none"},
+                          "collective": ("one NCCL all_gather_into_tensor of joints [B,17,3] f32 per step, issued on a side stream behind "
+                                         "that step's decode so that it overlaps the next step's forward (two rotating gather "
+                                         "buffers, results consumed one step later)") if world > 1 else "none"},
                "clocks": clocks,
                "e2e": {"value": round(e2e_value, 2), "unit": "persons/s", "h2d_bytes_per_step": h2d,
                        "d2h_bytes_per_step": d2h, "steps": e2e_steps, "call": e2e_call,

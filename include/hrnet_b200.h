@@ -49,6 +49,9 @@ extern "C" {
 #define HRNET_FLAG_NO_CHAIN 128u   /* debug / cross-check: launch the eight convs of a StageModule branch one by one
                                       instead of as one persistent branch-chain kernel (bit-identical results)     */
 
+#define HRNET_FLAG_NO_XUNIT 256u   /* debug / cross-check: launch the convs of a StageModule's fuse layers one by one instead
+                                      of as one persistent exchange-unit kernel (bit-identical results)                */
+
 /* Tuning / diagnostic knobs of a plan (HrnetDesc.tune[]); 0 = the library's default.  They select between kernel
  * variants that compute the same function (results agree to accumulation-order noise at most; the default set is what
  * the parity tests pin).  Nothing in the library reads the process environment. */
@@ -73,6 +76,8 @@ extern "C" {
                                       output checksums with HRNET_FLAG_NO_GRAPH (stderr); bit 2: finish times of grouped
                                       launches; bit 3: single-op halo-patch conv without global stores (timing only)  */
 #define HRNET_TUNE_GRID_CAP 17      /* single-op entry points: cap on the persistent grid (experiments)              */
+#define HRNET_TUNE_CHAIN_M2 18       /* im2col chains: 2 = two M-tiles per ticket sharing every weight k-block (30 % fewer TMA
+                                      bytes, no accumulator double buffering); default one tile per ticket             */
 #define HRNET_TUNE_COUNT 24
 
 typedef struct HrnetPlan HrnetPlan;
@@ -190,6 +195,16 @@ int hrnet_final_preds(const float* heatmaps, int n, int nof_joints, int hh, int 
  * joint j (identity outside the left/right pairs).  averaged may alias output. */
 int hrnet_flip_average(const float* output, const float* output_flipped, const int32_t* joint_perm_host, int n,
                        int nof_joints, int hh, int wh, float* averaged, void* stream);
+/* Device-side image resize of the reference's preprocessing (`cv2.resize(image, (W, H), interpolation=cv2.INTER_CUBIC)`,
+ * SimpleHRNet.py:216-220 and :356-360): OpenCV's own 8-bit cubic kernel (4 taps per axis, Keys weights A = -0.75 in
+ * 11-bit fixed point, int32 accumulation, rounding shift by 22, saturation).  Bit-identical to cv2.resize with OpenCV's
+ * vendor-optimised paths disabled (cv2.setUseOptimized(False)); the IPP path most cv2 wheels take by default differs
+ * from OpenCV's own kernel by one grey level on ~3.5 % of the pixels.
+ *   src [n,sh,sw,3] uint8, dst [n,dh,dw,3] uint8 (device); per axis the first tap index sx-1 (xofs [dw], yofs [dh]) and the
+ *   four 11-bit weights (xcoef [dw][4], ycoef [dh][4], int16), device arrays built by the host
+ *   (simple_hrnet_b200.preprocess.cubic_tables restates OpenCV's float32 table computation). */
+int hrnet_resize_cubic_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* xofs,
+                          const int16_t* xcoef, const int32_t* yofs, const int16_t* ycoef, void* stream);
 /* median device time in microseconds of `iters` launches of one conv (CUDA events on `stream`),
  * same arguments as hrnet_conv_bn_act; used by bench.py for the per-kernel roofline. */
 int hrnet_conv_bench(const void* in_nhwc_f16, const void* w_f16, const float* scale, const float* bias,

@@ -21,7 +21,7 @@ class SimpleHRNet:
                  interpolation=None, multiperson=True, return_heatmaps=False, return_bounding_boxes=False,
                  max_batch_size=32, yolo_version='v3', yolo_model_def=None, yolo_class_path=None,
                  yolo_weights_path=None, device=torch.device("cuda"), enable_tensorrt=False, engine_flags=0,
-                 device_preprocess=True, detector=None):
+                 device_preprocess=True, detector=None, device_resize=False):
         self.c = c
         self.nof_joints = nof_joints
         self.checkpoint_path = checkpoint_path
@@ -68,6 +68,11 @@ class SimpleHRNet:
         # device-side transform (uint8 in) for HRNet at a fixed resolution; set device_preprocess=False to feed the
         # host-normalised fp32 tensor exactly like the reference does
         self._u8_path = bool(device_preprocess) and arch == "hrnet" and self.resolution is not None and not self.multiperson
+        # device_resize=True: the images go to the device at their ORIGINAL size and the cubic resize of
+        # SimpleHRNet.py:216-220 runs there too (OpenCV's own 8-bit cubic kernel, see preprocess.py: bit-identical to cv2
+        # without its vendor path, one grey level away from the default cv2 call on a few per cent of the pixels -- hence opt-in)
+        self._device_resize = bool(device_resize) and self._u8_path
+        self._resizer = None
         self._mp_transform = None
         self._mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1, 1)
         self._std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1, 1)
@@ -101,6 +106,17 @@ class SimpleHRNet:
             image = cv2.resize(image, (self.resolution[1], self.resolution[0]), interpolation=interp)
         return image
 
+    def _to_network_size(self, images_u8):
+        """uint8 [n,h,w,3] at any size -> network resolution: on the device (device_resize) or with cv2 like the reference."""
+        if self.resolution is None or tuple(images_u8.shape[1:3]) == tuple(self.resolution):
+            return images_u8
+        if self._device_resize and (self.interpolation is None or self.interpolation == 2):   # cv2.INTER_CUBIC == 2
+            if self._resizer is None:
+                from .preprocess import CubicResizer
+                self._resizer = CubicResizer(self.device)
+            return self._resizer(np.ascontiguousarray(images_u8), self.resolution[0], self.resolution[1])
+        return np.stack([self._resize_only(im) for im in images_u8])
+
     def _run_u8(self, images_u8, boxes):
         """HRNet fast path: the uint8 BGR crops go to the device as they are (4x fewer bytes than the fp32 tensor) and
         cvtColor + ToTensor + Normalize happen inside the stem kernel, bit-identically to the host transform."""
@@ -108,7 +124,7 @@ class SimpleHRNet:
         J, Hh, Wh = self.nof_joints, self.resolution[0] // 4, self.resolution[1] // 4
         pts = np.empty((n, J, 3), dtype=np.float32)
         heatmaps = np.zeros((n, J, Hh, Wh), dtype=np.float32)
-        dev = torch.from_numpy(np.ascontiguousarray(images_u8)).to(self.device)
+        dev = images_u8 if torch.is_tensor(images_u8) else torch.from_numpy(np.ascontiguousarray(images_u8)).to(self.device)
         for i in range(0, n, self.max_batch_size):
             sl = slice(i, min(n, i + self.max_batch_size))
             joints, _idx, hm = self.model.forward_decode_u8(dev[sl], boxes=boxes[sl], return_heatmaps=self.return_heatmaps)
@@ -236,7 +252,7 @@ class SimpleHRNet:
         old_res = image.shape
         boxes = np.asarray([[0, 0, old_res[1], old_res[0]]], dtype=np.float32)   # [x1, y1, x2, y2]
         if self._u8_path:
-            heatmaps, pts = self._run_u8(self._resize_only(image)[None], boxes)
+            heatmaps, pts = self._run_u8(self._to_network_size(image[None]), boxes)
         else:
             heatmaps, pts = self._run(self._prep(image).unsqueeze(dim=0), boxes)
         return self._pack(heatmaps, boxes, pts)
@@ -249,7 +265,7 @@ class SimpleHRNet:
         old_res = images[0].shape
         boxes = np.repeat(np.asarray([[0, 0, old_res[1], old_res[0]]], dtype=np.float32), len(images), axis=0)
         if self._u8_path:
-            heatmaps, pts = self._run_u8(np.stack([self._resize_only(im) for im in images]), boxes)
+            heatmaps, pts = self._run_u8(self._to_network_size(images), boxes)
         else:
             x = torch.empty(images.shape[0], 3, self.resolution[0], self.resolution[1])
             for i, image in enumerate(images):

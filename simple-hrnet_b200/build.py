@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhrnet_b200.so")
-SOURCES = ["plan.cu", "conv_igemm_tc.cu", "conv3x3_patch_tc.cu", "conv_group.cu", "conv_chain.cu", "stem_tc.cu", "simt_kernels.cu"]
-HEADERS = ["hrnet_internal.h", "ptx.cuh", "epilogue.cuh", "conv3x3_patch_body.cuh", "conv_igemm_body.cuh", os.path.join("..", "..", "include", "hrnet_b200.h")]
+SOURCES = ["plan.cu", "conv_igemm_tc.cu", "conv3x3_patch_tc.cu", "conv_group.cu", "conv_chain.cu", "conv_xunit.cu", "stem_tc.cu", "simt_kernels.cu"]
+HEADERS = ["hrnet_internal.h", "ptx.cuh", "epilogue.cuh", "conv3x3_patch_body.cuh", "conv_igemm_body.cuh", "chain_common.cuh", os.path.join("..", "..", "include", "hrnet_b200.h")]
 
 
 def _nvcc():

@@ -28,226 +28,9 @@
 #include <algorithm>
 
 #include "conv3x3_patch_body.cuh"
-#include "conv_igemm_body.cuh"
+#include "chain_common.cuh"
 
 namespace hrnet {
-
-constexpr int kChainRing = 8;
-constexpr uint32_t kChainDone = 0xffffffffu;
-
-struct ChainRing {
-  uint64_t full[kChainRing];
-  uint64_t empty[kChainRing];
-  uint32_t info[kChainRing];     // conv | tile (kChainDone after the last one)
-  uint32_t coord[kChainRing];    // the tile's coordinates, decoded once by the scheduler (no divisions in the other roles)
-};
-
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_add_relaxed_gpu(unsigned* p, unsigned v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// 256-bit global accesses (sm_100: LDG / STG.E.256).  The thread-per-row epilogue is bound by the load/store unit's sector
-// rate -- every lane touches its own 32-byte sector, ~1 sector per clock per SM (profiles/r02_s2_chain_sched_v2_roles.log:
-// four epilogue warpgroups took exactly as long per tile as two) -- so moving a whole sector per access instead of half
-// of one halves the epilogue's load/store time.  The load is GPU-coherent (.cg: L2, never a stale L1 line).
-struct __align__(32) U256 { uint32_t w[8]; };
-__device__ __forceinline__ U256 ldg256_cg(const void* p) {
-  U256 v;
-  asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7])
-               : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void stg256(void* p, const U256& v) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7]) : "memory");
-}
-// 16 accumulator columns starting at tile column c: the arithmetic of epi_cols16 (epilogue.cuh) with the residual arriving
-// as and the result leaving as ONE 32-byte access.  fp16 outputs only.
-__device__ __forceinline__ void chain_cols16(const uint32_t (&v)[16], const U256& r, const EpiRow& e, int c) {
-  float y[16];
-  const float4* sc = reinterpret_cast<const float4*>(e.s_scale + e.ch0 + c);
-  const float4* bi = reinterpret_cast<const float4*>(e.s_bias + e.ch0 + c);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 s4 = sc[i], b4 = bi[i];
-    y[4 * i + 0] = fmaf(__uint_as_float(v[4 * i + 0]), s4.x, b4.x);
-    y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), s4.y, b4.y);
-    y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), s4.z, b4.z);
-    y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), s4.w, b4.w);
-  }
-  if (e.residual != nullptr) {
-    const __half2* h = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 f = __half22float2(h[i]);
-      y[2 * i] += f.x; y[2 * i + 1] += f.y;
-    }
-  }
-  if (e.relu) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
-  }
-  U256 o;
-  __half2* oh2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) oh2[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
-  stg256(reinterpret_cast<__half*>(e.out) + e.row_off + c, o);
-}
-
-// generic-proxy accesses before / async-proxy (TMA) accesses after, all state spaces
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_volatile_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
-// A dependency that never arrives would hang the GPU: after ~2 s of polling the CTA traps (launch failure on the host).
-static __device__ __noinline__ void chain_wait_counter_slow(const unsigned* c, unsigned want) {
-  const long long t0 = clock64();
-  while (ld_acquire_gpu(c) < want) {
-    __nanosleep(32);
-    if (clock64() - t0 > 4000000000ll) {
-      printf("hrnet_b200: chain dependency timeout (block %d counter %p want %u have %u)\n", (int)blockIdx.x, (const void*)c,
-             want, ld_acquire_gpu(c));
-      __trap();
-    }
-  }
-}
-// counters[k-1][u] has reached `want`: every tile of units u-1 .. u+1 of the previous conv is stored and visible
-__device__ __forceinline__ void chain_wait_counter(const unsigned* c, unsigned want) {
-  if (ld_acquire_gpu(c) < want) chain_wait_counter_slow(c, want);
-}
-// Ring consumer: every consuming thread walks every entry (tile descriptor or kChainDone), in order.
-struct RingReader {
-  uint32_t full0, empty0, info0, coord0;
-  int i;
-  __device__ __forceinline__ void init(ChainRing* r) {
-    full0 = ptx::smem_u32(&r->full[0]); empty0 = ptx::smem_u32(&r->empty[0]); info0 = ptx::smem_u32(&r->info[0]);
-    coord0 = ptx::smem_u32(&r->coord[0]);
-    i = 0;
-  }
-  __device__ __forceinline__ uint32_t next(uint32_t& coord) {
-    const uint32_t slot = (uint32_t)(i % kChainRing);
-    const uint32_t ph = (uint32_t)((i / kChainRing) & 1);
-    ptx::mbar_wait(full0 + 8u * slot, ph);
-    const uint32_t v = lds_volatile_u32(info0 + 4u * slot);
-    coord = lds_volatile_u32(coord0 + 4u * slot);
-    ptx::mbar_arrive(empty0 + 8u * slot);
-    ++i;
-    return v;
-  }
-  __device__ __forceinline__ uint32_t next() { uint32_t c; return next(c); }
-};
-
-// Ring producer side of the scheduler thread.
-struct RingWriter {
-  uint32_t full0, empty0, info0, coord0;
-  int i;
-  __device__ __forceinline__ void init(ChainRing* r) {
-    full0 = ptx::smem_u32(&r->full[0]); empty0 = ptx::smem_u32(&r->empty[0]); info0 = ptx::smem_u32(&r->info[0]);
-    coord0 = ptx::smem_u32(&r->coord[0]);
-    i = 0;
-  }
-  __device__ __forceinline__ void acquire_slot() {
-    const uint32_t slot = (uint32_t)(i % kChainRing);
-    const uint32_t ph = (uint32_t)((i / kChainRing) & 1);
-    ptx::mbar_wait(empty0 + 8u * slot, ph ^ 1u);
-  }
-  __device__ __forceinline__ void publish(uint32_t v, uint32_t coord = 0u) {
-    const uint32_t slot = (uint32_t)(i % kChainRing);
-    sts_volatile_u32(info0 + 4u * slot, v);
-    sts_volatile_u32(coord0 + 4u * slot, coord);
-    ptx::mbar_arrive(full0 + 8u * slot);     // release at CTA scope: the descriptor is visible to the waiters
-    ++i;
-  }
-};
-
-// Block-wide, after the final __syncthreads: the last CTA of the launch clears the unit counters it and the others used
-// (`nconv` x `units`, row pitch `stride`) and re-arms the ticket.  `flag` is a shared-memory word.
-__device__ __forceinline__ void chain_exit(unsigned* ctrl, unsigned* counters, int nconv, int units, int stride, uint32_t* flag) {
-  if (threadIdx.x == 0) {
-    __threadfence();
-    *flag = atomicAdd(&ctrl[1], 1u) == gridDim.x - 1 ? 1u : 0u;
-  }
-  __syncthreads();
-  if (*flag == 0u) return;
-  __threadfence();
-  for (int k = 0; k < nconv; ++k)
-    for (int u = threadIdx.x; u < units; u += blockDim.x) counters[(size_t)k * stride + u] = 0u;
-  if (threadIdx.x == 0) { ctrl[0] = 0u; ctrl[1] = 0u; }
-}
-
-// Epilogue of one row of the im2col chain: the residual of the next 64 channels is in flight while the current 64 are
-// converted (4 x 256-bit loads; written earlier in this launch by another SM, hence the coherent loads).
-__device__ __forceinline__ void chain_load_residual(U256 (&r)[4], const EpiRow& e, int c_begin) {
-  if (e.residual == nullptr || !e.valid) return;
-  const __half* rp = e.residual + e.row_off + c_begin;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (c_begin + 16 * i < e.ncols) r[i] = ldg256_cg(rp + 16 * i);
-}
-__device__ __forceinline__ void chain_store_row(U256 (&r)[4], const EpiRow& e, uint32_t t_row) {
-  for (int c64 = 0; c64 < e.ncols; c64 += 64) {
-    U256 cur[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) cur[i] = r[i];
-    if (c64 + 64 < e.ncols) chain_load_residual(r, e, c64 + 64);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int c = c64 + 32 * h;
-      if (c < e.ncols) {                       // warp-uniform
-        uint32_t v0[16], v1[16];
-        const bool two = c + 16 < e.ncols;     // warp-uniform
-        ptx::tmem_ld16(t_row + (uint32_t)c, v0);
-        if (two) ptx::tmem_ld16(t_row + (uint32_t)(c + 16), v1);
-        ptx::tmem_ld_wait();
-        if (e.valid) {
-          chain_cols16(v0, cur[2 * h], e, c);
-          if (two) chain_cols16(v1, cur[2 * h + 1], e, c + 16);
-        }
-      }
-    }
-  }
-}
-
-// Register-lean variant for the 20-warp halo-patch chain (96 registers per thread): 16 columns per step, the residual of
-// the next 16 columns in flight while the current ones are converted.  r0 = residual of columns [0, 16), loaded before
-// the wait on the accumulator barrier.  Same arithmetic as epi_cols16, so results do not change.
-__device__ __forceinline__ void chain_store_row_lean(const EpiRow& e, uint32_t t_row, U256 r0) {
-  const bool has_res = e.residual != nullptr && e.valid;
-  const __half* rp = e.residual + e.row_off;
-  for (int c = 0; c < e.ncols; c += 16) {
-    U256 n0 = r0;
-    if (has_res && c + 16 < e.ncols) n0 = ldg256_cg(rp + c + 16);
-    uint32_t v[16];
-    ptx::tmem_ld16(t_row + (uint32_t)c, v);
-    ptx::tmem_ld_wait();
-    if (e.valid) chain_cols16(v, r0, e, c);
-    r0 = n0;
-  }
-}
-
-// After a warpgroup has stored its tile of unit u: make the stores visible GPU-wide and count the tile in the
-// neighbourhood counters of units u-1 (if has_lo), u and u+1 (if has_hi).
-__device__ __forceinline__ void chain_publish_tile(unsigned* counter_u, bool has_lo, bool has_hi, int bar_id, bool leader) {
-  ptx::bar_sync(bar_id, 128);                  // all four warps of the warpgroup have issued their stores
-  if (leader) {
-    fence_proxy_async_all();                   // generic-proxy stores before later async-proxy (TMA) reads
-    __threadfence();
-    red_add_relaxed_gpu(counter_u, 1u);
-    if (has_lo) red_add_relaxed_gpu(counter_u - 1, 1u);
-    if (has_hi) red_add_relaxed_gpu(counter_u + 1, 1u);
-  }
-}
 
 // =====================================================================================================================
 // im2col chain (branches whose map does not tile into 8x16 patches / whose weights do not fit: C = 192, 384 at W48)
@@ -274,7 +57,14 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
   const int lane = threadIdx.x & 31;
   ptx::pdl_launch_dependents();
 
-  const int a_stage_bytes = p.bps * p.a_blk_bytes;
+  // Two M-tiles per ticket (p.m2 == 2): both tiles consume every weight k-block of a stage, so a stage carries A0 | A1 | B
+  // and the TMA bytes per output drop by 30 % (weights fetched once per 256 rows).  What paced the single-tile pipeline was
+  // the per-SM TMA delivery rate: 40 KB per 128 x 192 x 64 step in ~800 clk against 384 clk of math
+  // (profiles/r02_s3_*.log: 17.9 k clk per 27-k-block tile).  The two accumulators fill the 2 x n_tile TMEM columns the
+  // single-tile mode uses for double buffering, so the MMAs of a ticket wait for the epilogue of the previous one; the
+  // operand loads keep streaming meanwhile.
+  const int m2 = p.m2;
+  const int a_stage_bytes = m2 * p.bps * p.a_blk_bytes;
   const int b_stage_bytes = p.bps * p.b_blk_bytes;
   const int stage_bytes = a_stage_bytes + b_stage_bytes;
   ChainIgemmBars* bars = reinterpret_cast<ChainIgemmBars*>(smem_aligned + (size_t)p.stages * stage_bytes);
@@ -288,7 +78,7 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->tmem_full[i]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128u);
+      ptx::mbar_init(ptx::smem_u32(&bars->tmem_empty[i]), 128u * (uint32_t)m2);
     }
     for (int i = 0; i < kChainRing; ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->ring.full[i]), 1);
@@ -319,35 +109,38 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
     if (ptx::elect_one()) {
       RingWriter rw; rw.init(&bars->ring);
       long long dbg_dep = 0; int dbg_tiles = 0;
-      // one ticket = one M-tile (all of its N-tiles: same dependencies, same A operand)
-      const unsigned total_chunks = (unsigned)(p.nconv * p.m_tiles);
+      // one ticket = one unit = m2 neighbouring M-tiles (all of their N-tiles: same dependencies, same A operands)
+      const unsigned total_chunks = (unsigned)(p.nconv * p.units);
       unsigned next = atomicAdd(&p.ctrl[0], 1u);
       for (;;) {
         const unsigned t = next;
         if (t >= total_chunks) { rw.acquire_slot(); rw.publish(kChainDone); break; }
-        next = atomicAdd(&p.ctrl[0], 1u);            // in flight while this chunk's dependency is polled
-        const int k = (int)t / p.m_tiles;
-        const int mt = (int)t - k * p.m_tiles;
+        next = atomicAdd(&p.ctrl[0], 1u);            // in flight while this ticket's dependency is polled
+        const int k = (int)t / p.units;
+        const int u = (int)t - k * p.units;
         if (k > 0) {
-          // rows [m0 - (OW + 1), m0 + 127 + OW + 1] of conv k-1: OW + 1 < 128, so M-tiles mt-1 .. mt+1 (all N-tiles)
+          // rows [m0 - (OW + 1), m_last + OW + 1] of conv k-1: OW + 1 < 128, so the neighbouring units (all N-tiles)
           const long long tq = p.dbg ? clock64() : 0;
-          const int nb = 1 + (mt > 0 ? 1 : 0) + (mt < p.m_tiles - 1 ? 1 : 0);
-          chain_wait_counter(p.counters + (size_t)(k - 1) * p.unit_stride + mt, (unsigned)(nb * p.n_tiles));
+          const int nb = 1 + (u > 0 ? 1 : 0) + (u < p.units - 1 ? 1 : 0);
+          chain_wait_counter(p.counters + (size_t)(k - 1) * p.unit_stride + u, (unsigned)(nb * p.n_tiles * m2));
           fence_proxy_async_all();   // the acquired generic-proxy stores before the TMA (async-proxy) reads issued downstream
           if (p.dbg) dbg_dep += clock64() - tq;
         }
-        const int m0 = mt * kTileM;
-        const int img = m0 / p.OHW;
-        const int rem = m0 - img * p.OHW;
-        const int oh0 = rem / p.OW;
-        const uint32_t coord = ((uint32_t)img << 16) | ((uint32_t)oh0 << 8) | (uint32_t)(rem - oh0 * p.OW);
+        uint32_t coord[2] = {0u, 0u};
+        for (int i = 0; i < m2; ++i) {
+          const int m0 = (u * m2 + i) * kTileM;    // (a tile past the last image loads zeros and stores nothing)
+          const int img = m0 / p.OHW;
+          const int rem = m0 - img * p.OHW;
+          const int oh0 = rem / p.OW;
+          coord[i] = ((uint32_t)img << 16) | ((uint32_t)oh0 << 8) | (uint32_t)(rem - oh0 * p.OW);
+        }
         for (int nt = 0; nt < p.n_tiles; ++nt) {
           rw.acquire_slot();
-          rw.publish(((uint32_t)k << 28) | ((uint32_t)nt << 24) | (uint32_t)mt, coord);
+          rw.publish(((uint32_t)k << 28) | ((uint32_t)nt << 24) | (uint32_t)u, coord[0], coord[1]);
           ++dbg_tiles;
         }
       }
-      if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = dbg_dep; p.dbg[blockIdx.x * 16 + 1] = dbg_tiles; }
+      if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = dbg_dep; p.dbg[blockIdx.x * 16 + 1] = dbg_tiles * m2; }
     }
     __syncwarp();
   } else if (warp < 2) {
@@ -355,35 +148,43 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
     if (ptx::elect_one()) {
       RingReader rr; rr.init(&bars->ring);
       int L = 0;
-      int stage = warp;
-      uint32_t phase = 0;
+      int stage = warp % p.stages;
+      uint32_t phase = (uint32_t)(warp / p.stages) & 1u;
+      long long dbg_slot = 0;
       for (;;) {
-        uint32_t coord;
-        const uint32_t info = rr.next(coord);
+        uint32_t coord, coord2;
+        const uint32_t info = rr.next(coord, coord2);
         if (info == kChainDone) break;
         const int k = (int)(info >> 28), nt = (int)((info >> 24) & 15u);
-        const int img = (int)(coord >> 16);
-        const int bw = (int)(coord & 255u) - 1, bh = (int)((coord >> 8) & 255u) - 1;
+        const int img0 = (int)(coord >> 16), bw0 = (int)(coord & 255u) - 1, bh0 = (int)((coord >> 8) & 255u) - 1;
+        const int img1 = (int)(coord2 >> 16), bw1 = (int)(coord2 & 255u) - 1, bh1 = (int)((coord2 >> 8) & 255u) - 1;
         const int n0 = nt * p.n_tile;
         for (int ks = 0; ks < nstages_k; ++ks, ++L) {
           if ((L & 1) != warp) continue;
           const int kb0 = ks * p.bps;
           const int nblk = min(p.bps, p.nkb - kb0);
+          const long long tq = p.dbg ? clock64() : 0;
           ptx::mbar_wait(ptx::smem_u32(&bars->empty[stage]), phase ^ 1u);
+          if (p.dbg) dbg_slot += clock64() - tq;
           const uint32_t full = ptx::smem_u32(&bars->full[stage]);
           const uint32_t a_dst = smem_base + (uint32_t)(stage * stage_bytes);
           const uint32_t b_dst = a_dst + (uint32_t)a_stage_bytes;
-          ptx::mbar_expect_tx(full, (uint32_t)(nblk * (kTileM * kKC * 2 + p.n_tile * kKC * 2)));
+          ptx::mbar_expect_tx(full, (uint32_t)(nblk * (m2 * kTileM * kKC * 2 + p.n_tile * kKC * 2)));
           for (int j = 0; j < nblk; ++j) {
             const uint32_t e = kb_tab[kb0 + j];
-            ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &maps.a[k], full, (int)((e >> 15) & 0xfffu), bw, bh,
-                                    img, (uint16_t)((e >> 27) & 3u), (uint16_t)(e >> 29));
+            ptx::tma_load_im2col_4d(a_dst + (uint32_t)(j * p.a_blk_bytes), &maps.a[k], full, (int)((e >> 15) & 0xfffu), bw0, bh0,
+                                    img0, (uint16_t)((e >> 27) & 3u), (uint16_t)(e >> 29));
+            if (m2 == 2)
+              ptx::tma_load_im2col_4d(a_dst + (uint32_t)((p.bps + j) * p.a_blk_bytes), &maps.a[k], full, (int)((e >> 15) & 0xfffu),
+                                      bw1, bh1, img1, (uint16_t)((e >> 27) & 3u), (uint16_t)(e >> 29));
             ptx::tma_load_2d(b_dst + (uint32_t)(j * p.b_blk_bytes), &maps.b[k], full, (int)(e & 0x7fffu), n0);
           }
+          // this producer's next load is two stages further round the ring
           stage += 2;
-          if (stage >= p.stages) { stage -= p.stages; phase ^= 1u; }
+          while (stage >= p.stages) { stage -= p.stages; phase ^= 1u; }
         }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 16 + 11 + warp] = dbg_slot;
     }
     __syncwarp();
   } else if (warp == 2) {
@@ -395,19 +196,25 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
       int stage = 0;
       uint32_t phase = 0;
       bool ready = false;
+      long long dbg_wfull = 0, dbg_wtm = 0;
       for (int it = 0;; ++it) {
         const uint32_t info = rr.next();
         if (info == kChainDone) break;
-        const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        // single tile: two accumulator buffers alternate; two tiles: both halves belong to this ticket
+        const int acc = m2 == 2 ? 0 : (it & 1);
+        const uint32_t acc_phase = (uint32_t)((m2 == 2 ? it : (it >> 1)) & 1);
+        long long tq = p.dbg ? clock64() : 0;
         ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        if (p.dbg) dbg_wtm += clock64() - tq;
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
         int cblk = 0;
         for (int ks = 0; ks < nstages_k; ++ks) {
           const int kb0 = ks * p.bps;
           const int nblk = min(p.bps, p.nkb - kb0);
+          if (p.dbg) tq = clock64();
           if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
+          if (p.dbg) dbg_wfull += clock64() - tq;
           ptx::tc_fence_after_sync();
           const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
           const uint32_t b_src = a_src + (uint32_t)a_stage_bytes;
@@ -418,14 +225,17 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
           for (int j = 0; j < nblk; ++j) {
             const int nk = (cblk == p.cpt - 1 ? ctail : kKC) / 16;
             cblk = cblk + 1 == p.cpt ? 0 : cblk + 1;
-            const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)(j * p.a_blk_bytes), 128u, 1024u);
             const uint64_t bdesc = ptx::umma_desc_kmajor(b_src + (uint32_t)(j * p.b_blk_bytes), 128u, 1024u);
             const uint32_t first = (uint32_t)((kb0 + j) != 0);
-            switch (nk) {
-              case 4: issue_k16<4, false>(d_tmem, adesc, bdesc, idesc, first); break;
-              case 3: issue_k16<3, false>(d_tmem, adesc, bdesc, idesc, first); break;
-              case 2: issue_k16<2, false>(d_tmem, adesc, bdesc, idesc, first); break;
-              default: issue_k16<1, false>(d_tmem, adesc, bdesc, idesc, first); break;
+            for (int i = 0; i < m2; ++i) {
+              const uint64_t adesc = ptx::umma_desc_kmajor(a_src + (uint32_t)((i * p.bps + j) * p.a_blk_bytes), 128u, 1024u);
+              const uint32_t d = d_tmem + (uint32_t)(i * p.n_tile);
+              switch (nk) {
+                case 4: issue_k16<4, false>(d, adesc, bdesc, idesc, first); break;
+                case 3: issue_k16<3, false>(d, adesc, bdesc, idesc, first); break;
+                case 2: issue_k16<2, false>(d, adesc, bdesc, idesc, first); break;
+                default: issue_k16<1, false>(d, adesc, bdesc, idesc, first); break;
+              }
             }
           }
           ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
@@ -433,24 +243,32 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
         }
         ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
       }
+      if (p.dbg) { p.dbg[blockIdx.x * 16 + 5] = dbg_wfull; p.dbg[blockIdx.x * 16 + 6] = dbg_wtm; }
     }
     __syncwarp();
   } else {
-    // ===================================================================== epilogue (two warpgroups, alternating tiles)
+    // ===================================================================== epilogue (two warpgroups)
+    // single tile per ticket: warpgroup g drains buffer g of alternate tickets; two tiles: warpgroup g drains tile g of
+    // every ticket
     const int g = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool leader = (q == 0) && (lane == 0);
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * p.n_tile);
     RingReader rr; rr.init(&bars->ring);
+    PendingPublish pend; pend.clear();
+    long long dbg_wait = 0, dbg_work = 0;
     for (int it = 0;; ++it) {
+      if (!rr.ready()) pend.flush(1 + g, leader);      // about to sleep on the ring: publish first (see PendingPublish)
       const uint32_t info = rr.next();
       if (info == kChainDone) break;
-      if ((it & 1) != g) continue;
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int k = (int)(info >> 28), nt = (int)((info >> 24) & 15u), mt = (int)(info & 0xffffffu);
+      if (m2 == 1 && (it & 1) != g) continue;
+      pend.flush(1 + g, leader);                        // the previous tile of this warpgroup
+      const int accb = m2 == 2 ? 0 : g;
+      const uint32_t acc_phase = (uint32_t)((m2 == 2 ? it : (it >> 1)) & 1);
+      const int k = (int)(info >> 28), nt = (int)((info >> 24) & 15u), u = (int)(info & 0xffffffu);
       const ChainConv& cv = p.conv[k];
-      const int m = mt * kTileM + row;
+      const int m = (u * m2 + (m2 == 2 ? g : 0)) * kTileM + row;
       const int n0 = nt * p.n_tile;
       EpiRow e;
       e.s_scale = cv.scale; e.s_bias = cv.bias; e.residual = cv.residual; e.out = cv.out;
@@ -458,13 +276,18 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
       e.ch0 = n0; e.ncols = p.n_tile; e.relu = cv.relu; e.out_f32 = 0; e.valid = m < p.M_total;
       U256 rres[4];
       chain_load_residual(rres, e, 0);
-      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
+      long long tq = p.dbg ? clock64() : 0;
+      ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[accb]), acc_phase);
+      if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq; tq = t; }
       ptx::tc_fence_after_sync();
       chain_store_row(rres, e, t_row);
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
-      chain_publish_tile(p.counters + (size_t)k * p.unit_stride + mt, mt > 0, mt < p.m_tiles - 1, 1 + g, leader);
+      ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[accb]));
+      pend.set(p.counters + (size_t)k * p.unit_stride + u, u > 0, u < p.units - 1);
+      if (p.dbg) dbg_work += clock64() - tq;
     }
+    pend.flush(1 + g, leader);
+    if (p.dbg && threadIdx.x == 128) { p.dbg[blockIdx.x * 16 + 3] = dbg_wait; p.dbg[blockIdx.x * 16 + 4] = dbg_work; }
   }
 
   ptx::tc_fence_before_sync();
@@ -474,7 +297,7 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const Chain
     ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
   if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 16 + 2] = clock64() - t_begin;
-  chain_exit(p.ctrl, p.counters, p.nconv, p.m_tiles, p.unit_stride, &bars->pad);
+  chain_exit(p.ctrl, p.counters, p.nconv, p.units, p.unit_stride, &bars->pad);
 }
 
 // =====================================================================================================================
@@ -740,12 +563,15 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
     const bool leader = (q == 0) && (lane == 0);
     ptx::pdl_wait();
     RingReader rr; rr.init(&bars->ring);
+    PendingPublish pend; pend.clear();
     long long dbg_work = 0, dbg_wait = 0;
     for (int it = 0;; ++it) {
+      if (!rr.ready()) pend.flush(1 + g, leader);      // about to sleep on the ring: publish first (see PendingPublish)
       uint32_t coord;
       const uint32_t info = rr.next(coord);
       if (info == kChainDone) break;
       if ((it & (kCPEpiGroups - 1)) != g) continue;
+      pend.flush(1 + g, leader);                        // the previous tile of this warpgroup
       const int k = (int)(info >> 28);
       const ChainConv& cv = cp.conv[k];
       const int acc = it & (p.nacc - 1);
@@ -756,20 +582,25 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const Chain
       e.s_scale = s_sb + (2 * k) * p.Cout; e.s_bias = e.s_scale + p.Cout; e.residual = cv.residual; e.out = cv.out;
       e.row_off = (((size_t)img * p.H + oh) * p.W + ow) * p.Cout;
       e.ch0 = 0; e.ncols = p.Cout; e.relu = cv.relu; e.out_f32 = 0; e.valid = oh < p.H && ow < p.W;
-      U256 r0;
+      U256 rres[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r0.w[i] = 0u;
-      if (e.residual != nullptr && e.valid) r0 = ldg256_cg(e.residual + e.row_off);   // in flight while the MMAs of this tile finish
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rres[j].w[i] = 0u;
+        // in flight while the MMAs of this tile finish
+        if (e.residual != nullptr && e.valid && 16 * j < e.ncols) rres[j] = ldg256_cg(e.residual + e.row_off + 16 * j);
+      }
       long long tq = cp.dbg ? clock64() : 0;
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
       if (cp.dbg) { const long long t = clock64(); dbg_wait += t - tq; tq = t; }
       ptx::tc_fence_after_sync();
-      chain_store_row_lean(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout), r0);
+      chain_store_row_lean(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout), rres);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));
-      chain_publish_tile(cp.counters + (size_t)k * cp.unit_stride + img * p.tiles_h + th, th > 0, th < p.tiles_h - 1, 1 + g, leader);
+      pend.set(cp.counters + (size_t)k * cp.unit_stride + img * p.tiles_h + th, th > 0, th < p.tiles_h - 1);
       if (cp.dbg) dbg_work += clock64() - tq;
     }
+    pend.flush(1 + g, leader);
     if (cp.dbg && threadIdx.x == 128) { cp.dbg[blockIdx.x * 16 + 3] = dbg_wait; cp.dbg[blockIdx.x * 16 + 4] = dbg_work; }
   }
 

@@ -140,7 +140,9 @@ struct ChainIgemmParams {
   int nconv;
   int M_total, OH, OW, OHW, C;
   int cpt, nkb, bps, n_tile, n_tiles, m_tiles, stages, tmem_cols, a_blk_bytes, b_blk_bytes;
-  int unit_stride;           // counters per conv (M-tiles at max batch)
+  int m2;                    // M-tiles per ticket: 1, or 2 (both tiles share every weight k-block of a pipeline stage)
+  int units;                 // tickets per conv = ceil(m_tiles / m2)
+  int unit_stride;           // counters per conv (units at max batch)
   int pdl;                   // host side: launch with programmatic stream serialization
   unsigned* ctrl;
   unsigned* counters;
@@ -163,6 +165,35 @@ struct ChainPatchMaps { CUtensorMap a[kChainMaxConv]; CUtensorMap b[kChainMaxCon
 cudaError_t launch_chain_igemm(const ChainIgemmMaps& maps, const ChainIgemmParams& p, int smem_bytes, int grid, cudaStream_t st);
 cudaError_t launch_chain_patch(const ChainPatchMaps& maps, const ChainPatchParams& p, int smem_bytes, int grid, cudaStream_t st);
 cudaError_t conv_chain_set_attributes(int max_smem);
+
+// ---- exchange unit (conv_xunit.cu): every conv of one StageModule's fuse layers (reference models_/hrnet.py:23-51) in ONE
+// persistent kernel: tickets = M-tiles of the member convs in dependency order, a conv of a down-chain starts when its
+// producer conv is complete.
+constexpr int kXMaxOps = 16;
+struct XOp {
+  int M_total, OH, OW, OHW;      // output geometry (flattened NHWC rows)
+  int ksize, stride, pad;
+  int Cin, Cout, cpt, nkb;       // channel blocks per tap, k-blocks per tile
+  int n_tile, n_tiles, m_tiles;
+  int relu;
+  int dep, dep_need;             // producer op within the unit (-1: a module input) and its tile count
+  int kb0;                       // first entry of this op in the k-block table
+  int ticket0;                   // first ticket (one ticket = one M-tile, all of its N-tiles)
+  const float* scale;
+  const float* bias;
+  __half* out;
+};
+struct XUnitParams {
+  int nops, total_tickets, total_kb;
+  int stages, tmem_cols, a_blk_bytes, b_blk_bytes, pdl;
+  unsigned* ctrl;                // [0] ticket counter, [1] exited-CTA counter
+  unsigned* counters;            // [nops] finished tiles per op
+  long long* dbg;
+  XOp op[kXMaxOps];
+};
+struct XUnitMaps { CUtensorMap a[kXMaxOps], b[kXMaxOps]; };
+cudaError_t launch_xunit(const XUnitMaps& maps, const XUnitParams& p, int smem_bytes, int grid, cudaStream_t st);
+cudaError_t conv_xunit_set_attributes(int max_smem);
 
 struct FuseParams {
   int N, H, W, C, nsrc, relu;
@@ -192,6 +223,7 @@ struct Op {
   float sm_frac = 1.f;         // share of the SMs this op's persistent grid may occupy (branch-level SM partitioning)
   int group = -1;              // ops with the same group id run concurrently on different streams and split the SMs
   int chain = -1, chain_pos = 0;   // branch chain (conv_chain.cu) this conv belongs to / its position in it
+  int xunit = -1, xpos = 0, xlevel = 0;   // exchange unit (conv_xunit.cu) / position in its ticket order / step in its down-chain
   // tcgen05 path
   bool use_tc = false;
   ConvTcCfg tc;
@@ -239,6 +271,8 @@ cudaError_t launch_final_preds(const float* hm, int N, int J, int Hh, int Wh, in
                                float* maxvals, cudaStream_t st);
 cudaError_t launch_flip_average(const float* a, const float* b, float* out, const int* perm, int N, int J, int Hh, int Wh,
                                 cudaStream_t st);
+cudaError_t launch_resize_cubic_u8(const uint8_t* src, uint8_t* dst, int n, int sh, int sw, int dh, int dw, const int32_t* xofs,
+                                   const int16_t* xcoef, const int32_t* yofs, const int16_t* ycoef, cudaStream_t st);
 cudaError_t launch_maxpool(const __half* in, __half* out, int N, int IH, int IW, int C, cudaStream_t st);
 cudaError_t launch_stem7(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
                          int N, int H, int W, cudaStream_t st);

@@ -50,9 +50,20 @@ struct ChainInfo {
   int grid = 0;                    // ... resolved to CTAs by hrnet_plan_bind
   double cost = 0;                 // estimated SM-cycles of the whole chain (grid split)
   int flag_stride = 0;             // unit counters per conv (at max batch)
+  int m2 = 1, stages = 0;          // im2col chain: M-tiles per ticket, pipeline stages
   size_t ctrl_off = 0, flags_off = 0;   // bytes into the activation workspace
   ChainIgemmMaps imaps;            // filled by hrnet_plan_bind
   ChainPatchMaps pmaps;
+};
+
+// One exchange unit (conv_xunit.cu): every conv of a StageModule's fuse layers issued as one persistent kernel.
+struct XUnitInfo {
+  std::vector<int> ops;            // member convs in ticket (dependency) order
+  int module = -1;
+  bool enabled = false;
+  int smem = 0, stages = 0, tmem_cols = 0, b_blk = 0;
+  size_t ctrl_off = 0, counters_off = 0;
+  XUnitMaps maps;                  // filled by hrnet_plan_bind
 };
 
 struct HrnetPlan {
@@ -62,6 +73,7 @@ struct HrnetPlan {
   std::vector<int> param_kind, param_a, param_b;  // deconv sub-pixel phases
   std::vector<Op> ops;
   std::vector<ChainInfo> chains;
+  std::vector<XUnitInfo> xunits;
   size_t sync_off = 0, sync_bytes = 0;   // chain control words + tile flags (zeroed by hrnet_plan_bind)
   size_t act_bytes = 0, weight_bytes = 0;
   int t_input = -1, t_heatmaps = -1;
@@ -224,6 +236,7 @@ void choose_tc_cfg(Op& op, uint32_t flags, const int32_t* tune, int max_nt = 256
 // Halo-patch path: 3x3 stride-1 convs whose 9-tap weights fit in shared memory next to >= 2 patch slots and
 // whose map tiles into 8x16 output tiles with little waste.
 constexpr int kMaxDynSmem = 226 * 1024;
+constexpr int kChainMaxSmem = 227 * 1024;   // the most a block may opt in to on sm_100 (228 KB per SM, 1 KB reserved per block)
 bool choose_patch_cfg(Op& op, int H, int W, uint32_t flags, const int32_t* tune) {
   op.use_patch = false;
   if (flags & (HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_NO_PATCH)) return false;
@@ -447,6 +460,13 @@ int build_hrnet(HrnetPlan& P) {
       for (int i = 0; i < S; ++i) ys[i] = cur[i];
     }
     std::vector<int> outs(O);
+    const int xid = (int)P.xunits.size();
+    { XUnitInfo xu; xu.module = module_idx; P.xunits.push_back(xu); }
+    auto mark_x = [&](int level) {
+      Op& o = P.ops.back();
+      o.xunit = xid; o.xlevel = level;
+      P.xunits[xid].ops.push_back((int)P.ops.size() - 1);
+    };
     for (int i = 0; i < O; ++i) {
       const TensorInfo ti = P.tensors[ys[i]];
       Op f; f.kind = OP_FUSE; f.name = prefix + ".fuse." + std::to_string(i); f.relu = 1; f.stream = i; f.nsrc = S;
@@ -458,16 +478,20 @@ int build_hrnet(HrnetPlan& P) {
         } else if (j > i) {
           // 1x1 conv + BN at the low resolution; the nearest upsample is folded into the fuse read (hrnet.py:30-35)
           f.src[j] = b.conv(p, p + ".0", p + ".1", ys[j], ti.C, 1, 1, false, -1, -1, arena, i, dt_term);
+          mark_x(0);
           f.shift[j] = j - i;
         } else {
           int t = ys[j];
           const int cj = P.tensors[ys[j]].C;
-          for (int k = 0; k < i - j - 1; ++k)
+          for (int k = 0; k < i - j - 1; ++k) {
             t = b.conv(p + "." + std::to_string(k), p + "." + std::to_string(k) + ".0", p + "." + std::to_string(k) + ".1",
                        t, cj, 3, 2, true, -1, -1, arena, i);
+            mark_x(k);
+          }
           const int k = i - j - 1;
           f.src[j] = b.conv(p + "." + std::to_string(k), p + "." + std::to_string(k) + ".0",
                             p + "." + std::to_string(k) + ".1", t, ti.C, 3, 2, false, -1, -1, arena, i, dt_term);
+          mark_x(k);
           f.shift[j] = 0;
         }
       }
@@ -630,10 +654,21 @@ void plan_chains(HrnetPlan& P) {
       ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * o0.work;
     } else {
       for (int i : ch.ops) P.ops[i].tc.mma_warps = 1;
-      ch.smem = o0.tc.smem_bytes;
       const int n_tiles = o0.cout / o0.tc.n_tile;
       const int m_tiles = (P.desc.max_batch * ti.H * ti.W + 127) / 128;
-      ch.flag_stride = m_tiles;                                      // one counter per M-tile (n_tiles arrivals)
+      // two M-tiles per ticket share every weight k-block (conv_chain.cu); their accumulators need 2 x n_tile TMEM columns
+      // (opt-in, HRNET_TUNE_CHAIN_M2 = 2: measured equal inside the forward -- 7.228 vs 7.229 ms -- and slower alone on
+      // the GPU, where half as many tickets per conv leave CTAs idle: profiles/r02_s5_chain_deferred_publish_m1_vs_m2.log)
+      ch.m2 = (P.desc.tune[HRNET_TUNE_CHAIN_M2] == 2 && 2 * o0.tc.n_tile <= 512) ? 2 : 1;
+      {
+        const int a_blk = (int)align_up((size_t)128 * o0.tc.kc * 2, 1024);
+        const int b_blk = (int)align_up((size_t)o0.tc.n_tile * o0.tc.kc * 2, 1024);
+        const int stage = o0.tc.bps * (ch.m2 * a_blk + b_blk);
+        const int fixed = 1024 + 2048;                               // alignment slack + barriers, ring, k-block table
+        ch.stages = std::max(2, std::min(o0.tc.stages > 4 ? o0.tc.stages : 4, (kChainMaxSmem - fixed) / stage));
+        ch.smem = fixed + ch.stages * stage;
+      }
+      ch.flag_stride = (m_tiles + ch.m2 - 1) / ch.m2;                // one counter per ticket (m2 M-tiles x n_tiles arrivals)
       // measured inside the per-conv kernels: ~200 clk per K16 step of a 128 x 192 tile (profiles/r01_exp_gridcap_pair_sweep.log)
       ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * (200.0 * o0.tc.n_tile / 192.0);
     }
@@ -667,6 +702,60 @@ void plan_chains(HrnetPlan& P) {
       const double share = tuned ? P.desc.tune[HRNET_TUNE_CHAIN_SHARE0 + std::min(ch.branch, 3)] / tsum : ch.cost / tot;
       ch.share = std::max(1, (int)std::lround(share * 1000.0));
     }
+  }
+}
+
+// Exchange units: which modules' fuse-layer convs run as one kernel, ticket order, shared-memory needs, control words.
+void plan_xunits(HrnetPlan& P) {
+  const uint32_t off_flags = HRNET_FLAG_NO_XUNIT | HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_GROUP | HRNET_FLAG_PARTITION | HRNET_FLAG_FUSE_F32;
+  const bool want = !(P.desc.flags & off_flags);
+  size_t cur = (P.act_bytes + 255) / 256 * 256;
+  const size_t begin = cur;
+  for (size_t x = 0; x < P.xunits.size(); ++x) {
+    XUnitInfo& xu = P.xunits[x];
+    xu.enabled = false;
+    bool ok = want && xu.ops.size() >= 2 && (int)xu.ops.size() <= kXMaxOps;
+    int max_nt = 0, total_kb = 0;
+    for (int i : xu.ops) {
+      const Op& o = P.ops[i];
+      ok = ok && o.use_tc && !o.use_patch && o.tc.cs == 1 && P.tensors[o.out].dtype == DT_F16 && o.res < 0 && o.pad < 100 &&
+           o.tc.n_tile <= 256 && o.cout / o.tc.n_tile <= 15;
+      max_nt = std::max(max_nt, o.tc.n_tile);
+      total_kb += o.k * o.k * ((o.cin + 63) / 64);
+    }
+    if (!ok || total_kb > 384) continue;
+    xu.enabled = true;
+    // ticket order = dependency order: all first steps (1x1 up convs, first 3x3 s2 of every down chain), then the second
+    // steps, then the third; within a level the plan's order
+    std::stable_sort(xu.ops.begin(), xu.ops.end(), [&](int a, int b) { return P.ops[a].xlevel < P.ops[b].xlevel; });
+    xu.b_blk = (int)align_up((size_t)max_nt * 64 * 2, 1024);
+    const int stage = 16384 + xu.b_blk;
+    xu.stages = std::min(4, (kChainMaxSmem - 4096) / stage);
+    xu.smem = 1024 + xu.stages * stage + 3072;      // alignment slack, pipeline, barriers + ring + k-block table
+    int cols = 32;
+    while (cols < 2 * max_nt) cols *= 2;
+    xu.tmem_cols = cols;
+    xu.ctrl_off = cur; cur += 256;
+    xu.counters_off = cur; cur += 256;
+    // one kernel on the caller's stream: the member convs lose their per-output streams; the first member (in plan order)
+    // stands for the launch and waits for everything any member waits for
+    int first = *std::min_element(xu.ops.begin(), xu.ops.end());
+    std::vector<int> deps;
+    for (int i : xu.ops) {
+      P.ops[i].stream = 0;
+      for (int dpi : P.ops[i].deps)
+        if (P.ops[dpi].xunit != (int)x && std::find(deps.begin(), deps.end(), dpi) == deps.end()) deps.push_back(dpi);
+    }
+    P.ops[first].deps = deps;
+    int pos = 1;
+    for (int i : xu.ops) P.ops[i].xpos = i == first ? 0 : pos++;
+  }
+  for (size_t x = 0; x < P.xunits.size(); ++x)
+    if (!P.xunits[x].enabled) for (int i : P.xunits[x].ops) { P.ops[i].xunit = -1; P.ops[i].xpos = 0; }
+  if (cur > begin) {
+    if (P.sync_bytes == 0) P.sync_off = begin;
+    P.sync_bytes = cur - P.sync_off;
+    P.act_bytes = cur;
   }
 }
 
@@ -742,6 +831,7 @@ void finalize_schedule(HrnetPlan& P) {
     }
   }
   plan_chains(P);
+  plan_xunits(P);
   // every stream's last op must be joined back into stream 0 before the head runs
   int head = -1;
   for (size_t i = 0; i < P.ops.size(); ++i) if (P.ops[i].kind == OP_HEAD) head = (int)i;
@@ -756,6 +846,7 @@ void finalize_schedule(HrnetPlan& P) {
   P.launch_count = 0;
   for (size_t i = 0; i < P.ops.size(); ++i) {
     if (P.ops[i].chain >= 0) { if (P.ops[i].chain_pos == 0) ++P.launch_count; continue; }   // one kernel per chain
+    if (P.ops[i].xunit >= 0) { if (P.ops[i].xpos == 0) ++P.launch_count; continue; }        // one kernel per exchange unit
     if (P.ops[i].grp < 0 || i == 0 || P.ops[i - 1].grp != P.ops[i].grp) ++P.launch_count;
   }
 }
@@ -1005,7 +1096,8 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     o << "{\"kind\":" << op.kind << ",\"name\":\"" << op.name << "\",\"in\":" << op.in << ",\"out\":" << op.out
       << ",\"res\":" << op.res << ",\"param\":" << op.param << ",\"cin\":" << op.cin << ",\"cout\":" << op.cout
       << ",\"k\":" << op.k << ",\"stride\":" << op.stride << ",\"pad\":" << op.pad << ",\"relu\":" << op.relu
-      << ",\"stream\":" << op.stream << ",\"chain\":" << op.chain << ",\"chain_pos\":" << op.chain_pos << ",\"grp\":" << op.grp << ",\"sm_frac\":" << op.sm_frac << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
+      << ",\"stream\":" << op.stream << ",\"chain\":" << op.chain << ",\"chain_pos\":" << op.chain_pos
+      << ",\"xunit\":" << op.xunit << ",\"xpos\":" << op.xpos << ",\"grp\":" << op.grp << ",\"sm_frac\":" << op.sm_frac << ",\"use_tc\":" << (op.use_tc ? 1 : 0) << ",\"use_patch\":" << (op.use_patch ? 1 : 0) << ",\"nsrc\":" << op.nsrc << ",\"src\":["
       << op.src[0] << "," << op.src[1] << "," << op.src[2] << "," << op.src[3] << "],\"shift\":[" << op.shift[0] << ","
       << op.shift[1] << "," << op.shift[2] << "," << op.shift[3] << "],\"deps\":[";
     for (size_t k = 0; k < op.deps.size(); ++k) o << (k ? "," : "") << op.deps[k];
@@ -1022,9 +1114,19 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     if (!first_chain) o << ",";
     first_chain = false;
     o << "{\"module\":" << ch.module << ",\"branch\":" << ch.branch << ",\"patch\":" << (ch.patch ? 1 : 0) << ",\"smem\":" << ch.smem
-      << ",\"share_permille\":" << ch.share << ",\"grid\":" << ch.grid << ",\"flag_stride\":" << ch.flag_stride << ",\"ctrl_off\":" << ch.ctrl_off
+      << ",\"share_permille\":" << ch.share << ",\"grid\":" << ch.grid << ",\"m2\":" << ch.m2 << ",\"stages\":" << ch.stages << ",\"flag_stride\":" << ch.flag_stride << ",\"ctrl_off\":" << ch.ctrl_off
       << ",\"flags_off\":" << ch.flags_off << ",\"ops\":[";
     for (size_t k = 0; k < ch.ops.size(); ++k) o << (k ? "," : "") << ch.ops[k];
+    o << "]}";
+  }
+  o << "],\"xunits\":[";
+  bool first_x = true;
+  for (const auto& xu : P->xunits) {
+    if (!xu.enabled) continue;
+    if (!first_x) o << ",";
+    first_x = false;
+    o << "{\"module\":" << xu.module << ",\"smem\":" << xu.smem << ",\"stages\":" << xu.stages << ",\"ops\":[";
+    for (size_t k = 0; k < xu.ops.size(); ++k) o << (k ? "," : "") << xu.ops[k];
     o << "]}";
   }
   o << "],\"sync_off\":" << P->sync_off << ",\"sync_bytes\":" << P->sync_bytes << "}";
@@ -1116,10 +1218,20 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
       P->chains[big].grid = std::max(1, P->chains[big].grid + left);    // rounding remainder to the largest chain
       for (int c : kv.second) P->chains[c].grid = std::min(P->chains[c].grid, cap);
     }
+    for (auto& xu : P->xunits) {
+      if (!xu.enabled) continue;
+      for (size_t k = 0; k < (size_t)kXMaxOps; ++k) {
+        const Op& op = P->ops[xu.ops[std::min(k, xu.ops.size() - 1)]];     // unused slots: any valid descriptor
+        xu.maps.a[k] = op.tmA;
+        xu.maps.b[k] = op.tmB;
+      }
+    }
     if (P->sync_bytes) {
-      cudaError_t e = cudaMemset(P->abase + P->sync_off, 0, P->sync_bytes);
+      cudaError_t e = conv_xunit_set_attributes(kChainMaxSmem);
+      if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute(xunit): ") + cudaGetErrorString(e));
+      e = cudaMemset(P->abase + P->sync_off, 0, P->sync_bytes);
       if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaMemset(chain flags): ") + cudaGetErrorString(e));
-      e = conv_chain_set_attributes(kMaxDynSmem);
+      e = conv_chain_set_attributes(kChainMaxSmem);
       if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute(chain): ") + cudaGetErrorString(e));
     }
   }
@@ -1315,21 +1427,57 @@ int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st, long 
     p.nconv = (int)ch.ops.size();
     p.M_total = t.M_total; p.OH = t.OH; p.OW = t.OW; p.OHW = t.OHW; p.C = o0.cin;
     p.cpt = t.cpt; p.nkb = t.nkb; p.bps = t.bps; p.n_tile = t.n_tile; p.n_tiles = t.n_tiles; p.m_tiles = t.m_tiles;
-    p.stages = t.stages; p.tmem_cols = t.tmem_cols; p.a_blk_bytes = t.a_blk_bytes; p.b_blk_bytes = t.b_blk_bytes;
+    p.stages = ch.stages; p.tmem_cols = t.tmem_cols; p.a_blk_bytes = t.a_blk_bytes; p.b_blk_bytes = t.b_blk_bytes;
     p.pdl = t.pdl;
+    p.m2 = ch.m2; p.units = (p.m_tiles + ch.m2 - 1) / ch.m2;
     p.unit_stride = ch.flag_stride;
     p.ctrl = (unsigned*)(P->abase + ch.ctrl_off);
     p.counters = (unsigned*)(P->abase + ch.flags_off);
     p.dbg = dbg;
     fill_convs(p.conv);
     if (p.m_tiles * p.n_tiles == 0) return 0;
-    grid = std::max(1, std::min(grid, p.m_tiles * p.n_tiles));
+    grid = std::max(1, std::min(grid, p.units));
     CK(launch_chain_igemm(ch.imaps, p, ch.smem, grid, st));
   }
   return 0;
 }
 
 // in_u8: `in_ext` holds NHWC BGR uint8 images (hrnet_forward_u8) instead of the NCHW fp32 network input
+// One launch for the whole exchange unit `x` at batch n.
+int launch_xunit_op(HrnetPlan* P, int x, int n, cudaStream_t st, long long* dbg = nullptr) {
+  const XUnitInfo& xu = P->xunits[x];
+  XUnitParams p{};
+  p.nops = (int)xu.ops.size();
+  p.stages = xu.stages; p.tmem_cols = xu.tmem_cols; p.a_blk_bytes = 16384; p.b_blk_bytes = xu.b_blk;
+  p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
+  p.ctrl = (unsigned*)(P->abase + xu.ctrl_off);
+  p.counters = (unsigned*)(P->abase + xu.counters_off);
+  p.dbg = dbg;
+  int ticket = 0, kb = 0;
+  for (int k = 0; k < p.nops; ++k) {
+    const Op& op = P->ops[xu.ops[k]];
+    const ConvTcParams t = fill_tc_params(P, op, n);
+    XOp& o = p.op[k];
+    o.M_total = t.M_total; o.OH = t.OH; o.OW = t.OW; o.OHW = t.OHW;
+    o.ksize = t.ksize; o.stride = t.stride; o.pad = t.pad_h;
+    o.Cin = t.Cin; o.Cout = t.Cout; o.cpt = t.cpt; o.nkb = t.nkb;
+    o.n_tile = t.n_tile; o.n_tiles = t.n_tiles; o.m_tiles = t.m_tiles;
+    o.relu = t.relu;
+    o.dep = -1; o.dep_need = 0;
+    for (int j = 0; j < p.nops; ++j)
+      if (P->ops[xu.ops[j]].out == op.in) { o.dep = j; }
+    o.kb0 = kb; kb += o.nkb;
+    o.ticket0 = ticket; ticket += o.m_tiles;
+    o.scale = t.scale; o.bias = t.bias; o.out = (__half*)t.out;
+  }
+  for (int k = 0; k < p.nops; ++k)
+    if (p.op[k].dep >= 0) p.op[k].dep_need = p.op[p.op[k].dep].m_tiles * p.op[p.op[k].dep].n_tiles;
+  p.total_tickets = ticket; p.total_kb = kb;
+  if (ticket == 0) return 0;
+  CK(launch_xunit(xu.maps, p, xu.smem, std::min(P->num_sms, ticket), st));
+  return 0;
+}
+
 int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_ext, float* joints, int32_t* idx,
               const float* boxes, cudaStream_t st, bool in_u8 = false) {
   auto tptr = [&](int t) -> uint8_t* { return P->abase + P->tensors[t].offset; };
@@ -1454,6 +1602,18 @@ int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, flo
       int rc = launch_chain_op(P, op.chain, n, (P->desc.flags & HRNET_FLAG_SERIAL) ? P->num_sms : 0, st);
       if (rc) return rc;
       for (int m : ch.ops)
+        if (P->ops[m].needs_event) CK(cudaEventRecord(P->events[m], st));
+      continue;
+    }
+    if (op.xunit >= 0) {
+      // the whole exchange unit is issued where its first conv stands; the other members are part of that launch
+      if (op.xpos != 0) continue;
+      const XUnitInfo& xu = P->xunits[op.xunit];
+      for (int dpi : op.deps)               // (the first member carries every member's external dependencies)
+        if (P->ops[dpi].stream != op.stream) CK(cudaStreamWaitEvent(st, P->events[dpi], 0));
+      int rc = launch_xunit_op(P, op.xunit, n, st);
+      if (rc) return rc;
+      for (int m : xu.ops)
         if (P->ops[m].needs_event) CK(cudaEventRecord(P->events[m], st));
       continue;
     }
@@ -1612,6 +1772,9 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
   std::vector<cudaEvent_t> ev(nops + 1);
   for (auto& e : ev) CK(cudaEventCreate(&e));
   std::vector<std::vector<float>> t(nops, std::vector<float>(iters));
+  std::vector<cudaEvent_t> xunit_ev(2 * P->xunits.size(), nullptr);
+  for (size_t x = 0; x < P->xunits.size(); ++x)
+    if (P->xunits[x].enabled) { CK(cudaEventCreate(&xunit_ev[2 * x])); CK(cudaEventCreate(&xunit_ev[2 * x + 1])); }
   std::vector<cudaEvent_t> chain_ev(2 * P->chains.size(), nullptr);
   for (size_t c = 0; c < P->chains.size(); ++c)
     if (P->chains[c].enabled) { CK(cudaEventCreate(&chain_ev[2 * c])); CK(cudaEventCreate(&chain_ev[2 * c + 1])); }
@@ -1622,13 +1785,40 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
     for (int i = 0; i < nops; ++i) {
       const Op& op = P->ops[i];
       if (op.chain >= 0) {
-        // a branch chain is one kernel: timed alone on the whole GPU where its first conv stands, its time is split
-        // evenly between the member convs (equal FLOPs) below
-        if (op.chain_pos == 0) {
-          CK(cudaEventRecord(chain_ev[2 * op.chain], s0));
-          int rc = launch_chain_op(P, op.chain, n, P->num_sms, s0);
+        // Branch chains are timed the way they run inside a forward: the chains of one StageModule are launched
+        // together on their own streams with their in-forward grids (they share the SMs) where the module's first conv
+        // stands; the time from the first launch to the last completion is split evenly between the module's branch convs
+        // (equal FLOPs) below.  chain_ev[2c], [2c+1] of the module's FIRST chain bracket the module.
+        const int mod = P->chains[op.chain].module;
+        int first_c = -1;
+        std::vector<int> mod_chains;
+        for (size_t c = 0; c < P->chains.size(); ++c)
+          if (P->chains[c].enabled && P->chains[c].module == mod) { if (first_c < 0) first_c = (int)c; mod_chains.push_back((int)c); }
+        if (op.chain == first_c && op.chain_pos == 0) {
+          CK(cudaEventRecord(chain_ev[2 * first_c], s0));
+          for (int c : mod_chains) {
+            const int br = P->ops[P->chains[c].ops[0]].stream;
+            cudaStream_t sc = br == 0 ? s0 : P->side[br - 1];
+            if (sc != s0) CK(cudaStreamWaitEvent(sc, chain_ev[2 * first_c], 0));
+            int rc = launch_chain_op(P, c, n, 0, sc);
+            if (rc) return rc;
+            if (sc != s0) {
+              CK(cudaEventRecord(chain_ev[2 * c + 1], sc));
+              CK(cudaStreamWaitEvent(s0, chain_ev[2 * c + 1], 0));
+            }
+          }
+          CK(cudaEventRecord(chain_ev[2 * first_c + 1], s0));
+        }
+        CK(cudaEventRecord(ev[i + 1], s0));
+        continue;
+      }
+      if (op.xunit >= 0) {
+        // an exchange unit is one kernel: timed where its first conv stands, split by FLOPs between the members below
+        if (op.xpos == 0) {
+          CK(cudaEventRecord(xunit_ev[2 * op.xunit], s0));
+          int rc = launch_xunit_op(P, op.xunit, n, s0);
           if (rc) return rc;
-          CK(cudaEventRecord(chain_ev[2 * op.chain + 1], s0));
+          CK(cudaEventRecord(xunit_ev[2 * op.xunit + 1], s0));
         }
         CK(cudaEventRecord(ev[i + 1], s0));
         continue;
@@ -1651,12 +1841,31 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
     CK(cudaStreamSynchronize(s0));
     if (it >= 0) {
       for (int i = 0; i < nops; ++i) { CK(cudaEventElapsedTime(&t[i][it], ev[i], ev[i + 1])); }
-      for (size_t c = 0; c < P->chains.size(); ++c) {
-        const ChainInfo& ch = P->chains[c];
-        if (!ch.enabled) continue;
+      {
+        std::map<int, std::vector<int>> by_module;
+        for (size_t c = 0; c < P->chains.size(); ++c) if (P->chains[c].enabled) by_module[P->chains[c].module].push_back((int)c);
+        for (auto& kv : by_module) {
+          float total = 0.f;
+          CK(cudaEventElapsedTime(&total, chain_ev[2 * kv.second[0]], chain_ev[2 * kv.second[0] + 1]));
+          size_t members = 0;
+          for (int c : kv.second) members += P->chains[c].ops.size();
+          for (int c : kv.second) for (int m : P->chains[c].ops) t[m][it] = total / (float)members;
+        }
+      }
+      for (size_t x = 0; x < P->xunits.size(); ++x) {
+        const XUnitInfo& xu = P->xunits[x];
+        if (!xu.enabled) continue;
         float total = 0.f;
-        CK(cudaEventElapsedTime(&total, chain_ev[2 * c], chain_ev[2 * c + 1]));
-        for (int m : ch.ops) t[m][it] = total / (float)ch.ops.size();
+        CK(cudaEventElapsedTime(&total, xunit_ev[2 * x], xunit_ev[2 * x + 1]));
+        double fsum = 0;
+        std::vector<double> fl;
+        for (int m : xu.ops) {
+          const Op& o = P->ops[m];
+          const TensorInfo& to = P->tensors[o.out];
+          fl.push_back((double)to.H * to.W * o.k * o.k * o.cin * o.cout);
+          fsum += fl.back();
+        }
+        for (size_t k = 0; k < xu.ops.size(); ++k) t[xu.ops[k]][it] = (float)(total * fl[k] / fsum);
       }
       for (size_t gi = 0; gi < spans.size(); ++gi) {   // one kernel for the whole span: split its time by estimated cost
         float total = 0.f;
@@ -1709,6 +1918,7 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
   }
   for (auto& e : ev) cudaEventDestroy(e);
   for (auto& e : chain_ev) if (e) cudaEventDestroy(e);
+  for (auto& e : xunit_ev) if (e) cudaEventDestroy(e);
   return HRNET_OK;
 }
 
@@ -1913,6 +2123,15 @@ int hrnet_argmax(const float* heatmaps, int n, int J, int hh, int wh, const floa
   if (n == 0) return HRNET_OK;
   if (!heatmaps || !joints) return fail(HRNET_E_INVALID, "null argument");
   CK(launch_argmax(heatmaps, n, J, hh, wh, boxes, joints, argmax_idx, (cudaStream_t)stream));
+  return HRNET_OK;
+}
+
+int hrnet_resize_cubic_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* xofs,
+                          const int16_t* xcoef, const int32_t* yofs, const int16_t* ycoef, void* stream) {
+  if (n < 0 || sh <= 0 || sw <= 0 || dh <= 0 || dw <= 0) return fail(HRNET_E_INVALID, "bad shape");
+  if (n == 0) return HRNET_OK;
+  if (!src || !dst || !xofs || !xcoef || !yofs || !ycoef) return fail(HRNET_E_INVALID, "null argument");
+  CK(launch_resize_cubic_u8(src, dst, n, sh, sw, dh, dw, xofs, xcoef, yofs, ycoef, (cudaStream_t)stream));
   return HRNET_OK;
 }
 

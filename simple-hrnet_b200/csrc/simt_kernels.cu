@@ -580,4 +580,74 @@ cudaError_t launch_conv_simt(const ConvSimtParams& p, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------ cubic resize (uint8)
+// OpenCV's own INTER_CUBIC kernel for 8-bit images (imgproc/src/resize.cpp: HResizeCubic + VResizeCubic), which is what
+// `cv2.resize(image, (W, H), interpolation=cv2.INTER_CUBIC)` of reference SimpleHRNet.py:216-220 / :356-360 computes when
+// OpenCV's vendor-optimised (IPP) path is off: per axis four taps sx-1 .. sx+2 (indices clamped to the image), Keys cubic
+// weights (A = -0.75) rounded to 11-bit fixed point; the horizontal pass is exact in int32.  The vertical pass has two
+// forms in OpenCV and both are restated: the vector loop (VResizeCubicVec_32s8u, the first 8 * floor(3 * dw / 8)
+// elements of a row with the baseline 128-bit lanes) evaluates s0*b0 + (s1*b1 + (s2*b2 + s3*b3)) in float32 with
+// b = weight / 2^22, unfused, rounds to nearest-even and saturates; the scalar tail adds 1 << 21 to the int32 sum,
+// shifts by 22 and saturates.  The tap tables are built on the host in float32 exactly like OpenCV does
+// (simple_hrnet_b200/preprocess.py).
+//   src [n, sh, sw, 3] uint8, dst [n, dh, dw, 3] uint8; xofs [dw] / yofs [dh] first tap (sx - 1), xcoef [dw][4] / ycoef [dh][4]
+__global__ void __launch_bounds__(256)
+resize_cubic_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n, int sh, int sw, int dh, int dw,
+                       const int32_t* __restrict__ xofs, const int16_t* __restrict__ xcoef,
+                       const int32_t* __restrict__ yofs, const int16_t* __restrict__ ycoef) {
+  const long total = (long)n * dh * dw;
+  const long i = (long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int dx = (int)(i % dw);
+  const long t = i / dw;
+  const int dy = (int)(t % dh);
+  const int img = (int)(t / dh);
+  const int x0 = xofs[dx], y0 = yofs[dy];
+  int xa[4], xi[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { xa[k] = xcoef[dx * 4 + k]; xi[k] = min(max(x0 + k, 0), sw - 1); }
+  int h[4][3];
+  const uint8_t* base = src + (size_t)img * sh * sw * 3;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int yy = min(max(y0 + r, 0), sh - 1);
+    const uint8_t* row = base + (size_t)yy * sw * 3;
+    h[r][0] = h[r][1] = h[r][2] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint8_t* px = row + xi[k] * 3;
+      h[r][0] += (int)px[0] * xa[k]; h[r][1] += (int)px[1] * xa[k]; h[r][2] += (int)px[2] * xa[k];
+    }
+  }
+  int yb[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) yb[r] = ycoef[dy * 4 + r];
+  const int nvec = (3 * dw) & ~7;          // elements of a row the 8-lane vector loop covers
+  const float scale = 1.f / (2048.f * 2048.f);
+  uint8_t* o = dst + (size_t)i * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    int v;
+    if (3 * dx + c < nvec) {
+      float f = __fmul_rn((float)h[3][c], __fmul_rn((float)yb[3], scale));
+      f = __fadd_rn(__fmul_rn((float)h[2][c], __fmul_rn((float)yb[2], scale)), f);
+      f = __fadd_rn(__fmul_rn((float)h[1][c], __fmul_rn((float)yb[1], scale)), f);
+      f = __fadd_rn(__fmul_rn((float)h[0][c], __fmul_rn((float)yb[0], scale)), f);
+      v = __float2int_rn(f);
+    } else {
+      v = (h[0][c] * yb[0] + h[1][c] * yb[1] + h[2][c] * yb[2] + h[3][c] * yb[3] + (1 << 21)) >> 22;
+    }
+    o[c] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+cudaError_t launch_resize_cubic_u8(const uint8_t* src, uint8_t* dst, int n, int sh, int sw, int dh, int dw, const int32_t* xofs,
+                                   const int16_t* xcoef, const int32_t* yofs, const int16_t* ycoef, cudaStream_t st) {
+  const long total = (long)n * dh * dw;
+  if (total == 0) return cudaSuccess;
+  resize_cubic_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, n, sh, sw, dh, dw, xofs, xcoef, yofs, ycoef);
+  return cudaGetLastError();
+}
+
 }  // namespace hrnet

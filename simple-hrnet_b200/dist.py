@@ -52,3 +52,51 @@ class ShardedPredictor:
                 a, b = shard_range(B, self.world, r)
                 buf[a:b] = slots[r * mx: r * mx + (b - a)]
         return buf
+
+    # ---- pipelined form: the collective of batch i overlaps the forward of batch i+1 -----------------------------------
+    def submit(self, images_global_count, images_local):
+        """Enqueue one global batch and return a handle; `result(handle)` gives joints [B,J,3] on every rank.
+
+        The forward + decode of the local shard runs on the caller's current stream; the all-gather is issued on a side
+        stream that only waits for THAT forward (one CUDA event), into one of two rotating gather buffers.  The next
+        `submit` can therefore start its forward immediately: the per-step NCCL launch latency and the rank skew a
+        collective exposes (the ranks never finish a forward at the same instant) hide behind compute instead of sitting
+        between two forwards.  At most two batches may be in flight; equal shards only (B % world == 0)."""
+        B = int(images_global_count)
+        if self.world > 1 and B % self.world:
+            raise ValueError("pipelined gather needs equal shards (B % world_size == 0); use predict_joints")
+        lo, hi = shard_range(B, self.world, self.rank)
+        assert images_local.shape[0] == hi - lo, "local shard does not match shard_range"
+        if not hasattr(self, "_slots"):
+            self._slots, self._turn = [None, None], 0
+            self._comm = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        slot = self._turn
+        self._turn ^= 1
+        st = self._slots[slot]
+        if st is None or st["buf"].shape[0] != B:
+            st = {"buf": torch.empty(B, self.J, 3, dtype=torch.float32, device=self.device), "done": None}
+            self._slots[slot] = st
+        if self._comm is not None and st["done"] is not None:
+            torch.cuda.current_stream(self.device).wait_event(st["done"])   # the buffer's previous gather has finished
+        buf = st["buf"]
+        if hi > lo:
+            self.local_fn(images_local, buf[lo:hi])
+        if self.world > 1:
+            if self._comm is not None:
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(self._comm):
+                    self._comm.wait_event(ready)
+                    dist.all_gather_into_tensor(buf, buf[lo:hi], group=self.group)
+                    st["done"] = torch.cuda.Event()
+                    st["done"].record(self._comm)
+            else:
+                dist.all_gather_into_tensor(buf, buf[lo:hi], group=self.group)
+        return slot
+
+    def result(self, handle):
+        """Joints [B,J,3] of the batch submitted under `handle`; the caller's stream waits for its gather."""
+        st = self._slots[handle]
+        if self._comm is not None and st["done"] is not None:
+            torch.cuda.current_stream(self.device).wait_event(st["done"])
+        return st["buf"]

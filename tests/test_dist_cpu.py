@@ -46,6 +46,14 @@ def _worker(rank, world, port, B, out_dir):
         joints = pred.predict_joints(B, torch.from_numpy(hm[lo:hi]))
         ref, _ = O.decode_joints(hm, boxes)
         assert np.array_equal(joints.numpy(), ref), f"rank {rank}: gathered joints differ"
+        if B % world == 0:   # pipelined form: two batches in flight, results in submission order
+            hm2 = rng.standard_normal((B, 17, 16, 12)).astype(np.float32)
+            ref2, _ = O.decode_joints(hm2, boxes)
+            h1 = pred.submit(B, torch.from_numpy(hm[lo:hi]))
+            h2 = pred.submit(B, torch.from_numpy(hm2[lo:hi]))
+            assert np.array_equal(pred.result(h1).numpy(), ref) and np.array_equal(pred.result(h2).numpy(), ref2)
+            h3 = pred.submit(B, torch.from_numpy(hm[lo:hi]))           # reuses the first buffer
+            assert np.array_equal(pred.result(h3).numpy(), ref)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

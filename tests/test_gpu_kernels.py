@@ -230,3 +230,24 @@ def test_argmax_random_ties_nan_and_full_size():
 
 def test_argmax_empty_batch_is_noop():
     _lib.check(G.lib().hrnet_argmax(None, 0, 17, 64, 48, None, None, None, G.stream()))
+
+
+@pytest.mark.parametrize("shape", [(3, 300, 210, 256, 192), (2, 480, 640, 384, 288), (1, 30, 20, 384, 288), (2, 385, 289, 384, 288),
+                                   (1, 700, 500, 257, 191)], ids=str)
+def test_device_cubic_resize_equals_opencv_kernel(shape):
+    """hrnet_resize_cubic_u8 (the resize of SimpleHRNet.py:216-220 on the device) == cv2.resize(INTER_CUBIC) evaluated by
+    OpenCV's own kernel (vendor path off), bit for bit; and == its host restatement."""
+    import cv2
+    from simple_hrnet_b200.preprocess import CubicResizer, resize_cubic_reference
+    n, sh, sw, dh, dw = shape
+    img = np.random.default_rng(sh + sw).integers(0, 256, (n, sh, sw, 3), dtype=np.uint8)
+    img[0, : sh // 3] = 255; img[0, sh // 3: 2 * sh // 3] = 0
+    out = CubicResizer(torch.device("cuda:0"))(img, dh, dw).cpu().numpy()
+    assert np.array_equal(out, resize_cubic_reference(img, dh, dw))
+    was = cv2.useOptimized()
+    cv2.setUseOptimized(False)
+    try:
+        want = np.stack([cv2.resize(i, (dw, dh), interpolation=cv2.INTER_CUBIC) for i in img])
+    finally:
+        cv2.setUseOptimized(was)
+    assert np.array_equal(out, want)

@@ -27,8 +27,11 @@ def fwd_ms(eng, reps=10):
 
 
 args = sys.argv[1:]
+base_tune = {_lib.TUNE_CHAIN_M2: 1} if "m1" in args else {}
+if "m1" in args:
+    print("im2col chains: one M-tile per ticket")
 if "debug" in args:
-    eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), tune={_lib.TUNE_CHAIN_DEBUG: 1})
+    eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), tune={**base_tune, _lib.TUNE_CHAIN_DEBUG: 1})
     eng.load_state_dict(sd)
     ops, desc = eng.profile_ops(x, iters=3)
     cls = {}
@@ -42,7 +45,7 @@ if "debug" in args:
     eng.close()
 splits = [a for a in args if "," in a]
 for sp in splits:
-    t = {i: int(v) for i, v in enumerate(sp.split(","))}
+    t = {**base_tune, **{i: int(v) for i, v in enumerate(sp.split(","))}}
     eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), tune=t)
     eng.load_state_dict(sd)
     d = eng.describe()
@@ -50,6 +53,9 @@ for sp in splits:
     print(f"split {sp}: {fwd_ms(eng):.3f} ms/forward   grids (module, branch, ctas): {grids}", flush=True)
     eng.close()
 if "nochain" in args:
-    eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), flags=_lib.FLAG_NO_CHAIN)
-    eng.load_state_dict(sd)
-    print(f"no chains: {fwd_ms(eng):.3f} ms/forward")
+    for name, fl in (("chains + exchange units (default)", 0), ("chains, per-conv exchange convs", _lib.FLAG_NO_XUNIT),
+                     ("exchange units, per-conv branch convs", _lib.FLAG_NO_CHAIN), ("every conv its own launch", _lib.FLAG_NO_CHAIN | _lib.FLAG_NO_XUNIT)):
+        eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), flags=fl, tune=base_tune)
+        eng.load_state_dict(sd)
+        print(f"{name}: {fwd_ms(eng):.3f} ms/forward ({eng.launch_count} launches)", flush=True)
+        eng.close()
