@@ -411,7 +411,11 @@ def main():
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    per_rank_ms = None
     if world > 1:
+        allms = torch.zeros(world, device=dev)
+        dist.all_gather_into_tensor(allms, ms)
+        per_rank_ms = [round(float(v) / args.steps, 4) for v in allms.tolist()]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
@@ -593,6 +597,9 @@ def main():
                "roofline": roofline, "layer_breakdown": breakdown, "cpu_baseline": cpu}
         if gather_check is not None:
             out["gather_check"] = gather_check
+            # every rank's own device time per step: the reported step time is the slowest rank's (the ranks only meet in
+            # the pipelined all-gather, so a spread here is GPU-to-GPU variation, not communication)
+            out["ms_per_step_per_rank"] = per_rank_ms
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
