@@ -49,8 +49,6 @@ extern "C" {
 #define HRNET_FLAG_NO_CHAIN 128u   /* debug / cross-check: launch the eight convs of a StageModule branch one by one
                                       instead of as one persistent branch-chain kernel (bit-identical results)     */
 
-#define HRNET_FLAG_NO_XUNIT 256u   /* debug / cross-check: launch the convs of a StageModule's fuse layers one by one instead
-                                      of as one persistent exchange-unit kernel (bit-identical results)                */
 
 /* Tuning / diagnostic knobs of a plan (HrnetDesc.tune[]); 0 = the library's default.  They select between kernel
  * variants that compute the same function (results agree to accumulation-order noise at most; the default set is what
@@ -78,6 +76,14 @@ extern "C" {
 #define HRNET_TUNE_GRID_CAP 17      /* single-op entry points: cap on the persistent grid (experiments)              */
 #define HRNET_TUNE_CHAIN_M2 18       /* im2col chains: 2 = two M-tiles per ticket sharing every weight k-block (30 % fewer TMA
                                       bytes, no accumulator double buffering); default one tile per ticket             */
+#define HRNET_TUNE_XUNIT 19          /* exchange-unit kernel (conv_xunit.cu), opt-in: 1 = the convs of a StageModule's fuse layers as
+                                      one ticket-scheduled kernel, 2 = its sums too (as sum tickets).  Bit-identical to the
+                                      default (one launch per conv, fuse_sum_kernel); measured no faster inside the forward  */
+#define HRNET_TUNE_CHAIN_PAIR 20     /* im2col chains on CTA pairs (tcgen05 cta_group::2: a unit = two M-tiles, each CTA stages half of
+                                      the weight tile): 2 = on                                                          */
+#define HRNET_TUNE_CHAIN_SKIP 21     /* experiments only, RESULTS INVALID: the im2col chain's epilogue does 1 = nothing, 2 = only its
+                                      accumulator loads, 3 = only its residual loads and stores (what slows the MMA stream?) */
+#define HRNET_TUNE_CHAIN_STAGES 22   /* im2col chains: pipeline stages (default: as many as fit in shared memory, <= 8)                 */
 #define HRNET_TUNE_COUNT 24
 
 typedef struct HrnetPlan HrnetPlan;

@@ -29,11 +29,14 @@ class HrnetParamInfo(ctypes.Structure):
 ARCH_HRNET, ARCH_POSERESNET = 0, 1
 FLAG_FORCE_SIMT, FLAG_NO_GRAPH, FLAG_FUSE_F32, FLAG_SERIAL, FLAG_NO_PATCH, FLAG_PARTITION, FLAG_GROUP = 1, 2, 4, 8, 16, 32, 64
 FLAG_NO_CHAIN = 128
-FLAG_NO_XUNIT = 256
 TUNE_CHAIN_SHARE0, TUNE_CHAIN_GRID_CAP, TUNE_CHAIN_DEBUG = 0, 4, 5
 TUNE_IGEMM_PAIR, TUNE_IGEMM_PAIR_MIN_K, TUNE_PATCH_PAIR_MIN_COUT, TUNE_PATCH_PAIR_MAX_COUT = 6, 7, 8, 9
 TUNE_EPILOGUE, TUNE_BPS, TUNE_IGEMM_MMA2, TUNE_PATCH_MMA2, TUNE_PATCH_NACC, TUNE_NO_PDL, TUNE_DEBUG, TUNE_GRID_CAP = 10, 11, 12, 13, 14, 15, 16, 17
 TUNE_CHAIN_M2 = 18
+TUNE_XUNIT = 19
+TUNE_CHAIN_PAIR = 20
+TUNE_CHAIN_SKIP = 21
+TUNE_CHAIN_STAGES = 22
 TUNE_COUNT = 24
 EPI_AUTO, EPI_DIRECT, EPI_TMA, EPI_COAL, EPI_TMA_PATCH, EPI_TMA_IGEMM, EPI_BATCH = 0, 1, 2, 3, 4, 5, 6
 

@@ -74,6 +74,40 @@ __device__ __forceinline__ void chain_cols16(const uint32_t (&v)[16], const U256
   stg256(reinterpret_cast<__half*>(e.out) + e.row_off + c, o);
 }
 
+// The same with the BN constants read from the KERNEL PARAMETERS (constant bank): `sb` must be a reference into the
+// __grid_constant__ parameter block ((scale, bias) per absolute output channel), so every access is an LDC -- no
+// shared-memory or L1 wavefront.  Why: the tensor core's operand reads, LDS and LDG / STG share the SM's L1 data pipe,
+// and a warp-wide LDS.128 costs four wavefronts even when all lanes read the same address: the constants of a 128 x 48
+// tile cost 452 wavefronts next to the 1,188 of its MMAs, and the pipe was 84 % busy -- the bound of the halo-patch
+// chains (profiles/r02_s11_ncu_chain_kernels.md; without any epilogue work the C = 48 chain runs 1,345 instead of
+// 2,150 clk per tile, profiles/r02_s18_*.log).  Same arithmetic, same results.
+template <typename SB>
+__device__ __forceinline__ void chain_cols16_c(const uint32_t (&v)[16], const U256& r, const EpiRow& e, int c, const SB& sb) {
+  float y[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 s = sb[e.ch0 + c + i];
+    y[i] = fmaf(__uint_as_float(v[i]), s.x, s.y);
+  }
+  if (e.residual != nullptr) {
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __half22float2(h[i]);
+      y[2 * i] += f.x; y[2 * i + 1] += f.y;
+    }
+  }
+  if (e.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+  }
+  U256 o;
+  __half2* oh2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oh2[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+  stg256(reinterpret_cast<__half*>(e.out) + e.row_off + c, o);
+}
+
 // generic-proxy accesses before / async-proxy (TMA) accesses after, all state spaces
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t addr) {
@@ -102,27 +136,34 @@ __device__ __forceinline__ void chain_wait_counter(const unsigned* c, unsigned w
   if (ld_acquire_gpu(c) < want) chain_wait_counter_slow(c, want);
 }
 // Ring consumer: every consuming thread walks every entry (tile descriptor or kChainDone), in order.
+// CTA pairs (conv_chain.cu, cta_group::2): the LEADER's scheduler fills both CTAs' rings.  A consumer of the peer CTA
+// (`peer`) waits on its own CTA's `full` barrier with cluster-scope acquire (the descriptor words were stored remotely)
+// and releases the slot on the leader's `empty` barrier.
 struct RingReader {
   uint32_t full0, empty0, info0, coord0;
   int i;
-  __device__ __forceinline__ void init(ChainRing* r) {
+  bool peer;
+  __device__ __forceinline__ void init(ChainRing* r, bool peer_cta = false) {
     full0 = ptx::smem_u32(&r->full[0]); empty0 = ptx::smem_u32(&r->empty[0]); info0 = ptx::smem_u32(&r->info[0]);
     coord0 = ptx::smem_u32(&r->coord[0]);
     i = 0;
+    peer = peer_cta;
   }
   __device__ __forceinline__ uint32_t next(uint32_t& coord, uint32_t& coord2) {
     const uint32_t slot = (uint32_t)(i % kChainRing);
     const uint32_t ph = (uint32_t)((i / kChainRing) & 1);
-    ptx::mbar_wait(full0 + 8u * slot, ph);
+    if (peer) ptx::mbar_wait_cluster(full0 + 8u * slot, ph);
+    else ptx::mbar_wait(full0 + 8u * slot, ph);
     const uint32_t v = lds_volatile_u32(info0 + 4u * slot);
     coord = lds_volatile_u32(coord0 + 4u * slot);
     coord2 = lds_volatile_u32(coord0 + 4u * (kChainRing + slot));
-    ptx::mbar_arrive(empty0 + 8u * slot);
+    if (peer) ptx::mbar_arrive_cluster(empty0 + 8u * slot, 0);
+    else ptx::mbar_arrive(empty0 + 8u * slot);
     ++i;
     return v;
   }
   // true when the next entry is already published (next() would not block)
-  __device__ __forceinline__ bool ready() const {
+  __device__ __forceinline__ bool ready() const {      // (a hint only: no acquire semantics needed)
     const uint32_t slot = (uint32_t)(i % kChainRing);
     const uint32_t ph = (uint32_t)((i / kChainRing) & 1);
     return ptx::mbar_test_wait(full0 + 8u * slot, ph);
@@ -135,10 +176,12 @@ struct RingReader {
 struct RingWriter {
   uint32_t full0, empty0, info0, coord0;
   int i;
-  __device__ __forceinline__ void init(ChainRing* r) {
+  bool pair;      // also fill the ring of CTA 1 of the cluster (same shared-memory offsets)
+  __device__ __forceinline__ void init(ChainRing* r, bool pair_mode = false) {
     full0 = ptx::smem_u32(&r->full[0]); empty0 = ptx::smem_u32(&r->empty[0]); info0 = ptx::smem_u32(&r->info[0]);
     coord0 = ptx::smem_u32(&r->coord[0]);
     i = 0;
+    pair = pair_mode;
   }
   __device__ __forceinline__ void acquire_slot() {
     const uint32_t slot = (uint32_t)(i % kChainRing);
@@ -150,6 +193,12 @@ struct RingWriter {
     sts_volatile_u32(info0 + 4u * slot, v);
     sts_volatile_u32(coord0 + 4u * slot, coord);
     sts_volatile_u32(coord0 + 4u * (kChainRing + slot), coord2);
+    if (pair) {
+      ptx::st_shared_cluster_u32(ptx::mapa_cluster(info0 + 4u * slot, 1), v);
+      ptx::st_shared_cluster_u32(ptx::mapa_cluster(coord0 + 4u * slot, 1), coord);
+      ptx::st_shared_cluster_u32(ptx::mapa_cluster(coord0 + 4u * (kChainRing + slot), 1), coord2);
+      ptx::mbar_arrive_cluster(full0 + 8u * slot, 1);   // release at cluster scope
+    }
     ptx::mbar_arrive(full0 + 8u * slot);     // release at CTA scope: the descriptor is visible to the waiters
     ++i;
   }
@@ -198,6 +247,49 @@ __device__ __forceinline__ void chain_store_row(U256 (&r)[4], const EpiRow& e, u
           chain_cols16(v0, cur[2 * h], e, c);
           if (two) chain_cols16(v1, cur[2 * h + 1], e, c + 16);
         }
+      }
+    }
+  }
+}
+
+template <typename SB>
+__device__ __forceinline__ void chain_store_row_c(U256 (&r)[4], const EpiRow& e, uint32_t t_row, const SB& sb) {
+  for (int c64 = 0; c64 < e.ncols; c64 += 64) {
+    U256 cur[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = r[i];
+    if (c64 + 64 < e.ncols) chain_load_residual(r, e, c64 + 64);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c64 + 32 * h;
+      if (c < e.ncols) {                       // warp-uniform
+        uint32_t v0[16], v1[16];
+        const bool two = c + 16 < e.ncols;     // warp-uniform
+        ptx::tmem_ld16(t_row + (uint32_t)c, v0);
+        if (two) ptx::tmem_ld16(t_row + (uint32_t)(c + 16), v1);
+        ptx::tmem_ld_wait();
+        if (e.valid) {
+          chain_cols16_c(v0, cur[2 * h], e, c, sb);
+          if (two) chain_cols16_c(v1, cur[2 * h + 1], e, c + 16, sb);
+        }
+      }
+    }
+  }
+}
+template <typename SB>
+__device__ __forceinline__ void chain_store_row_lean_c(const EpiRow& e, uint32_t t_row, U256 (&r)[4], const SB& sb) {
+  const bool has_res = e.residual != nullptr && e.valid;
+  const __half* rp = e.residual + e.row_off;
+  for (int c64 = 0; c64 < e.ncols; c64 += 64) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c64 + 16 * j;
+      if (c < e.ncols) {                         // warp-uniform
+        uint32_t v[16];
+        ptx::tmem_ld16(t_row + (uint32_t)c, v);
+        ptx::tmem_ld_wait();
+        if (e.valid) chain_cols16_c(v, r[j], e, c, sb);
+        if (has_res && c + 64 < e.ncols) r[j] = ldg256_cg(rp + c + 64);
       }
     }
   }

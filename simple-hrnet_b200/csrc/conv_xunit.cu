@@ -10,7 +10,13 @@
 // counter exactly like the branch chains (conv_chain.cu) and a conv of a later level starts when its producer conv has
 // published all of its tiles.  The pipeline inside the CTA is the im2col pipeline of conv_igemm_body.cuh with per-op
 // geometry (kernel size, stride, channels, map size, N tile) taken from an op table in the kernel parameters; outputs are
-// the same fp16 terms as before (bit-identical to the per-conv launches), summed by fuse_sum_kernel afterwards.
+// the same fp16 terms as before (bit-identical to the per-conv launches).
+//
+// The sums of the unit (out_i = ReLU(sum_j nearest_up(term_ij)), models_/hrnet.py:60-69) run in the SAME kernel as "sum
+// tickets": 1024 output pixels each, executed by the epilogue warpgroups (the other roles skip them), placed in the ticket
+// sequence right behind the last conv level they depend on -- so the HBM-bound sums of the high-resolution outputs
+// overlap the latency-bound down-chain convs of the others, and a module's exchange is one launch instead of 16 + 4.
+// Same arithmetic as fuse_sum_kernel (fp32 sum in ascending branch order, one rounding), terms read with ld.global.cg.
 #include <algorithm>
 
 #include "chain_common.cuh"
@@ -18,6 +24,86 @@
 namespace hrnet {
 
 constexpr int kXThreads = 384;
+constexpr uint32_t kXSumFlag = 1u << 27;      // ring entry: sum ticket (bits 28-29: output, bits 0-23: chunk)
+
+// one sum ticket: pixels [chunk * kXSumChunk, ...) of output `sm`, by the 128 threads of one epilogue warpgroup.
+// The sum is HBM-bound and only 256 threads per SM work on it, so every thread keeps four items (8 channels of one pixel
+// each) x up to four sources = 16 independent 16-byte loads in flight (one item at a time ran 4x over the stand-alone
+// fuse_sum_kernel's time: profiles/r02_s9_xunit_sum_tickets_v1_slow.log).
+__device__ __forceinline__ void xunit_sum_chunk(const XSum& sm, int chunk, int tid128) {
+  constexpr int kU = 4;
+  const int CV = sm.C >> 3;
+  const int p0 = chunk * kXSumChunk;
+  const int npx = min(kXSumChunk, (int)sm.npix - p0);
+  const int items = npx * CV;
+  // item i = (pixel p0 + i / CV, channel group i % CV); a thread's items are 128 apart: (pixel, group) advance by
+  // (128 / CV, 128 % CV) with carry, and (image, row, column) follow the pixel -- no division inside the loop
+  const int dq = 128 / CV, dr = 128 - dq * CV;
+  int px = tid128 / CV, cv = tid128 - px * CV;
+  int n = (p0 + px) / (sm.H * sm.W);
+  int rem = (p0 + px) - n * sm.H * sm.W;
+  int h = rem / sm.W, w = rem - h * sm.W;
+  for (int i0 = tid128; i0 < items; i0 += 128 * kU) {
+    uint4 u[kU][4];
+    size_t ooff[kU];
+#pragma unroll
+    for (int q = 0; q < kU; ++q) {
+      ooff[q] = 0;
+      if (i0 + 128 * q < items) {
+        ooff[q] = (size_t)(p0 + px) * sm.C + (size_t)cv * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < sm.nsrc) {
+            const int sh = sm.shift[j];
+            const int sH = sm.H >> sh, sW = sm.W >> sh;
+            const size_t off = ((((size_t)n * sH + (h >> sh)) * sW + (w >> sh)) * sm.C) + (size_t)cv * 8;
+            u[q][j] = __ldcg(reinterpret_cast<const uint4*>(sm.src[j] + off));
+          }
+        }
+      }
+      // advance to this thread's next item
+      int adv = dq;
+      cv += dr;
+      if (cv >= CV) { cv -= CV; ++adv; }
+      px += adv;
+      w += adv;
+      while (w >= sm.W) { w -= sm.W; ++h; }
+      while (h >= sm.H) { h -= sm.H; ++n; }
+    }
+#pragma unroll
+    for (int q = 0; q < kU; ++q) {
+      if (i0 + 128 * q < items) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < sm.nsrc) {
+            const __half2* hh = reinterpret_cast<const __half2*>(&u[q][j]);
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hh[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+            if (j == 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] = v[k];
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) acc[k] += v[k];
+            }
+          }
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a = acc[2 * k], b = acc[2 * k + 1];
+          if (sm.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          oh[k] = __floats2half2_rn(a, b);
+        }
+        *reinterpret_cast<uint4*>(sm.out + ooff[q]) = o;
+      }
+    }
+  }
+}
+
 constexpr int kXMaxKb = 384;     // k-blocks of all member convs together (W48: 167)
 
 struct __align__(8) XUnitBars {
@@ -86,34 +172,53 @@ conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant_
     if (ptx::elect_one()) {
       RingWriter rw; rw.init(&bars->ring);
       long long dbg_dep = 0; int dbg_tiles = 0;
-      int o = 0;
-      int dep_checked = -1;             // ops up to this index have had their producer confirmed complete
+      // Tickets interleave conv ops and sums in dependency order; `seg` walks the merged sequence (tickets only grow).
+      // seg < nops + nsums; order[] is implicit: every op / sum carries its ticket0, so find the owner by range.
+      uint32_t conv_ok = 0u, sum_ok = 0u;      // producers confirmed complete (per op / per sum), cached per CTA
       unsigned next = atomicAdd(&p.ctrl[0], 1u);
       for (;;) {
         const unsigned t = next;
         if (t >= (unsigned)p.total_tickets) { rw.acquire_slot(); rw.publish(kChainDone); break; }
         next = atomicAdd(&p.ctrl[0], 1u);
-        while (o + 1 < p.nops && (int)t >= p.op[o + 1].ticket0) ++o;      // tickets only grow
-        const XOp& op = p.op[o];
-        const int mt = (int)t - op.ticket0;
-        if (o > dep_checked) {
-          if (op.dep >= 0) {
-            const long long tq = p.dbg ? clock64() : 0;
-            chain_wait_counter(p.counters + op.dep, (unsigned)op.dep_need);
-            fence_proxy_async_all();   // the acquired generic-proxy stores before the TMA (async-proxy) reads issued downstream
-            if (p.dbg) dbg_dep += clock64() - tq;
+        int owner = -1;                       // conv op index, or nops + sum index
+        for (int o = 0; o < p.nops; ++o)
+          if ((int)t >= p.op[o].ticket0 && (int)t < p.op[o].ticket0 + p.op[o].m_tiles) owner = o;
+        for (int q = 0; q < p.nsums; ++q)
+          if ((int)t >= p.sum[q].ticket0 && (int)t < p.sum[q].ticket0 + p.sum[q].nchunks) owner = p.nops + q;
+        if (owner < p.nops) {
+          const XOp& op = p.op[owner];
+          const int mt = (int)t - op.ticket0;
+          if (!((conv_ok >> owner) & 1u)) {
+            if (op.dep >= 0) {
+              const long long tq = p.dbg ? clock64() : 0;
+              chain_wait_counter(p.counters + op.dep, (unsigned)op.dep_need);
+              fence_proxy_async_all();   // the acquired generic-proxy stores before the TMA (async-proxy) reads issued downstream
+              if (p.dbg) dbg_dep += clock64() - tq;
+            }
+            conv_ok |= 1u << owner;
           }
-          dep_checked = o;
-        }
-        const int m0 = mt * kTileM;
-        const int img = m0 / op.OHW;
-        const int rem = m0 - img * op.OHW;
-        const int oh0 = rem / op.OW;
-        const uint32_t coord = ((uint32_t)img << 16) | ((uint32_t)oh0 << 8) | (uint32_t)(rem - oh0 * op.OW);
-        for (int nt = 0; nt < op.n_tiles; ++nt) {
+          const int m0 = mt * kTileM;
+          const int img = m0 / op.OHW;
+          const int rem = m0 - img * op.OHW;
+          const int oh0 = rem / op.OW;
+          const uint32_t coord = ((uint32_t)img << 16) | ((uint32_t)oh0 << 8) | (uint32_t)(rem - oh0 * op.OW);
+          for (int nt = 0; nt < op.n_tiles; ++nt) {
+            rw.acquire_slot();
+            rw.publish(((uint32_t)owner << 28) | ((uint32_t)nt << 24) | (uint32_t)mt, coord);
+            ++dbg_tiles;
+          }
+        } else {
+          const int q = owner - p.nops;
+          const XSum& sm = p.sum[q];
+          if (!((sum_ok >> q) & 1u)) {
+            const long long tq = p.dbg ? clock64() : 0;
+            for (int j = 0; j < sm.nsrc; ++j)
+              if (sm.dep[j] >= 0) chain_wait_counter(p.counters + sm.dep[j], (unsigned)sm.dep_need[j]);
+            if (p.dbg) dbg_dep += clock64() - tq;
+            sum_ok |= 1u << q;
+          }
           rw.acquire_slot();
-          rw.publish(((uint32_t)o << 28) | ((uint32_t)nt << 24) | (uint32_t)mt, coord);
-          ++dbg_tiles;
+          rw.publish(kXSumFlag | ((uint32_t)q << 28) | (uint32_t)((int)t - sm.ticket0));
         }
       }
       if (p.dbg) { p.dbg[blockIdx.x * 16 + 0] = dbg_dep; p.dbg[blockIdx.x * 16 + 1] = dbg_tiles; }
@@ -130,7 +235,8 @@ conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant_
         uint32_t coord;
         const uint32_t info = rr.next(coord);
         if (info == kChainDone) break;
-        const int o = (int)(info >> 28), nt = (int)((info >> 24) & 15u);
+        if (info & kXSumFlag) continue;          // sum tickets belong to the epilogue warpgroups
+        const int o = (int)(info >> 28), nt = (int)((info >> 24) & 7u);
         const XOp& op = p.op[o];
         const int img = (int)(coord >> 16);
         const int bw = (int)(coord & 255u) * op.stride - op.pad, bh = (int)((coord >> 8) & 255u) * op.stride - op.pad;
@@ -160,9 +266,10 @@ conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       bool ready = false;
-      for (int it = 0;; ++it) {
+      for (int it = 0;;) {
         const uint32_t info = rr.next();
         if (info == kChainDone) break;
+        if (info & kXSumFlag) continue;
         const XOp& op = p.op[info >> 28];
         const uint32_t idesc = ptx::umma_idesc_f16(kTileM, op.n_tile);
         const int ctail = op.Cin - (op.cpt - 1) * kKC;
@@ -196,6 +303,7 @@ conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant_
           stage = nstage; phase = nphase; ready = nready;
         }
         ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
+        ++it;
       }
     }
     __syncwarp();
@@ -208,14 +316,22 @@ conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant_
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * acc_stride;
     RingReader rr; rr.init(&bars->ring);
     PendingPublish pend; pend.clear();
-    for (int it = 0;; ++it) {
+    int it = 0, its = 0;                 // conv tiles / sum tickets seen so far (both warpgroups count all of them)
+    for (;;) {
       if (!rr.ready()) pend.flush(1 + g, leader);      // about to sleep on the ring: publish first (see PendingPublish)
       const uint32_t info = rr.next();
       if (info == kChainDone) break;
-      if ((it & 1) != g) continue;
+      if (info & kXSumFlag) {
+        if ((its++ & 1) == g) {
+          pend.flush(1 + g, leader);
+          xunit_sum_chunk(p.sum[(info >> 28) & 3u], (int)(info & 0xffffffu), (int)threadIdx.x - 128 - 128 * g);
+        }
+        continue;
+      }
+      if ((it++ & 1) != g) continue;
       pend.flush(1 + g, leader);
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int o = (int)(info >> 28), nt = (int)((info >> 24) & 15u), mt = (int)(info & 0xffffffu);
+      const uint32_t acc_phase = (uint32_t)(((it - 1) >> 1) & 1);
+      const int o = (int)(info >> 28), nt = (int)((info >> 24) & 7u), mt = (int)(info & 0xffffffu);
       const XOp& op = p.op[o];
       const int m = mt * kTileM + row;
       const int n0 = nt * op.n_tile;

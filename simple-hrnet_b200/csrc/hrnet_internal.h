@@ -136,18 +136,24 @@ struct ChainConv {
 // control words of one chain in global memory: [0] ticket counter, [1] exited-CTA counter.
 // counters[conv * unit_stride + unit] = finished tiles of that unit (a row of 8x16 tiles of one image / a 128-pixel
 // M-tile); the last CTA of a launch clears what the launch used.
+constexpr int kChainMaxCoutI = 384;   // widest im2col chain / halo-patch chain whose BN constants travel in the kernel parameters
+constexpr int kChainMaxCoutP = 128;
 struct ChainIgemmParams {
   int nconv;
   int M_total, OH, OW, OHW, C;
   int cpt, nkb, bps, n_tile, n_tiles, m_tiles, stages, tmem_cols, a_blk_bytes, b_blk_bytes;
   int m2;                    // M-tiles per ticket: 1, or 2 (both tiles share every weight k-block of a pipeline stage)
-  int units;                 // tickets per conv = ceil(m_tiles / m2)
+  int skip;                  // experiments only (HRNET_TUNE_CHAIN_SKIP, results invalid): 1 no epilogue work, 2 accumulator loads
+                             // only, 3 residual loads + stores only
+  int pair;                  // CTA pairs (cta_group::2): a unit = two M-tiles, one per CTA of the cluster (m2 == 1 then)
+  int units;                 // tickets per conv = ceil(m_tiles / tiles per unit)
   int unit_stride;           // counters per conv (units at max batch)
   int pdl;                   // host side: launch with programmatic stream serialization
   unsigned* ctrl;
   unsigned* counters;
   long long* dbg;            // optional per-CTA counters (8 x int64 per CTA)
   ChainConv conv[kChainMaxConv];
+  float2 sb[kChainMaxConv][kChainMaxCoutI];   // (BN scale, bias) per conv and output channel: read as constants (LDC) by the epilogue
 };
 struct ChainIgemmMaps { CUtensorMap a[kChainMaxConv], b[kChainMaxConv]; };
 struct ChainPatchParams {
@@ -155,11 +161,13 @@ struct ChainPatchParams {
   ConvPatchParams pp;        // geometry / shared-memory layout common to all convs of the chain (scale .. out unused)
   int unit_stride;           // counters per conv (tile rows at max batch)
   int chunk;                 // tiles per ticket: a divisor of pp.tiles_w (neighbouring tiles of one tile row)
+  int skip;                  // experiments only (HRNET_TUNE_CHAIN_SKIP): 9 = the general MMA issue loop
   int pdl;                   // host side: launch with programmatic stream serialization
   unsigned* ctrl;
   unsigned* counters;
   long long* dbg;
   ChainConv conv[kChainMaxConv];
+  float2 sb[kChainMaxConv][kChainMaxCoutP];   // (BN scale, bias) per conv and output channel (see ChainIgemmParams)
 };
 struct ChainPatchMaps { CUtensorMap a[kChainMaxConv]; CUtensorMap b[kChainMaxConv][2]; };
 cudaError_t launch_chain_igemm(const ChainIgemmMaps& maps, const ChainIgemmParams& p, int smem_bytes, int grid, cudaStream_t st);
@@ -183,8 +191,21 @@ struct XOp {
   const float* bias;
   __half* out;
 };
+// one output of the exchange unit: out = ReLU(sum_j nearest_up(src_j)), models_/hrnet.py:60-69 (fp32 sum in ascending j)
+constexpr int kXSumChunk = 1024;   // output pixels per sum ticket
+struct XSum {
+  int H, W, C, nsrc, relu;
+  int shift[4];
+  int dep[4], dep_need[4];       // member conv producing src j (-1: a module input, e.g. the identity term) and its tile count
+  long long npix;                // N * H * W
+  int ticket0, nchunks;
+  const __half* src[4];
+  __half* out;
+};
 struct XUnitParams {
   int nops, total_tickets, total_kb;
+  int nsums;
+  XSum sum[4];
   int stages, tmem_cols, a_blk_bytes, b_blk_bytes, pdl;
   unsigned* ctrl;                // [0] ticket counter, [1] exited-CTA counter
   unsigned* counters;            // [nops] finished tiles per op

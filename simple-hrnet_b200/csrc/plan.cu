@@ -51,6 +51,9 @@ struct ChainInfo {
   double cost = 0;                 // estimated SM-cycles of the whole chain (grid split)
   int flag_stride = 0;             // unit counters per conv (at max batch)
   int m2 = 1, stages = 0;          // im2col chain: M-tiles per ticket, pipeline stages
+  bool pair = false;               // im2col chain on CTA pairs (cta_group::2): a unit = two M-tiles, one per CTA
+  std::vector<float> sb;           // host copy of the member convs' BN (scale, bias) pairs [conv][cout][2], read back by
+                                   // hrnet_plan_bind: they travel to the chain kernels as kernel parameters (constant bank)
   size_t ctrl_off = 0, flags_off = 0;   // bytes into the activation workspace
   ChainIgemmMaps imaps;            // filled by hrnet_plan_bind
   ChainPatchMaps pmaps;
@@ -58,6 +61,7 @@ struct ChainInfo {
 
 // One exchange unit (conv_xunit.cu): every conv of a StageModule's fuse layers issued as one persistent kernel.
 struct XUnitInfo {
+  std::vector<int> sums;           // the module's exchange sums (OP_FUSE ops), executed as sum tickets of the same kernel
   std::vector<int> ops;            // member convs in ticket (dependency) order
   int module = -1;
   bool enabled = false;
@@ -498,6 +502,8 @@ int build_hrnet(HrnetPlan& P) {
       f.out = b.new_tensor(arena, ti.C, ti.H, ti.W);
       outs[i] = f.out;
       b.push(f);
+      P.ops.back().xunit = xid;
+      P.xunits[xid].sums.push_back((int)P.ops.size() - 1);
     }
     xs = outs;
     return arena;
@@ -642,6 +648,7 @@ void plan_chains(HrnetPlan& P) {
       if (o.use_patch) ok = ok && o.pp.cs == 1 && !o.pp.b_stream && o.pp.epi_tma == 0 && o.pp.nacc == 4;
       else ok = ok && o.tc.cs == 1 && o.tc.epi == 0 && o.tc.n_tile <= 256 && o.cout / o.tc.n_tile <= 15;
     }
+    ok = ok && o0.cout <= (o0.use_patch ? kChainMaxCoutP : kChainMaxCoutI);
     if (!ok) continue;
     ch.enabled = true;
     ch.patch = o0.use_patch;
@@ -660,17 +667,25 @@ void plan_chains(HrnetPlan& P) {
       // (opt-in, HRNET_TUNE_CHAIN_M2 = 2: measured equal inside the forward -- 7.228 vs 7.229 ms -- and slower alone on
       // the GPU, where half as many tickets per conv leave CTAs idle: profiles/r02_s5_chain_deferred_publish_m1_vs_m2.log)
       ch.m2 = (P.desc.tune[HRNET_TUNE_CHAIN_M2] == 2 && 2 * o0.tc.n_tile <= 512) ? 2 : 1;
+      // CTA pairs (HRNET_TUNE_CHAIN_PAIR = 2): one cta_group::2 MMA spans the two M-tiles of a unit, each CTA stages half
+      // of the weight tile -> 56 instead of 80 KB of shared-memory traffic per 128 x 192 x 64 step and SM
+      ch.pair = P.desc.tune[HRNET_TUNE_CHAIN_PAIR] == 2 && o0.tc.n_tile % 32 == 0 && 2 * o0.tc.n_tile <= 512;
+      if (ch.pair) ch.m2 = 1;
+      const int tpu = ch.pair ? 2 : ch.m2;                           // M-tiles per unit
       {
         const int a_blk = (int)align_up((size_t)128 * o0.tc.kc * 2, 1024);
-        const int b_blk = (int)align_up((size_t)o0.tc.n_tile * o0.tc.kc * 2, 1024);
+        const int b_blk = (int)align_up((size_t)(o0.tc.n_tile / (ch.pair ? 2 : 1)) * o0.tc.kc * 2, 1024);
         const int stage = o0.tc.bps * (ch.m2 * a_blk + b_blk);
         const int fixed = 1024 + 2048;                               // alignment slack + barriers, ring, k-block table
-        ch.stages = std::max(2, std::min(o0.tc.stages > 4 ? o0.tc.stages : 4, (kChainMaxSmem - fixed) / stage));
+        // as deep as shared memory allows: under load a stage refill (commit -> empty -> TMA -> full) takes ~2.2 k clk, i.e.
+        // 5-7 k-blocks of MMA time (tools/exp/mma_tma_mix.cu: 148 CTAs x 160 KB in flight move 72 B/clk per SM)
+        ch.stages = std::max(2, std::min(P.desc.tune[HRNET_TUNE_CHAIN_STAGES] > 0 ? P.desc.tune[HRNET_TUNE_CHAIN_STAGES] : 8 /* kMaxStages of conv_igemm_body.cuh */,
+                                         (kChainMaxSmem - fixed) / stage));
         ch.smem = fixed + ch.stages * stage;
       }
-      ch.flag_stride = (m_tiles + ch.m2 - 1) / ch.m2;                // one counter per ticket (m2 M-tiles x n_tiles arrivals)
+      ch.flag_stride = (m_tiles + tpu - 1) / tpu;                    // one counter per ticket (tpu M-tiles x n_tiles arrivals)
       // measured inside the per-conv kernels: ~200 clk per K16 step of a 128 x 192 tile (profiles/r01_exp_gridcap_pair_sweep.log)
-      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * (200.0 * o0.tc.n_tile / 192.0);
+      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * ((ch.pair ? 140.0 : 200.0) * o0.tc.n_tile / 192.0);
     }
     ch.ctrl_off = cur; cur += 256;
     ch.flags_off = cur; cur += ((size_t)ch.ops.size() * ch.flag_stride * 4 + 255) / 256 * 256;
@@ -707,8 +722,14 @@ void plan_chains(HrnetPlan& P) {
 
 // Exchange units: which modules' fuse-layer convs run as one kernel, ticket order, shared-memory needs, control words.
 void plan_xunits(HrnetPlan& P) {
-  const uint32_t off_flags = HRNET_FLAG_NO_XUNIT | HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_GROUP | HRNET_FLAG_PARTITION | HRNET_FLAG_FUSE_F32;
-  const bool want = !(P.desc.flags & off_flags);
+  // Opt-in (HRNET_TUNE_XUNIT): measured on B200 the single kernel cuts the exchange convs' serial kernel time 2.6x (1,350 ->
+  // 525 us per forward) but not the forward (7.37 vs 7.33 ms, 7.70 vs 7.35 ms in a second session): launched one by one on
+  // four streams the small convs already overlap each other and the tails of the unevenly finishing branch chains, while
+  // one kernel waits for the slowest chain; sums as tickets (256 epilogue threads per SM) cannot match fuse_sum_kernel's
+  // bandwidth (8.80 ms).  profiles/r02_s7_xunit_first_contact.log, r02_s9_xunit_sum_tickets_v2.log
+  const uint32_t off_flags = HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_GROUP | HRNET_FLAG_PARTITION | HRNET_FLAG_FUSE_F32;
+  const int mode = P.desc.tune[HRNET_TUNE_XUNIT];
+  const bool want = (mode == 1 || mode == 2) && !(P.desc.flags & off_flags);
   size_t cur = (P.act_bytes + 255) / 256 * 256;
   const size_t begin = cur;
   for (size_t x = 0; x < P.xunits.size(); ++x) {
@@ -723,6 +744,13 @@ void plan_xunits(HrnetPlan& P) {
       max_nt = std::max(max_nt, o.tc.n_tile);
       total_kb += o.k * o.k * ((o.cin + 63) / 64);
     }
+    if (mode != 2) {      // sums as separate launches
+      for (int i : xu.sums) { P.ops[i].xunit = -1; P.ops[i].xpos = 0; }
+      xu.sums.clear();
+    }
+    if (xu.sums.size() > 4) ok = false;
+    for (int i : xu.sums)
+      for (int j = 0; j < P.ops[i].nsrc; ++j) ok = ok && P.tensors[P.ops[i].src[j]].dtype == DT_F16;
     if (!ok || total_kb > 384) continue;
     xu.enabled = true;
     // ticket order = dependency order: all first steps (1x1 up convs, first 3x3 s2 of every down chain), then the second
@@ -741,17 +769,22 @@ void plan_xunits(HrnetPlan& P) {
     // stands for the launch and waits for everything any member waits for
     int first = *std::min_element(xu.ops.begin(), xu.ops.end());
     std::vector<int> deps;
-    for (int i : xu.ops) {
+    std::vector<int> members = xu.ops;
+    members.insert(members.end(), xu.sums.begin(), xu.sums.end());      // the sums run as tickets of the same kernel
+    for (int i : members) {
       P.ops[i].stream = 0;
       for (int dpi : P.ops[i].deps)
         if (P.ops[dpi].xunit != (int)x && std::find(deps.begin(), deps.end(), dpi) == deps.end()) deps.push_back(dpi);
     }
     P.ops[first].deps = deps;
     int pos = 1;
-    for (int i : xu.ops) P.ops[i].xpos = i == first ? 0 : pos++;
+    for (int i : members) P.ops[i].xpos = i == first ? 0 : pos++;
   }
   for (size_t x = 0; x < P.xunits.size(); ++x)
-    if (!P.xunits[x].enabled) for (int i : P.xunits[x].ops) { P.ops[i].xunit = -1; P.ops[i].xpos = 0; }
+    if (!P.xunits[x].enabled) {
+      for (int i : P.xunits[x].ops) { P.ops[i].xunit = -1; P.ops[i].xpos = 0; }
+      for (int i : P.xunits[x].sums) { P.ops[i].xunit = -1; P.ops[i].xpos = 0; }
+    }
   if (cur > begin) {
     if (P.sync_bytes == 0) P.sync_off = begin;
     P.sync_bytes = cur - P.sync_off;
@@ -1114,7 +1147,7 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     if (!first_chain) o << ",";
     first_chain = false;
     o << "{\"module\":" << ch.module << ",\"branch\":" << ch.branch << ",\"patch\":" << (ch.patch ? 1 : 0) << ",\"smem\":" << ch.smem
-      << ",\"share_permille\":" << ch.share << ",\"grid\":" << ch.grid << ",\"m2\":" << ch.m2 << ",\"stages\":" << ch.stages << ",\"flag_stride\":" << ch.flag_stride << ",\"ctrl_off\":" << ch.ctrl_off
+      << ",\"share_permille\":" << ch.share << ",\"grid\":" << ch.grid << ",\"m2\":" << ch.m2 << ",\"pair\":" << (ch.pair ? 1 : 0) << ",\"stages\":" << ch.stages << ",\"flag_stride\":" << ch.flag_stride << ",\"ctrl_off\":" << ch.ctrl_off
       << ",\"flags_off\":" << ch.flags_off << ",\"ops\":[";
     for (size_t k = 0; k < ch.ops.size(); ++k) o << (k ? "," : "") << ch.ops[k];
     o << "]}";
@@ -1127,6 +1160,8 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     first_x = false;
     o << "{\"module\":" << xu.module << ",\"smem\":" << xu.smem << ",\"stages\":" << xu.stages << ",\"ops\":[";
     for (size_t k = 0; k < xu.ops.size(); ++k) o << (k ? "," : "") << xu.ops[k];
+    o << "],\"sums\":[";
+    for (size_t k = 0; k < xu.sums.size(); ++k) o << (k ? "," : "") << xu.sums[k];
     o << "]}";
   }
   o << "],\"sync_off\":" << P->sync_off << ",\"sync_bytes\":" << P->sync_bytes << "}";
@@ -1199,6 +1234,23 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
         } else {
           ch.imaps.a[k] = op.tmA;
           ch.imaps.b[k] = op.tmB;
+          if (ch.pair) {      // each CTA of a pair loads half of the weight tile's rows
+            const ParamInfo& pi = P->params[op.param];
+            rc = encode_weights(&ch.imaps.b[k], P->wbase + pi.w_offset, op.cout, op.k * op.k * op.cin, op.tc.kc, op.tc.n_tile / 2);
+            if (rc) return rc;
+          }
+        }
+      }
+      {   // BN constants of the member convs -> host (the caller's weight buffer must hold the packed weights now)
+        const int cout = P->ops[ch.ops[0]].cout;
+        ch.sb.assign(ch.ops.size() * (size_t)cout * 2, 0.f);
+        std::vector<float> tmp((size_t)cout * 2);
+        for (size_t k = 0; k < ch.ops.size(); ++k) {
+          const ParamInfo& pi = P->params[P->ops[ch.ops[k]].param];
+          if (cudaMemcpy(tmp.data(), P->wbase + pi.scale_offset, (size_t)cout * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+              cudaMemcpy(tmp.data() + cout, P->wbase + pi.bias_offset, (size_t)cout * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(HRNET_E_CUDA, "cudaMemcpy(BN constants of a branch chain)");
+          for (int c = 0; c < cout; ++c) { ch.sb[(k * cout + c) * 2] = tmp[c]; ch.sb[(k * cout + c) * 2 + 1] = tmp[cout + c]; }
         }
       }
       for (size_t k = ch.ops.size(); k < (size_t)kChainMaxConv; ++k) {   // unused slots: any valid descriptor
@@ -1216,7 +1268,11 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
         if (ch.share > P->chains[big].share) big = c;
       }
       P->chains[big].grid = std::max(1, P->chains[big].grid + left);    // rounding remainder to the largest chain
-      for (int c : kv.second) P->chains[c].grid = std::min(P->chains[c].grid, cap);
+      for (int c : kv.second) {
+        ChainInfo& ch = P->chains[c];
+        ch.grid = std::min(ch.grid, cap);
+        if (ch.pair) ch.grid = std::max(2, ch.grid / 2 * 2);
+      }
     }
     for (auto& xu : P->xunits) {
       if (!xu.enabled) continue;
@@ -1406,13 +1462,27 @@ int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st, long 
       cv[k].pad_ = 0;
     }
   };
+  auto fill_sb = [&](auto& sb) {
+    const int cout = o0.cout;
+    for (size_t k = 0; k < ch.ops.size(); ++k)
+      for (int c = 0; c < cout; ++c) sb[k][c] = make_float2(ch.sb[(k * cout + c) * 2], ch.sb[(k * cout + c) * 2 + 1]);
+  };
   if (ch.patch) {
-    ChainPatchParams p{};
+    static thread_local ChainPatchParams p;      // (the parameter blocks are tens of KB: keep them off the stack)
+    p = ChainPatchParams{};
     p.nconv = (int)ch.ops.size();
+    fill_sb(p.sb);
     p.pp = o0.pp;
     p.pp.N = n; p.pp.total_tiles = n * p.pp.tiles_w * p.pp.tiles_h;
+    if (8 * p.pp.Cout <= 512 && P->desc.tune[HRNET_TUNE_PATCH_NACC] == 0) {      // eight accumulator buffers (conv_chain.cu)
+      p.pp.nacc = 8; p.pp.nacc_log2 = 3;
+      int cols = 32;
+      while (cols < 8 * p.pp.Cout) cols *= 2;
+      p.pp.tmem_cols = cols;
+    }
     p.unit_stride = ch.flag_stride;
     p.chunk = p.pp.tiles_w;   // one ticket = one tile row
+    p.skip = P->desc.tune[HRNET_TUNE_CHAIN_SKIP];
     p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
     p.ctrl = (unsigned*)(P->abase + ch.ctrl_off);
     p.counters = (unsigned*)(P->abase + ch.flags_off);
@@ -1423,20 +1493,27 @@ int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st, long 
     CK(launch_chain_patch(ch.pmaps, p, ch.smem, grid, st));
   } else {
     const ConvTcParams t = fill_tc_params(P, o0, n);
-    ChainIgemmParams p{};
+    static thread_local ChainIgemmParams p;
+    p = ChainIgemmParams{};
     p.nconv = (int)ch.ops.size();
+    fill_sb(p.sb);
     p.M_total = t.M_total; p.OH = t.OH; p.OW = t.OW; p.OHW = t.OHW; p.C = o0.cin;
     p.cpt = t.cpt; p.nkb = t.nkb; p.bps = t.bps; p.n_tile = t.n_tile; p.n_tiles = t.n_tiles; p.m_tiles = t.m_tiles;
     p.stages = ch.stages; p.tmem_cols = t.tmem_cols; p.a_blk_bytes = t.a_blk_bytes; p.b_blk_bytes = t.b_blk_bytes;
     p.pdl = t.pdl;
-    p.m2 = ch.m2; p.units = (p.m_tiles + ch.m2 - 1) / ch.m2;
+    p.m2 = ch.m2; p.pair = ch.pair ? 1 : 0;
+    p.skip = P->desc.tune[HRNET_TUNE_CHAIN_SKIP];
+    const int tpu = ch.pair ? 2 : ch.m2;
+    p.units = (p.m_tiles + tpu - 1) / tpu;
+    if (ch.pair) p.b_blk_bytes = (int)align_up((size_t)(t.n_tile / 2) * t.kc * 2, 1024);
     p.unit_stride = ch.flag_stride;
     p.ctrl = (unsigned*)(P->abase + ch.ctrl_off);
     p.counters = (unsigned*)(P->abase + ch.flags_off);
     p.dbg = dbg;
     fill_convs(p.conv);
     if (p.m_tiles * p.n_tiles == 0) return 0;
-    grid = std::max(1, std::min(grid, p.units));
+    grid = std::max(1, std::min(grid, p.units * (ch.pair ? 2 : 1)));
+    if (ch.pair) grid = std::max(2, grid / 2 * 2);
     CK(launch_chain_igemm(ch.imaps, p, ch.smem, grid, st));
   }
   return 0;
@@ -1453,7 +1530,7 @@ int launch_xunit_op(HrnetPlan* P, int x, int n, cudaStream_t st, long long* dbg 
   p.ctrl = (unsigned*)(P->abase + xu.ctrl_off);
   p.counters = (unsigned*)(P->abase + xu.counters_off);
   p.dbg = dbg;
-  int ticket = 0, kb = 0;
+  int kb = 0;
   for (int k = 0; k < p.nops; ++k) {
     const Op& op = P->ops[xu.ops[k]];
     const ConvTcParams t = fill_tc_params(P, op, n);
@@ -1467,11 +1544,42 @@ int launch_xunit_op(HrnetPlan* P, int x, int n, cudaStream_t st, long long* dbg 
     for (int j = 0; j < p.nops; ++j)
       if (P->ops[xu.ops[j]].out == op.in) { o.dep = j; }
     o.kb0 = kb; kb += o.nkb;
-    o.ticket0 = ticket; ticket += o.m_tiles;
     o.scale = t.scale; o.bias = t.bias; o.out = (__half*)t.out;
   }
   for (int k = 0; k < p.nops; ++k)
     if (p.op[k].dep >= 0) p.op[k].dep_need = p.op[p.op[k].dep].m_tiles * p.op[p.op[k].dep].n_tiles;
+  // the sums: one XSum per OP_FUSE of the module, its level = the deepest down-chain step it reads
+  p.nsums = (int)xu.sums.size();
+  int sum_level[4] = {-1, -1, -1, -1};
+  for (int q = 0; q < p.nsums; ++q) {
+    const Op& f = P->ops[xu.sums[q]];
+    const TensorInfo& to = P->tensors[f.out];
+    XSum& sm = p.sum[q];
+    sm.H = to.H; sm.W = to.W; sm.C = to.C; sm.nsrc = f.nsrc; sm.relu = f.relu;
+    sm.npix = (long long)n * to.H * to.W;
+    sm.nchunks = (int)((sm.npix + kXSumChunk - 1) / kXSumChunk);
+    sm.out = (__half*)(P->abase + to.offset);
+    for (int j = 0; j < 4; ++j) { sm.shift[j] = 0; sm.dep[j] = -1; sm.dep_need[j] = 0; sm.src[j] = nullptr; }
+    for (int j = 0; j < f.nsrc; ++j) {
+      sm.src[j] = (const __half*)(P->abase + P->tensors[f.src[j]].offset);
+      sm.shift[j] = f.shift[j];
+      for (int k = 0; k < p.nops; ++k)
+        if (P->ops[xu.ops[k]].out == f.src[j]) {
+          sm.dep[j] = k; sm.dep_need[j] = p.op[k].m_tiles * p.op[k].n_tiles;
+          sum_level[q] = std::max(sum_level[q], P->ops[xu.ops[k]].xlevel);
+        }
+    }
+  }
+  // ticket sequence: convs of level L (plan order), then the sums whose deepest source is level L
+  int ticket = 0;
+  for (int q = 0; q < p.nsums; ++q)
+    if (sum_level[q] < 0) { p.sum[q].ticket0 = ticket; ticket += p.sum[q].nchunks; }
+  for (int L = 0; L < 8; ++L) {
+    for (int k = 0; k < p.nops; ++k)
+      if (P->ops[xu.ops[k]].xlevel == L) { p.op[k].ticket0 = ticket; ticket += p.op[k].m_tiles; }
+    for (int q = 0; q < p.nsums; ++q)
+      if (sum_level[q] == L) { p.sum[q].ticket0 = ticket; ticket += p.sum[q].nchunks; }
+  }
   p.total_tickets = ticket; p.total_kb = kb;
   if (ticket == 0) return 0;
   CK(launch_xunit(xu.maps, p, xu.smem, std::min(P->num_sms, ticket), st));
@@ -1614,6 +1722,8 @@ int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, flo
       int rc = launch_xunit_op(P, op.xunit, n, st);
       if (rc) return rc;
       for (int m : xu.ops)
+        if (P->ops[m].needs_event) CK(cudaEventRecord(P->events[m], st));
+      for (int m : xu.sums)
         if (P->ops[m].needs_event) CK(cudaEventRecord(P->events[m], st));
       continue;
     }
@@ -1857,15 +1967,25 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
         if (!xu.enabled) continue;
         float total = 0.f;
         CK(cudaEventElapsedTime(&total, xunit_ev[2 * x], xunit_ev[2 * x + 1]));
+        // split by a simple cost model: convs by FLOPs at 500 TFLOP/s, sums by bytes at 3 TB/s
         double fsum = 0;
         std::vector<double> fl;
-        for (int m : xu.ops) {
+        std::vector<int> mem = xu.ops;
+        mem.insert(mem.end(), xu.sums.begin(), xu.sums.end());
+        for (int m : mem) {
           const Op& o = P->ops[m];
           const TensorInfo& to = P->tensors[o.out];
-          fl.push_back((double)to.H * to.W * o.k * o.k * o.cin * o.cout);
-          fsum += fl.back();
+          double c;
+          if (o.kind == OP_CONV) c = 2.0 * to.H * to.W * o.k * o.k * o.cin * o.cout / 500e12;
+          else {
+            double bytes = 2.0 * to.H * to.W * to.C;
+            for (int j = 0; j < o.nsrc; ++j) { const TensorInfo& ts = P->tensors[o.src[j]]; bytes += 2.0 * ts.H * ts.W * ts.C; }
+            c = bytes / 3e12;
+          }
+          fl.push_back(c);
+          fsum += c;
         }
-        for (size_t k = 0; k < xu.ops.size(); ++k) t[xu.ops[k]][it] = (float)(total * fl[k] / fsum);
+        for (size_t k = 0; k < mem.size(); ++k) t[mem[k]][it] = (float)(total * fl[k] / fsum);
       }
       for (size_t gi = 0; gi < spans.size(); ++gi) {   // one kernel for the whole span: split its time by estimated cost
         float total = 0.f;
@@ -1907,7 +2027,7 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
           for (double& v : avg) v /= std::max(1, act);
           fprintf(stderr, "[chain-dbg] %s %s grid=%d (ctas seen %d) %.1f us | per CTA: tiles %.1f, cta clk %.0f, sched: ticket %.0f dep-wait %.0f "
                   "ring %.0f | producer: ring-wait %.0f slot-wait %.0f | epi(wg0) wait_acc %.0f work %.0f | mma0 wait_full %.0f wait_tmem %.0f "
-                  "wait_weights %.0f\n",
+                  "wait_weights / ring %.0f\n",
                   P->ops[ch.ops[0]].name.c_str(), ch.patch ? "patch" : "im2col", g, act, ms * 1000.f, avg[1], avg[2], avg[8], avg[0], avg[9],
                   avg[10], avg[11], avg[3], avg[4], avg[5], avg[6], avg[7]);
           cudaEventDestroy(a); cudaEventDestroy(b);

@@ -28,6 +28,19 @@ def fwd_ms(eng, reps=10):
 
 args = sys.argv[1:]
 base_tune = {_lib.TUNE_CHAIN_M2: 1} if "m1" in args else {}
+if "pair" in args:
+    base_tune[_lib.TUNE_CHAIN_PAIR] = 2
+    print("im2col chains: CTA pairs (cta_group::2)")
+for a in args:
+    if a.startswith("t") and "=" in a:          # any knob: t<index>=<value>
+        base_tune[int(a[1:a.index("=")])] = int(a[a.index("=") + 1:])
+        print("tune", a)
+    if a.startswith("stages"):
+        base_tune[_lib.TUNE_CHAIN_STAGES] = int(a[6:])
+        print("im2col chains:", a)
+    if a.startswith("skip"):
+        base_tune[_lib.TUNE_CHAIN_SKIP] = int(a[4:])
+        print("im2col chains: epilogue experiment", a, "(results invalid)")
 if "m1" in args:
     print("im2col chains: one M-tile per ticket")
 if "debug" in args:
@@ -53,9 +66,10 @@ for sp in splits:
     print(f"split {sp}: {fwd_ms(eng):.3f} ms/forward   grids (module, branch, ctas): {grids}", flush=True)
     eng.close()
 if "nochain" in args:
-    for name, fl in (("chains + exchange units (default)", 0), ("chains, per-conv exchange convs", _lib.FLAG_NO_XUNIT),
-                     ("exchange units, per-conv branch convs", _lib.FLAG_NO_CHAIN), ("every conv its own launch", _lib.FLAG_NO_CHAIN | _lib.FLAG_NO_XUNIT)):
-        eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), flags=fl, tune=base_tune)
+    for name, fl, tn in (("chains (default)", 0, {}), ("chains + exchange-unit kernel (convs)", 0, {_lib.TUNE_XUNIT: 1}),
+                         ("chains + exchange-unit kernel (convs + sums)", 0, {_lib.TUNE_XUNIT: 2}),
+                         ("every conv its own launch", _lib.FLAG_NO_CHAIN, {})):
+        eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), flags=fl, tune={**base_tune, **tn})
         eng.load_state_dict(sd)
         print(f"{name}: {fwd_ms(eng):.3f} ms/forward ({eng.launch_count} launches)", flush=True)
         eng.close()

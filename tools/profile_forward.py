@@ -15,8 +15,9 @@ from simple_hrnet_b200 import B200Engine, _lib  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+tune = {int(k): int(v) for k, v in (kv.split("=") for kv in sys.argv[3].split(","))} if len(sys.argv) > 3 else None   # "20=2,18=1"
 sd = O.make_state_dict(O.hrnet_param_spec(48, 17), seed=0, bn="default")
-eng = B200Engine("hrnet", 48, 17, (384, 288), n, torch.device("cuda:0"), flags=flags)
+eng = B200Engine("hrnet", 48, 17, (384, 288), n, torch.device("cuda:0"), flags=flags, tune=tune)
 eng.load_state_dict(sd)
 x = torch.randn(n, 3, 384, 288, generator=torch.Generator().manual_seed(1)).cuda()
 for _ in range(2):
