@@ -76,9 +76,10 @@ extern "C" {
 #define HRNET_TUNE_GRID_CAP 17      /* single-op entry points: cap on the persistent grid (experiments)              */
 #define HRNET_TUNE_CHAIN_M2 18       /* im2col chains: 2 = two M-tiles per ticket sharing every weight k-block (30 % fewer TMA
                                       bytes, no accumulator double buffering); default one tile per ticket             */
-#define HRNET_TUNE_XUNIT 19          /* exchange-unit kernel (conv_xunit.cu), opt-in: 1 = the convs of a StageModule's fuse layers as
-                                      one ticket-scheduled kernel, 2 = its sums too (as sum tickets).  Bit-identical to the
-                                      default (one launch per conv, fuse_sum_kernel); measured no faster inside the forward  */
+#define HRNET_TUNE_XUNIT 19          /* exchange-unit kernel (conv_xunit.cu: several fuse-layer convs as one ticket-scheduled kernel).
+                                      0 / 1 = one unit per StageModule and SOURCE branch, launched behind that branch's chain
+                                      (default); 2 = one unit per module that also executes the sums as sum tickets (measured
+                                      slower); 3 = off: every fuse-layer conv its own launch.  Bit-identical results.          */
 #define HRNET_TUNE_CHAIN_PAIR 20     /* im2col chains on CTA pairs (tcgen05 cta_group::2: a unit = two M-tiles, each CTA stages half of
                                       the weight tile): 2 = on                                                          */
 #define HRNET_TUNE_CHAIN_SKIP 21     /* experiments only, RESULTS INVALID: the im2col chain's epilogue does 1 = nothing, 2 = only its

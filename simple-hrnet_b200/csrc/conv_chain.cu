@@ -248,7 +248,7 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const __gri
           const int acc = it & 1;
           ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), (uint32_t)((it >> 1) & 1) ^ 1u);
           ptx::tc_fence_after_sync();
-          lean_issue_tile<4, kPair>(lp, tmem_base + (uint32_t)(acc * p.n_tile), idesc, p.nkb, p.bps);
+          lean_issue_tile<4, kPair>(lp, tmem_base + (uint32_t)(acc * p.n_tile), idesc, p.nkb, p.bps, p.cpt);
           if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
           else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->tmem_full[acc]), (uint16_t)3);
         }
@@ -732,7 +732,20 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const __gri
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[acc]), acc_phase);
       if (cp.dbg) { const long long t = clock64(); dbg_wait += t - tq; tq = t; }
       ptx::tc_fence_after_sync();
-      if (cp.skip != 1)      // (skip == 1: experiment, no epilogue work -- results invalid)
+      if (cp.skip == 2) {            // experiment (results invalid): accumulator loads only
+        uint32_t x = 0;
+        for (int c = 0; c < e.ncols; c += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout + c), v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x ^= v[i];
+        }
+        if (x == 0x12345679u && e.valid) reinterpret_cast<__half*>(e.out)[e.row_off] = __float2half(0.f);
+      } else if (cp.skip == 3) {     // experiment (results invalid): residual loads and output stores only
+        if (e.valid)
+          for (int j = 0; j < 4; ++j) if (16 * j < e.ncols) stg256(reinterpret_cast<__half*>(e.out) + e.row_off + 16 * j, rres[j]);
+      } else if (cp.skip != 1)       // (skip == 1: experiment, no epilogue work -- results invalid)
         chain_store_row_lean_c(e, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Cout), rres, cp.sb[k]);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[acc]));

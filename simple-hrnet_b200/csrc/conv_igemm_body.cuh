@@ -72,8 +72,7 @@ __device__ __forceinline__ void issue_k16(uint32_t d_tmem, uint64_t adesc, uint6
 // below spends ~750 clk per k-block on constant-bank reads, descriptor arithmetic and bookkeeping around four MMAs
 // that need 384 clk of tensor time (N = 192); tools/exp/mma_tma_mix.cu runs the same loads and MMAs at 400-450 clk per
 // k-block behind a minimal loop (profiles/r02_exp_mma_tma_mix.log, r02_s14_lean_issue_loop.log: C = 192 chain 20.4 k ->
-// 15.0 k clk per tile).  Usable whenever every k-block has the same number NK of K16 steps (Cin % 64 == 0, or one
-// block per tap) and no debug timers are wanted.  Per stage: the next stage's barrier is probed first (its ~150 clk
+// 15.0 k clk per tile).  Used whenever no debug timers are wanted.  Per stage: the next stage's barrier is probed first (its ~150 clk
 // latency overlaps the MMAs), the descriptors of a stage differ from the previous one's by constants, one commit.
 struct LeanPipe {
   uint32_t full0, empty0;      // `full` / `empty` barriers of stage 0 of this issuer's ring
@@ -84,10 +83,12 @@ struct LeanPipe {
   int stage; uint32_t phase; bool ready; uint32_t enc;   // running state
   __device__ __forceinline__ void reset() { stage = 0; phase = 0u; ready = false; enc = enc0; }
 };
-template <int NK, bool kPair>
-__device__ __forceinline__ void lean_issue_tile(LeanPipe& s, uint32_t d_tmem, uint32_t idesc, int nkb, int bps) {
+// NKT = K16 steps of the LAST k-block of every tap (Cin % 64 real channels; all other k-blocks have four); cpt = k-blocks
+// per tap.  cpt == 1: every block is a last block.
+template <int NKT, bool kPair>
+__device__ __forceinline__ void lean_issue_tile(LeanPipe& s, uint32_t d_tmem, uint32_t idesc, int nkb, int bps, int cpt) {
   const uint64_t desc_hi = ptx::umma_desc_kmajor(0u, 128u, 1024u);        // everything but the start address
-  int kb = 0;
+  int kb = 0, cblk = 0;
 #pragma unroll 1
   while (kb < nkb) {
     if (!s.ready) ptx::mbar_wait(s.full0 + 8u * (uint32_t)s.stage, s.phase);
@@ -97,21 +98,30 @@ __device__ __forceinline__ void lean_issue_tile(LeanPipe& s, uint32_t d_tmem, ui
     ++s.stage; s.enc += s.enc_stage;
     if (s.stage == s.nst) { s.stage = 0; s.phase ^= 1u; s.enc = s.enc0; }
     s.ready = ptx::mbar_test_wait(s.full0 + 8u * (uint32_t)s.stage, s.phase);   // answer needed one stage later
-    issue_k16<NK, kPair>(d_tmem, desc_hi | (uint64_t)a_enc, desc_hi | (uint64_t)(a_enc + s.enc_b), idesc, (uint32_t)(kb != 0));
-    if (bps == 2 && kb + 1 < nkb)
-      issue_k16<NK, kPair>(d_tmem, desc_hi | (uint64_t)(a_enc + s.enc_ablk), desc_hi | (uint64_t)(a_enc + s.enc_b + s.enc_bblk), idesc, 1u);
+    {
+      const uint64_t ad = desc_hi | (uint64_t)a_enc, bd = desc_hi | (uint64_t)(a_enc + s.enc_b);
+      if (NKT == 4 || cblk != cpt - 1) issue_k16<4, kPair>(d_tmem, ad, bd, idesc, (uint32_t)(kb != 0));
+      else issue_k16<NKT, kPair>(d_tmem, ad, bd, idesc, (uint32_t)(kb != 0));
+      cblk = cblk + 1 == cpt ? 0 : cblk + 1;
+    }
+    if (bps == 2 && kb + 1 < nkb) {
+      const uint64_t ad = desc_hi | (uint64_t)(a_enc + s.enc_ablk), bd = desc_hi | (uint64_t)(a_enc + s.enc_b + s.enc_bblk);
+      if (NKT == 4 || cblk != cpt - 1) issue_k16<4, kPair>(d_tmem, ad, bd, idesc, 1u);
+      else issue_k16<NKT, kPair>(d_tmem, ad, bd, idesc, 1u);
+      cblk = cblk + 1 == cpt ? 0 : cblk + 1;
+    }
     if constexpr (!kPair) ptx::mma_commit(cur_empty);
     else ptx::mma_commit_2cta_mc(cur_empty, (uint16_t)3);
     kb += bps;
   }
 }
 template <bool kPair>
-__device__ __forceinline__ void lean_issue_tile_nk(int nk, LeanPipe& s, uint32_t d_tmem, uint32_t idesc, int nkb, int bps) {
-  switch (nk) {     // once per tile, not per k-block
-    case 4: lean_issue_tile<4, kPair>(s, d_tmem, idesc, nkb, bps); break;
-    case 3: lean_issue_tile<3, kPair>(s, d_tmem, idesc, nkb, bps); break;
-    case 2: lean_issue_tile<2, kPair>(s, d_tmem, idesc, nkb, bps); break;
-    default: lean_issue_tile<1, kPair>(s, d_tmem, idesc, nkb, bps); break;
+__device__ __forceinline__ void lean_issue_tile_nk(int nk_tail, LeanPipe& s, uint32_t d_tmem, uint32_t idesc, int nkb, int bps, int cpt) {
+  switch (nk_tail) {     // once per tile, not per k-block
+    case 4: lean_issue_tile<4, kPair>(s, d_tmem, idesc, nkb, bps, cpt); break;
+    case 3: lean_issue_tile<3, kPair>(s, d_tmem, idesc, nkb, bps, cpt); break;
+    case 2: lean_issue_tile<2, kPair>(s, d_tmem, idesc, nkb, bps, cpt); break;
+    default: lean_issue_tile<1, kPair>(s, d_tmem, idesc, nkb, bps, cpt); break;
   }
 }
 
@@ -295,9 +305,9 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
       bool first_stage = true;
       const bool dbg_on = p.dbg != nullptr && mw == 0;
       long long dbg_wfull = 0, dbg_wtm = 0, dbg_mma = 0, dbg_t0 = dbg_on ? clock64() : 0;
-      // every k-block has the same number of K16 steps: the lean loop (see LeanPipe)
-      const int lean_nk = p.cpt == 1 ? (p.Cin + 15) / 16 : ((p.Cin & 63) == 0 ? 4 : 0);
-      if (lean_nk != 0 && p.dbg == nullptr && p.bps <= 2) {
+      // the lean loop (see LeanPipe) unless debug timers are wanted
+      const int lean_nk = (ctail + 15) / 16;          // K16 steps of the last k-block of a tap
+      if (p.dbg == nullptr && p.bps <= 2) {
         LeanPipe lp;
         lp.full0 = ptx::smem_u32(&bars->full[sbase]); lp.empty0 = ptx::smem_u32(&bars->empty[sbase]);
         lp.enc0 = ((smem_base + (uint32_t)(sbase * stage_bytes)) & 0x3FFFFu) >> 4;
@@ -308,7 +318,7 @@ __device__ __forceinline__ void conv_igemm_body(const CUtensorMap& tmA, const CU
           const int acc = it & 1;
           ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), (uint32_t)((it >> 1) & 1) ^ 1u);
           ptx::tc_fence_after_sync();
-          lean_issue_tile_nk<kPair>(lean_nk, lp, tmem_base + (uint32_t)(acc * p.n_tile), idesc, p.nkb, p.bps);
+          lean_issue_tile_nk<kPair>(lean_nk, lp, tmem_base + (uint32_t)(acc * p.n_tile), idesc, p.nkb, p.bps, p.cpt);
           if constexpr (!kPair) ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
           else ptx::mma_commit_2cta_mc(ptx::smem_u32(&bars->tmem_full[acc]), mc_mask);
         }

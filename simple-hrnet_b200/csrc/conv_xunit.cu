@@ -117,6 +117,13 @@ struct __align__(8) XUnitBars {
   uint32_t kb_tab[kXMaxKb];
 };
 
+// (scale, bias) of absolute output channel i of one member conv, read straight from the parameter block
+struct XSb {
+  const XUnitParams& p;
+  int off;
+  __device__ __forceinline__ float2 operator[](int i) const { return p.sb[off + i]; }
+};
+
 __global__ void __launch_bounds__(kXThreads, 1)
 conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant__ XUnitParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -263,9 +270,13 @@ conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant_
     // ===================================================================== MMA issuer
     if (ptx::elect_one()) {
       RingReader rr; rr.init(&bars->ring);
-      int stage = 0;
-      uint32_t phase = 0;
-      bool ready = false;
+      // lean issue loop (LeanPipe, conv_igemm_body.cuh): one k-block per stage, per-op k-block count / channel tail
+      LeanPipe lp;
+      lp.full0 = ptx::smem_u32(&bars->full[0]); lp.empty0 = ptx::smem_u32(&bars->empty[0]);
+      lp.enc0 = (smem_base & 0x3FFFFu) >> 4;
+      lp.enc_stage = (uint32_t)stage_bytes >> 4; lp.enc_b = (uint32_t)p.a_blk_bytes >> 4;
+      lp.enc_ablk = 0u; lp.enc_bblk = 0u;
+      lp.nst = p.stages; lp.reset();
       for (int it = 0;;) {
         const uint32_t info = rr.next();
         if (info == kChainDone) break;
@@ -274,34 +285,9 @@ conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant_
         const uint32_t idesc = ptx::umma_idesc_f16(kTileM, op.n_tile);
         const int ctail = op.Cin - (op.cpt - 1) * kKC;
         const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        ptx::mbar_wait(ptx::smem_u32(&bars->tmem_empty[acc]), (uint32_t)((it >> 1) & 1) ^ 1u);
         ptx::tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
-        int cblk = 0;
-        for (int kb = 0; kb < op.nkb; ++kb) {
-          if (!ready) ptx::mbar_wait(ptx::smem_u32(&bars->full[stage]), phase);
-          ptx::tc_fence_after_sync();
-          const uint32_t a_src = smem_base + (uint32_t)(stage * stage_bytes);
-          const uint32_t b_src = a_src + (uint32_t)p.a_blk_bytes;
-          int nstage = stage + 1;
-          uint32_t nphase = phase;
-          if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
-          const bool nready = ptx::mbar_test_wait(ptx::smem_u32(&bars->full[nstage]), nphase);
-          const int nk = (cblk == op.cpt - 1 ? ctail : kKC) / 16;
-          cblk = cblk + 1 == op.cpt ? 0 : cblk + 1;
-          const uint64_t adesc = ptx::umma_desc_kmajor(a_src, 128u, 1024u);
-          const uint64_t bdesc = ptx::umma_desc_kmajor(b_src, 128u, 1024u);
-          const uint32_t first = (uint32_t)(kb != 0);
-          switch (nk) {
-            case 4: issue_k16<4, false>(d_tmem, adesc, bdesc, idesc, first); break;
-            case 3: issue_k16<3, false>(d_tmem, adesc, bdesc, idesc, first); break;
-            case 2: issue_k16<2, false>(d_tmem, adesc, bdesc, idesc, first); break;
-            default: issue_k16<1, false>(d_tmem, adesc, bdesc, idesc, first); break;
-          }
-          ptx::mma_commit(ptx::smem_u32(&bars->empty[stage]));
-          stage = nstage; phase = nphase; ready = nready;
-        }
+        lean_issue_tile_nk<false>((ctail + 15) / 16, lp, tmem_base + (uint32_t)acc * acc_stride, idesc, op.nkb, 1, op.cpt);
         ptx::mma_commit(ptx::smem_u32(&bars->tmem_full[acc]));
         ++it;
       }
@@ -346,7 +332,7 @@ conv_xunit_kernel(const __grid_constant__ XUnitMaps maps, const __grid_constant_
         for (int i = 0; i < 8; ++i) rres[j].w[i] = 0u;
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[g]), acc_phase);
       ptx::tc_fence_after_sync();
-      chain_store_row(rres, e, t_row);
+      chain_store_row_c(rres, e, t_row, XSb{p, op.sb_off});      // BN constants from the kernel parameters (LDC)
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(ptx::smem_u32(&bars->tmem_empty[g]));
       pend.set(p.counters + o, false, false);

@@ -178,6 +178,7 @@ cudaError_t conv_chain_set_attributes(int max_smem);
 // persistent kernel: tickets = M-tiles of the member convs in dependency order, a conv of a down-chain starts when its
 // producer conv is complete.
 constexpr int kXMaxOps = 16;
+constexpr int kXMaxSb = 2560;      // output channels of all member convs together (W48 stage 4: 2,400)
 struct XOp {
   int M_total, OH, OW, OHW;      // output geometry (flattened NHWC rows)
   int ksize, stride, pad;
@@ -187,6 +188,8 @@ struct XOp {
   int dep, dep_need;             // producer op within the unit (-1: a module input) and its tile count
   int kb0;                       // first entry of this op in the k-block table
   int ticket0;                   // first ticket (one ticket = one M-tile, all of its N-tiles)
+  int sb_off;                    // first (scale, bias) pair of this op in XUnitParams::sb
+  int pad_;
   const float* scale;
   const float* bias;
   __half* out;
@@ -211,6 +214,7 @@ struct XUnitParams {
   unsigned* counters;            // [nops] finished tiles per op
   long long* dbg;
   XOp op[kXMaxOps];
+  float2 sb[kXMaxSb];            // BN (scale, bias) of every member conv's output channels: constants (LDC) for the epilogue
 };
 struct XUnitMaps { CUtensorMap a[kXMaxOps], b[kXMaxOps]; };
 cudaError_t launch_xunit(const XUnitMaps& maps, const XUnitParams& p, int smem_bytes, int grid, cudaStream_t st);

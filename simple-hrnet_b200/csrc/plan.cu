@@ -61,6 +61,8 @@ struct ChainInfo {
 
 // One exchange unit (conv_xunit.cu): every conv of a StageModule's fuse layers issued as one persistent kernel.
 struct XUnitInfo {
+  int stream = 0;                  // the launch runs on this stream (per-source units: the source branch's, right behind its chain)
+  std::vector<float> sb;           // host copy of the member convs' BN (scale, bias) pairs, in member order (hrnet_plan_bind)
   std::vector<int> sums;           // the module's exchange sums (OP_FUSE ops), executed as sum tickets of the same kernel
   std::vector<int> ops;            // member convs in ticket (dependency) order
   int module = -1;
@@ -464,12 +466,18 @@ int build_hrnet(HrnetPlan& P) {
       for (int i = 0; i < S; ++i) ys[i] = cur[i];
     }
     std::vector<int> outs(O);
+    // Exchange units.  Default / HRNET_TUNE_XUNIT = 1: ONE UNIT PER SOURCE BRANCH j -- the 1x1 up convs and the 3x3 s2 down
+    // chains that read branch j's output -- launched on branch j's stream right behind its chain: it starts when THAT chain
+    // is done and runs under the tails of the others (a unit of all 16 convs had to wait for the slowest chain, which ate
+    // what it saved: profiles/r02_s7_*.log, r02_s21_*.log).  HRNET_TUNE_XUNIT = 2: one unit per module that also executes
+    // the sums (measured slower, kept as an experiment).
+    const bool per_source = P.desc.tune[HRNET_TUNE_XUNIT] != 2;
     const int xid = (int)P.xunits.size();
-    { XUnitInfo xu; xu.module = module_idx; P.xunits.push_back(xu); }
-    auto mark_x = [&](int level) {
+    for (int j = 0; j < (per_source ? S : 1); ++j) { XUnitInfo xu; xu.module = module_idx; xu.stream = per_source ? j : 0; P.xunits.push_back(xu); }
+    auto mark_x = [&](int level, int src_branch) {
       Op& o = P.ops.back();
-      o.xunit = xid; o.xlevel = level;
-      P.xunits[xid].ops.push_back((int)P.ops.size() - 1);
+      o.xunit = xid + (per_source ? src_branch : 0); o.xlevel = level;
+      P.xunits[o.xunit].ops.push_back((int)P.ops.size() - 1);
     };
     for (int i = 0; i < O; ++i) {
       const TensorInfo ti = P.tensors[ys[i]];
@@ -482,7 +490,7 @@ int build_hrnet(HrnetPlan& P) {
         } else if (j > i) {
           // 1x1 conv + BN at the low resolution; the nearest upsample is folded into the fuse read (hrnet.py:30-35)
           f.src[j] = b.conv(p, p + ".0", p + ".1", ys[j], ti.C, 1, 1, false, -1, -1, arena, i, dt_term);
-          mark_x(0);
+          mark_x(0, j);
           f.shift[j] = j - i;
         } else {
           int t = ys[j];
@@ -490,20 +498,22 @@ int build_hrnet(HrnetPlan& P) {
           for (int k = 0; k < i - j - 1; ++k) {
             t = b.conv(p + "." + std::to_string(k), p + "." + std::to_string(k) + ".0", p + "." + std::to_string(k) + ".1",
                        t, cj, 3, 2, true, -1, -1, arena, i);
-            mark_x(k);
+            mark_x(k, j);
           }
           const int k = i - j - 1;
           f.src[j] = b.conv(p + "." + std::to_string(k), p + "." + std::to_string(k) + ".0",
                             p + "." + std::to_string(k) + ".1", t, ti.C, 3, 2, false, -1, -1, arena, i, dt_term);
-          mark_x(k);
+          mark_x(k, j);
           f.shift[j] = 0;
         }
       }
       f.out = b.new_tensor(arena, ti.C, ti.H, ti.W);
       outs[i] = f.out;
       b.push(f);
-      P.ops.back().xunit = xid;
-      P.xunits[xid].sums.push_back((int)P.ops.size() - 1);
+      if (!per_source) {
+        P.ops.back().xunit = xid;
+        P.xunits[xid].sums.push_back((int)P.ops.size() - 1);
+      }
     }
     xs = outs;
     return arena;
@@ -658,7 +668,9 @@ void plan_chains(HrnetPlan& P) {
       ch.smem = o0.patch_smem + (int)(ch.ops.size() - 1) * 2 * o0.cout * 4;   // BN constants of every conv stay in shared memory
       if (ch.smem > kMaxDynSmem) { ch.enabled = false; continue; }
       ch.flag_stride = P.desc.max_batch * o0.pp.tiles_h;             // one counter per row of tiles of an image
-      ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * o0.work;
+      // measured inside the chains (profiles/r02_s19_*.log): 1,973 clk per 128 x 48 x 432 tile (27 MMAs), 4,380 per
+      // 128 x 96 x 864 tile (54 MMAs) -- the L1 data pipe shared by the MMAs' operand reads and the epilogue's accesses
+      ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * k16 * (o0.cout <= 64 ? 73.0 : 81.0);
     } else {
       for (int i : ch.ops) P.ops[i].tc.mma_warps = 1;
       const int n_tiles = o0.cout / o0.tc.n_tile;
@@ -685,7 +697,8 @@ void plan_chains(HrnetPlan& P) {
       }
       ch.flag_stride = (m_tiles + tpu - 1) / tpu;                    // one counter per ticket (tpu M-tiles x n_tiles arrivals)
       // measured inside the per-conv kernels: ~200 clk per K16 step of a 128 x 192 tile (profiles/r01_exp_gridcap_pair_sweep.log)
-      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * ((ch.pair ? 140.0 : 200.0) * o0.tc.n_tile / 192.0);
+      // ... and ~490 clk per 128 x 192 x 64 k-block of the im2col chains (four K16 steps; CTA pairs ~470)
+      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * ((ch.pair ? 118.0 : 123.0) * o0.tc.n_tile / 192.0);
     }
     ch.ctrl_off = cur; cur += 256;
     ch.flags_off = cur; cur += ((size_t)ch.ops.size() * ch.flag_stride * 4 + 255) / 256 * 256;
@@ -728,15 +741,17 @@ void plan_xunits(HrnetPlan& P) {
   // one kernel waits for the slowest chain; sums as tickets (256 epilogue threads per SM) cannot match fuse_sum_kernel's
   // bandwidth (8.80 ms).  profiles/r02_s7_xunit_first_contact.log, r02_s9_xunit_sum_tickets_v2.log
   const uint32_t off_flags = HRNET_FLAG_FORCE_SIMT | HRNET_FLAG_GROUP | HRNET_FLAG_PARTITION | HRNET_FLAG_FUSE_F32;
-  const int mode = P.desc.tune[HRNET_TUNE_XUNIT];
-  const bool want = (mode == 1 || mode == 2) && !(P.desc.flags & off_flags);
+  const int mode = P.desc.tune[HRNET_TUNE_XUNIT];      // 0 / 1: per-source units (default), 2: module units with sum tickets, 3: off
+  const bool want = mode != 3 && !(P.desc.flags & off_flags);
   size_t cur = (P.act_bytes + 255) / 256 * 256;
   const size_t begin = cur;
   for (size_t x = 0; x < P.xunits.size(); ++x) {
     XUnitInfo& xu = P.xunits[x];
     xu.enabled = false;
     bool ok = want && xu.ops.size() >= 2 && (int)xu.ops.size() <= kXMaxOps;
-    int max_nt = 0, total_kb = 0;
+    int max_nt = 0, total_kb = 0, total_cout = 0;
+    for (int i : xu.ops) total_cout += P.ops[i].cout;
+    ok = ok && total_cout <= kXMaxSb;
     for (int i : xu.ops) {
       const Op& o = P.ops[i];
       ok = ok && o.use_tc && !o.use_patch && o.tc.cs == 1 && P.tensors[o.out].dtype == DT_F16 && o.res < 0 && o.pad < 100 &&
@@ -772,7 +787,7 @@ void plan_xunits(HrnetPlan& P) {
     std::vector<int> members = xu.ops;
     members.insert(members.end(), xu.sums.begin(), xu.sums.end());      // the sums run as tickets of the same kernel
     for (int i : members) {
-      P.ops[i].stream = 0;
+      P.ops[i].stream = xu.stream;
       for (int dpi : P.ops[i].deps)
         if (P.ops[dpi].xunit != (int)x && std::find(deps.begin(), deps.end(), dpi) == deps.end()) deps.push_back(dpi);
     }
@@ -1276,6 +1291,16 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
     }
     for (auto& xu : P->xunits) {
       if (!xu.enabled) continue;
+      xu.sb.clear();
+      for (int i : xu.ops) {        // BN constants -> host (they travel as kernel parameters)
+        const Op& op = P->ops[i];
+        const ParamInfo& pi = P->params[op.param];
+        std::vector<float> tmp((size_t)op.cout * 2);
+        if (cudaMemcpy(tmp.data(), P->wbase + pi.scale_offset, (size_t)op.cout * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(tmp.data() + op.cout, P->wbase + pi.bias_offset, (size_t)op.cout * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+          return fail(HRNET_E_CUDA, "cudaMemcpy(BN constants of an exchange unit)");
+        for (int c = 0; c < op.cout; ++c) { xu.sb.push_back(tmp[c]); xu.sb.push_back(tmp[op.cout + c]); }
+      }
       for (size_t k = 0; k < (size_t)kXMaxOps; ++k) {
         const Op& op = P->ops[xu.ops[std::min(k, xu.ops.size() - 1)]];     // unused slots: any valid descriptor
         xu.maps.a[k] = op.tmA;
@@ -1523,18 +1548,21 @@ int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st, long 
 // One launch for the whole exchange unit `x` at batch n.
 int launch_xunit_op(HrnetPlan* P, int x, int n, cudaStream_t st, long long* dbg = nullptr) {
   const XUnitInfo& xu = P->xunits[x];
-  XUnitParams p{};
+  static thread_local XUnitParams p;      // (20 KB of BN constants: off the stack)
+  p = XUnitParams{};
   p.nops = (int)xu.ops.size();
+  for (size_t i = 0; i + 1 < xu.sb.size() && i / 2 < (size_t)kXMaxSb; i += 2) p.sb[i / 2] = make_float2(xu.sb[i], xu.sb[i + 1]);
   p.stages = xu.stages; p.tmem_cols = xu.tmem_cols; p.a_blk_bytes = 16384; p.b_blk_bytes = xu.b_blk;
   p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
   p.ctrl = (unsigned*)(P->abase + xu.ctrl_off);
   p.counters = (unsigned*)(P->abase + xu.counters_off);
   p.dbg = dbg;
-  int kb = 0;
+  int kb = 0, sb_off = 0;
   for (int k = 0; k < p.nops; ++k) {
     const Op& op = P->ops[xu.ops[k]];
     const ConvTcParams t = fill_tc_params(P, op, n);
     XOp& o = p.op[k];
+    o.sb_off = sb_off; sb_off += op.cout;
     o.M_total = t.M_total; o.OH = t.OH; o.OW = t.OW; o.OHW = t.OHW;
     o.ksize = t.ksize; o.stride = t.stride; o.pad = t.pad_h;
     o.Cin = t.Cin; o.Cout = t.Cout; o.cpt = t.cpt; o.nkb = t.nkb;

@@ -21,8 +21,9 @@ def _engine(c, res, maxb, sd, flags=0, tune=None):
     return e
 
 
-PER_CONV = _lib.FLAG_NO_CHAIN      # every conv its own launch: the path test_gpu_forward.py pins
-XUNIT_CONVS, XUNIT_ALL = {_lib.TUNE_XUNIT: 1}, {_lib.TUNE_XUNIT: 2}   # opt-in exchange-unit kernel: convs / convs + sums
+PER_CONV = _lib.FLAG_NO_CHAIN      # with NO_XUNIT: every conv its own launch (round 1's path)
+NO_XUNIT = {_lib.TUNE_XUNIT: 3}
+XUNIT_CONVS, XUNIT_ALL = {_lib.TUNE_XUNIT: 1}, {_lib.TUNE_XUNIT: 2}   # exchange units per source branch (default) / per module + sums
 PAIR = {_lib.TUNE_CHAIN_PAIR: 2}       # im2col chains on CTA pairs (cta_group::2)
 
 
@@ -30,23 +31,25 @@ def test_chain_plan_is_active():
     e = _engine(32, (64, 64), 2, O.make_state_dict(O.hrnet_param_spec(32, 17), seed=3, bn="random"))
     d = e.describe()
     assert len(d["chains"]) == 26 and all(len(ch["ops"]) == 8 for ch in d["chains"])
-    assert d["xunits"] == [] and e.launch_count == 317 - 26 * 7
+    # exchange units per source branch: stage 3 modules 3 + 2 + 2 convs, stage 4 modules 6 + 4 + 3 + 3 (single-conv groups stay launches)
+    assert sorted(len(x["ops"]) for x in d["xunits"]) == sorted([3, 2, 2] * 4 + [6, 4, 3, 3] * 2)
+    assert e.launch_count == 317 - 26 * 7 - (60 - 20)
     sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=3, bn="random")
-    assert _engine(32, (64, 64), 2, sd, PER_CONV).launch_count == 317
-    x1 = _engine(32, (64, 64), 2, sd, 0, XUNIT_CONVS)
-    dx = x1.describe()
-    assert sorted(len(x["ops"]) for x in dx["xunits"]) == [2, 3, 7, 7, 7, 7, 16, 16] and x1.launch_count == 317 - 26 * 7 - (65 - 8)
-    assert _engine(32, (64, 64), 2, sd, 0, XUNIT_ALL).launch_count == 317 - 26 * 7 - (65 - 8) - 23    # sums as tickets
+    assert _engine(32, (64, 64), 2, sd, PER_CONV, NO_XUNIT).launch_count == 317
+    assert _engine(32, (64, 64), 2, sd, 0, NO_XUNIT).launch_count == 317 - 26 * 7
+    xa = _engine(32, (64, 64), 2, sd, 0, XUNIT_ALL)
+    assert sorted(len(x["ops"]) for x in xa.describe()["xunits"]) == [2, 3, 7, 7, 7, 7, 16, 16]
+    assert xa.launch_count == 317 - 26 * 7 - (65 - 8) - 23    # sums as tickets
 
 
 @pytest.mark.parametrize("c,res,n", [(32, (64, 64), 2), (32, (128, 96), 5), (32, (256, 192), 32), (48, (384, 288), 16)])
 def test_chain_equals_per_conv_launches(c, res, n):
     sd = O.make_state_dict(O.hrnet_param_spec(c, 17), seed=5, bn="random")
     x = torch.randn(n, 3, *res, generator=torch.Generator().manual_seed(2)).cuda()
-    ref = _engine(c, res, n, sd, PER_CONV)
+    ref = _engine(c, res, n, sd, PER_CONV, NO_XUNIT)
     jr, ir, hr = ref.forward_decode(x, return_heatmaps=True)
     for flags, tune in ((0, None), (_lib.FLAG_NO_GRAPH, None), (_lib.FLAG_SERIAL, None), (0, PAIR), (_lib.FLAG_SERIAL, PAIR),
-                        (0, XUNIT_CONVS), (0, XUNIT_ALL), (_lib.FLAG_NO_CHAIN, XUNIT_ALL)):
+                        (0, NO_XUNIT), (_lib.FLAG_NO_CHAIN, None), (0, XUNIT_ALL), (_lib.FLAG_NO_CHAIN, XUNIT_ALL)):
         e = _engine(c, res, n, sd, flags, tune)
         for rep in range(3):                          # graph replays / epoch stamps of consecutive launches
             j, i, h = e.forward_decode(x, return_heatmaps=True)
@@ -62,10 +65,10 @@ def test_chain_full_size_headline_and_grid_splits():
     and for skewed ones (few CTAs per chain: long dependency waits; one CTA: strictly sequential tickets)."""
     sd = O.make_state_dict(O.hrnet_param_spec(48, 17), seed=0, bn="default")
     x = torch.randn(64, 3, 384, 288, generator=torch.Generator().manual_seed(3)).cuda()
-    hr = _engine(48, (384, 288), 64, sd, PER_CONV)(x)
+    hr = _engine(48, (384, 288), 64, sd, PER_CONV, NO_XUNIT)(x)
     for tune in (None, {_lib.TUNE_CHAIN_SHARE0: 100, 1: 100, 2: 400, 3: 400}, {_lib.TUNE_CHAIN_GRID_CAP: 3}, {_lib.TUNE_CHAIN_M2: 2},
                  PAIR, {**PAIR, _lib.TUNE_CHAIN_GRID_CAP: 5}, {**PAIR, _lib.TUNE_CHAIN_SHARE0: 100, 1: 100, 2: 400, 3: 400},
-                 XUNIT_CONVS, XUNIT_ALL):
+                 NO_XUNIT, XUNIT_ALL):
         e = _engine(48, (384, 288), 64, sd, 0, tune)
         for rep in range(2):
             h = e(x)

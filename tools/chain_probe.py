@@ -14,16 +14,21 @@ sd = O.make_state_dict(O.hrnet_param_spec(48, 17), seed=0, bn="default")
 x = torch.randn(64, 3, 384, 288, generator=torch.Generator().manual_seed(1)).cuda()
 
 
-def fwd_ms(eng, reps=10):
-    for _ in range(3):
+def fwd_ms(eng, reps=8, groups=6):
+    """median over `groups` timings of `reps` back-to-back forwards (a single short timing moves +-3 % with the clocks)"""
+    for _ in range(4):
         eng.forward_decode(x)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        eng.forward_decode(x)
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    ts = []
+    for _ in range(groups):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            eng.forward_decode(x)
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / reps)
+    ts.sort()
+    return 0.5 * (ts[len(ts) // 2] + ts[(len(ts) - 1) // 2])
 
 
 args = sys.argv[1:]
@@ -66,9 +71,10 @@ for sp in splits:
     print(f"split {sp}: {fwd_ms(eng):.3f} ms/forward   grids (module, branch, ctas): {grids}", flush=True)
     eng.close()
 if "nochain" in args:
-    for name, fl, tn in (("chains (default)", 0, {}), ("chains + exchange-unit kernel (convs)", 0, {_lib.TUNE_XUNIT: 1}),
-                         ("chains + exchange-unit kernel (convs + sums)", 0, {_lib.TUNE_XUNIT: 2}),
-                         ("every conv its own launch", _lib.FLAG_NO_CHAIN, {})):
+    for name, fl, tn in (("chains + exchange units per source branch (default)", 0, {}),
+                         ("chains, every fuse-layer conv its own launch", 0, {_lib.TUNE_XUNIT: 3}),
+                         ("chains + exchange unit per module with sum tickets", 0, {_lib.TUNE_XUNIT: 2}),
+                         ("every conv its own launch", _lib.FLAG_NO_CHAIN, {_lib.TUNE_XUNIT: 3})):
         eng = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), flags=fl, tune={**base_tune, **tn})
         eng.load_state_dict(sd)
         print(f"{name}: {fwd_ms(eng):.3f} ms/forward ({eng.launch_count} launches)", flush=True)
