@@ -79,7 +79,7 @@ __device__ __forceinline__ void chain_cols16(const uint32_t (&v)[16], const U256
 // shared-memory or L1 wavefront.  Why: the tensor core's operand reads, LDS and LDG / STG share the SM's L1 data pipe,
 // and a warp-wide LDS.128 costs four wavefronts even when all lanes read the same address: the constants of a 128 x 48
 // tile cost 452 wavefronts next to the 1,188 of its MMAs, and the pipe was 84 % busy -- the bound of the halo-patch
-// chains (profiles/r02_s11_ncu_chain_kernels.md; without any epilogue work the C = 48 chain runs 1,345 instead of
+// chains (profiles/r02_s11_ncu_chain_kernels.txt; without any epilogue work the C = 48 chain runs 1,345 instead of
 // 2,150 clk per tile, profiles/r02_s18_*.log).  Same arithmetic, same results.
 template <typename SB>
 __device__ __forceinline__ void chain_cols16_c(const uint32_t (&v)[16], const U256& r, const EpiRow& e, int c, const SB& sb) {

@@ -668,9 +668,10 @@ void plan_chains(HrnetPlan& P) {
       ch.smem = o0.patch_smem + (int)(ch.ops.size() - 1) * 2 * o0.cout * 4;   // BN constants of every conv stay in shared memory
       if (ch.smem > kMaxDynSmem) { ch.enabled = false; continue; }
       ch.flag_stride = P.desc.max_batch * o0.pp.tiles_h;             // one counter per row of tiles of an image
-      // measured inside the chains (profiles/r02_s19_*.log): 1,973 clk per 128 x 48 x 432 tile (27 MMAs), 4,380 per
-      // 128 x 96 x 864 tile (54 MMAs) -- the L1 data pipe shared by the MMAs' operand reads and the epilogue's accesses
-      ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * k16 * (o0.cout <= 64 ? 73.0 : 81.0);
+      // per-MMA costs calibrated on the in-situ module times of SM-split sweeps (profiles/r02_s26_split_sweep.log: per
+      // mille 365 / 265 / 185 / 185 for C = 48 / 96 / 192 / 384 is 6 % faster than the isolated per-tile times suggest --
+      // 1,973 clk per 128 x 48 x 432 tile, 4,380 per 128 x 96 x 864 tile -- because the chains also share L2 and power)
+      ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * k16 * (o0.cout <= 64 ? 65.5 : 85.5);
     } else {
       for (int i : ch.ops) P.ops[i].tc.mma_warps = 1;
       const int n_tiles = o0.cout / o0.tc.n_tile;
@@ -698,7 +699,7 @@ void plan_chains(HrnetPlan& P) {
       ch.flag_stride = (m_tiles + tpu - 1) / tpu;                    // one counter per ticket (tpu M-tiles x n_tiles arrivals)
       // measured inside the per-conv kernels: ~200 clk per K16 step of a 128 x 192 tile (profiles/r01_exp_gridcap_pair_sweep.log)
       // ... and ~490 clk per 128 x 192 x 64 k-block of the im2col chains (four K16 steps; CTA pairs ~470)
-      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * ((ch.pair ? 118.0 : 123.0) * o0.tc.n_tile / 192.0);
+      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * ((ch.pair ? 128.0 : 133.0) * o0.tc.n_tile / 192.0);
     }
     ch.ctrl_off = cur; cur += 256;
     ch.flags_off = cur; cur += ((size_t)ch.ops.size() * ch.flag_stride * 4 + 255) / 256 * 256;

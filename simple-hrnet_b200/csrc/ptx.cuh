@@ -57,9 +57,25 @@ __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a lost TMA / commit would otherwise hang the GPU until the watchdog; after ~2 s of
 // spinning the CTA traps, which surfaces as a launch failure on the host (never taken on the hot path).
+// try_wait with a suspend-time hint: the waiting thread may sleep in hardware until the phase completes (or `ns` pass)
+// instead of re-issuing the probe -- hundreds of waiting epilogue / producer threads per SM otherwise burn issue slots
+// and power in a forward that runs at the 1000 W cap.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+  return ok != 0;
+}
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
+#ifdef HRNET_NO_WAIT_HINT       // (A/B builds only: tools/chain_probe.py lib=...)
   while (!mbar_try_wait(bar, parity)) {
+#else
+  while (!mbar_try_wait_hint(bar, parity, 1000000u)) {
+#endif
     if (clock64() - t0 > 4000000000ll) {
       printf("hrnet_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, bar, parity);

@@ -8,7 +8,15 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import hrnet_oracle as O
-from simple_hrnet_b200 import B200Engine, _lib
+from simple_hrnet_b200 import _lib
+for _a in sys.argv[1:]:
+    if _a.startswith("lib="):              # A/B builds of the library (development only): lib=<path of another .so>
+        _p = os.path.join(ROOT, _a[4:])
+        _lib.library_path = lambda _p=_p: _p
+        from simple_hrnet_b200 import build as _b
+        _b.needs_build = lambda: False
+        print("library", _p)
+from simple_hrnet_b200 import B200Engine
 
 sd = O.make_state_dict(O.hrnet_param_spec(48, 17), seed=0, bn="default")
 x = torch.randn(64, 3, 384, 288, generator=torch.Generator().manual_seed(1)).cuda()
@@ -27,6 +35,26 @@ def fwd_ms(eng, reps=8, groups=6):
             eng.forward_decode(x)
         e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) / reps)
+    ts.sort()
+    return 0.5 * (ts[len(ts) // 2] + ts[(len(ts) - 1) // 2])
+
+
+def fwd_ms_dual(eng_a, eng_b, reps=8, groups=6):
+    """two forwards in flight: steps alternate between two engines (same weights, own workspaces) on two streams"""
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    def go(n):
+        for i in range(n):
+            with torch.cuda.stream(sa if i % 2 == 0 else sb):
+                (eng_a if i % 2 == 0 else eng_b).forward_decode(x)
+    go(4); torch.cuda.synchronize()
+    ts = []
+    for _ in range(groups):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main); sa.wait_event(e0); sb.wait_event(e0)
+        go(2 * reps)
+        main.wait_stream(sa); main.wait_stream(sb); e1.record(main); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / (2 * reps))
     ts.sort()
     return 0.5 * (ts[len(ts) // 2] + ts[(len(ts) - 1) // 2])
 
@@ -61,6 +89,12 @@ if "debug" in args:
         print(f"{k[0]} C={k[1]:3d}: {len(v):3d} convs, {sum(v) / len(v):6.1f} us per conv (chain alone on the GPU)")
     print(f"forward (default split): {fwd_ms(eng):.3f} ms")
     eng.close()
+if "dual" in args:
+    ea = B200Engine("hrnet", 48, 17, (384, 288), 64, torch.device("cuda:0"), tune=dict(base_tune))
+    ea.load_state_dict(sd)
+    eb = ea.clone_shared()
+    print(f"one forward at a time: {fwd_ms(ea):.3f} ms/forward; two in flight on two streams: {fwd_ms_dual(ea, eb):.3f} ms/forward", flush=True)
+    eb.close(); ea.close()
 splits = [a for a in args if "," in a]
 for sp in splits:
     t = {**base_tune, **{i: int(v) for i, v in enumerate(sp.split(","))}}
