@@ -85,6 +85,7 @@ extern "C" {
 #define HRNET_TUNE_CHAIN_SKIP 21     /* experiments only, RESULTS INVALID: the im2col chain's epilogue does 1 = nothing, 2 = only its
                                       accumulator loads, 3 = only its residual loads and stores (what slows the MMA stream?) */
 #define HRNET_TUNE_CHAIN_STAGES 22   /* im2col chains: pipeline stages (default: as many as fit in shared memory, <= 8)                 */
+#define HRNET_TUNE_CHAIN_EARLY 23    /* 1 = a module's branch chains do not wait for each other's inputs (default: they start together) */
 #define HRNET_TUNE_COUNT 24
 
 typedef struct HrnetPlan HrnetPlan;
@@ -131,12 +132,16 @@ int hrnet_plan_param_info(const HrnetPlan* plan, int index, HrnetParamInfo* out)
 int hrnet_plan_describe(const HrnetPlan* plan, char* buf, size_t cap, size_t* needed);
 
 /* ---- binding and execution: need a CUDA device ---------------------------------------------- */
-/* Creates the TMA descriptors over the caller's buffers.  Must be repeated if either moves. */
+/* Creates the TMA descriptors over the caller's buffers.  Must be repeated if either moves -- or if the weights are
+ * changed in place: `weights_dev` must already hold the packed weights, because the BN constants of the chained convs
+ * and the head's weights are read back here (synchronous device-to-host copies) and later passed to the kernels as
+ * launch parameters (constant bank). */
 int hrnet_plan_bind(HrnetPlan* plan, void* weights_dev, size_t weight_bytes, void* workspace_dev, size_t act_bytes);
 
 /* The hot path: `self.model(images)` + the argmax decode.
  *   in_nchw_f32 : [n,3,H,W] fp32, ImageNet-normalised RGB, device (what the reference feeds self.model)
- *   heatmaps    : [n,J,H/4,W/4] fp32 device, or NULL (kept in the workspace, not returned)
+ *   heatmaps    : [n,J,H/4,W/4] fp32 device, or NULL: the head then runs fused with the argmax and NO heat-maps are written
+ *                 (same joints / indices bit for bit)
  *   joints      : [n,J,3] fp32 device, (y, x, confidence) exactly as SimpleHRNet.py:306-308
  *   argmax_idx  : [n,J] int32 device flat np.argmax index, or NULL
  *   boxes       : [n,4] fp32 device (x1,y1,x2,y2), or NULL = [0,0,W,H] (multiperson=False crops)

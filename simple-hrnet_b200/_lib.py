@@ -37,6 +37,7 @@ TUNE_XUNIT = 19
 TUNE_CHAIN_PAIR = 20
 TUNE_CHAIN_SKIP = 21
 TUNE_CHAIN_STAGES = 22
+TUNE_CHAIN_EARLY = 23
 TUNE_COUNT = 24
 EPI_AUTO, EPI_DIRECT, EPI_TMA, EPI_COAL, EPI_TMA_PATCH, EPI_TMA_IGEMM, EPI_BATCH = 0, 1, 2, 3, 4, 5, 6
 

@@ -283,11 +283,32 @@ cudaError_t launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 cudaError_t launch_conv_simt(const ConvSimtParams& p, cudaStream_t st);
 cudaError_t launch_stem(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
                         int N, int H, int W, cudaStream_t st);
+cudaError_t stem_tc_set_attributes();     // once per device, before the first launch (hrnet_plan_bind)
 cudaError_t launch_stem_tc(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
-                           int N, int H, int W, cudaStream_t st);
+                           int N, int H, int W, int num_sms, cudaStream_t st);
 cudaError_t launch_stem_tc_u8(const uint8_t* in_nhwc_bgr, const float* w, const float* scale, const float* bias,
-                              __half* out, int N, int H, int W, cudaStream_t st);
+                              __half* out, int N, int H, int W, int num_sms, cudaStream_t st);
 cudaError_t launch_fuse(const FuseParams& p, cudaStream_t st);
+// Head 1x1 conv with the weights as kernel parameters (constant bank) and, optionally, the per-joint argmax fused in:
+// each 128-pixel block reduces its 17 maxima to one (value, index) candidate per joint (`pval` / `pidx`,
+// [N][J][nblk]); head_argmax_finish reduces the candidates and decodes the joints -- the heat-maps are then never
+// written (72 MB) nor re-read (30 MB) at W48 / 64 crops.  `out` (NCHW fp32 heat-maps) and the partials are each optional.
+constexpr int kHeadMaxW = 6144;      // J * Cin floats that fit the parameter block (W48: 816, PoseResNet-50: 4,352)
+constexpr int kHeadMaxJc = 32;
+struct HeadParams {
+  const __half* in;
+  float* out;
+  float* pval;
+  int* pidx;
+  int N, HW, Cin, J, nblk, pad_;
+  float bias[kHeadMaxJc];
+  float w[kHeadMaxW];                // [J][Cin]
+};
+int head_c_blocks(int hw);                   // argmax candidates per (person, joint): blocks of 512 pixels
+bool head_c_supported(int cin, int nj);     // shapes with a compiled specialisation (HRNet-W48 / W32, 17 joints)
+cudaError_t launch_head_c(const HeadParams& p, cudaStream_t st);
+cudaError_t launch_head_argmax_finish(const float* pval, const int* pidx, int N, int J, int nblk, int Hh, int Wh,
+                                      const float* boxes, float* joints, int32_t* idx, cudaStream_t st);
 cudaError_t launch_head(const __half* in, const float* w, const float* bias, float* out_nchw, int N, int HW, int Cin,
                         int J, cudaStream_t st);
 cudaError_t launch_argmax(const float* hm, int N, int J, int Hh, int Wh, const float* boxes, float* joints,

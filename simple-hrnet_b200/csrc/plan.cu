@@ -86,6 +86,9 @@ struct HrnetPlan {
   int Hh = 0, Wh = 0;
   // staging for hrnet_forward_host (inside the workspace)
   size_t off_in_stage = 0, off_joints = 0, off_idx = 0, off_boxes = 0;
+  size_t off_pval = 0, off_pidx = 0;      // per-block argmax candidates of the fused head [max_batch][J][head_nblk]
+  int head_nblk = 0;
+  std::vector<float> head_w, head_b;      // host copy of the head's fp32 weights / bias (kernel parameters), hrnet_plan_bind
   // bound state
   bool bound = false;
   uint8_t* wbase = nullptr;
@@ -549,6 +552,9 @@ int build_hrnet(HrnetPlan& P) {
   P.off_joints = cur;   cur += align_up((size_t)b.maxb * J * 3 * 4, 1024);
   P.off_idx = cur;      cur += align_up((size_t)b.maxb * J * 4, 1024);
   P.off_boxes = cur;    cur += align_up((size_t)b.maxb * 4 * 4, 1024);
+  P.head_nblk = head_c_blocks(P.Hh * P.Wh);
+  P.off_pval = cur;     cur += align_up((size_t)b.maxb * J * P.head_nblk * 4, 1024);
+  P.off_pidx = cur;     cur += align_up((size_t)b.maxb * J * P.head_nblk * 4, 1024);
   const size_t a0 = cur, a1 = b.arena_max[1], a2 = b.arena_max[2];
   for (size_t i = 0; i < P.tensors.size(); ++i) {
     const int a = b.tensor_arena[i];
@@ -633,6 +639,9 @@ int build_poseresnet(HrnetPlan& P) {
   P.off_joints = cur;   cur += align_up((size_t)b.maxb * J * 3 * 4, 1024);
   P.off_idx = cur;      cur += align_up((size_t)b.maxb * J * 4, 1024);
   P.off_boxes = cur;    cur += align_up((size_t)b.maxb * 4 * 4, 1024);
+  P.head_nblk = head_c_blocks(P.Hh * P.Wh);
+  P.off_pval = cur;     cur += align_up((size_t)b.maxb * J * P.head_nblk * 4, 1024);
+  P.off_pidx = cur;     cur += align_up((size_t)b.maxb * J * P.head_nblk * 4, 1024);
   P.act_bytes = cur;
   P.weight_bytes = align_up(b.wcur, 1024);
   return 0;
@@ -718,7 +727,9 @@ void plan_chains(HrnetPlan& P) {
     for (int c : kv.second)
       for (int dpi : P.ops[P.chains[c].ops[0]].deps)
         if (std::find(deps.begin(), deps.end(), dpi) == deps.end()) deps.push_back(dpi);
-    for (int c : kv.second) P.ops[P.chains[c].ops[0]].deps = deps;
+    // (HRNET_TUNE_CHAIN_EARLY = 1, experiment: every chain starts as soon as ITS input is summed)
+    if (P.desc.tune[HRNET_TUNE_CHAIN_EARLY] != 1)
+      for (int c : kv.second) P.ops[P.chains[c].ops[0]].deps = deps;
     // grid split: proportional to the estimated cost (HRNET_TUNE_CHAIN_SHARE* overrides, per mille of the SM count);
     // resolved to CTA counts at bind time, when the SM count is known
     double tot = 0;
@@ -1232,6 +1243,21 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
       if (rc) return rc;
     }
   }
+  {
+    cudaError_t e = stem_tc_set_attributes();
+    if (e != cudaSuccess) return fail(HRNET_E_CUDA, std::string("cudaFuncSetAttribute(stem): ") + cudaGetErrorString(e));
+  }
+  // head: fp32 weights / bias -> host, they travel as kernel parameters (head_c_kernel) when they fit
+  P->head_w.clear(); P->head_b.clear();
+  for (auto& op : P->ops) {
+    if (op.kind != OP_HEAD) continue;
+    const ParamInfo& pi = P->params[op.param];
+    if (op.cout > kHeadMaxJc || op.cout * op.cin > kHeadMaxW || !head_c_supported(op.cin, op.cout)) break;
+    P->head_w.resize((size_t)op.cout * op.cin); P->head_b.resize(op.cout);
+    if (cudaMemcpy(P->head_w.data(), P->wbase + pi.w_offset, P->head_w.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(P->head_b.data(), P->wbase + pi.bias_offset, P->head_b.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return fail(HRNET_E_CUDA, "cudaMemcpy(head weights)");
+  }
   // branch chains: tensor maps of the member convs side by side, grid split of each module's chains, cleared flags
   {
     std::map<int, std::vector<int>> by_module;
@@ -1616,7 +1642,7 @@ int launch_xunit_op(HrnetPlan* P, int x, int n, cudaStream_t st, long long* dbg 
 }
 
 int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_ext, float* joints, int32_t* idx,
-              const float* boxes, cudaStream_t st, bool in_u8 = false) {
+              const float* boxes, cudaStream_t st, bool in_u8 = false, bool no_hm = false) {
   auto tptr = [&](int t) -> uint8_t* { return P->abase + P->tensors[t].offset; };
   switch (op.kind) {
     case OP_STEM:
@@ -1627,10 +1653,16 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         if (op.kind != OP_STEM) return fail(HRNET_E_INVALID, "uint8 image input is implemented for the HRNet stem only");
         CK(launch_stem_tc_u8((const uint8_t*)in_ext, (const float*)(P->wbase + pi.w_offset),
                              (const float*)(P->wbase + pi.scale_offset), (const float*)(P->wbase + pi.bias_offset),
-                             (__half*)tptr(op.out), n, P->desc.height, P->desc.width, st));
+                             (__half*)tptr(op.out), n, P->desc.height, P->desc.width, P->num_sms, st));
         return 0;
       }
-      auto fn = op.kind == OP_STEM ? ((P->desc.flags & HRNET_FLAG_FORCE_SIMT) ? launch_stem : launch_stem_tc) : launch_stem7;
+      if (op.kind == OP_STEM && !(P->desc.flags & HRNET_FLAG_FORCE_SIMT)) {
+        CK(launch_stem_tc(in_ext, (const float*)(P->wbase + pi.w_offset), (const float*)(P->wbase + pi.scale_offset),
+                          (const float*)(P->wbase + pi.bias_offset), (__half*)tptr(op.out), n, P->desc.height, P->desc.width,
+                          P->num_sms, st));
+        return 0;
+      }
+      auto fn = op.kind == OP_STEM ? launch_stem : launch_stem7;
       CK(fn(in_ext, (const float*)(P->wbase + pi.w_offset), (const float*)(P->wbase + pi.scale_offset),
             (const float*)(P->wbase + pi.bias_offset), (__half*)tptr(op.out), n, P->desc.height, P->desc.width, st));
       return 0;
@@ -1709,11 +1741,30 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
       const TensorInfo& ti = P->tensors[op.in];
       const ParamInfo& pi = P->params[op.param];
       float* out = hm_ext ? hm_ext : (float*)tptr(op.out);
+      if (!P->head_w.empty()) {
+        // weights as kernel parameters; when nobody wants the heat-maps (no_hm) they are not written at all: the
+        // block-level argmax candidates go to the finishing kernel launched for OP_ARGMAX
+        static thread_local HeadParams hp;
+        hp.in = (const __half*)tptr(op.in);
+        hp.out = no_hm ? nullptr : out;
+        hp.pval = no_hm ? (float*)(P->abase + P->off_pval) : nullptr;
+        hp.pidx = no_hm ? (int*)(P->abase + P->off_pidx) : nullptr;
+        hp.N = n; hp.HW = ti.H * ti.W; hp.Cin = op.cin; hp.J = op.cout; hp.nblk = P->head_nblk; hp.pad_ = 0;
+        memcpy(hp.bias, P->head_b.data(), P->head_b.size() * 4);
+        memcpy(hp.w, P->head_w.data(), P->head_w.size() * 4);
+        CK(launch_head_c(hp, st));
+        return 0;
+      }
       CK(launch_head((const __half*)tptr(op.in), (const float*)(P->wbase + pi.w_offset),
                      (const float*)(P->wbase + pi.bias_offset), out, n, ti.H * ti.W, op.cin, op.cout, st));
       return 0;
     }
     case OP_ARGMAX: {
+      if (no_hm && !P->head_w.empty()) {
+        CK(launch_head_argmax_finish((const float*)(P->abase + P->off_pval), (const int*)(P->abase + P->off_pidx), n, op.cout,
+                                     P->head_nblk, P->Hh, P->Wh, boxes, joints, idx, st));
+        return 0;
+      }
       const float* hm = hm_ext ? hm_ext : (const float*)tptr(op.in);
       CK(launch_argmax(hm, n, op.cout, P->Hh, P->Wh, boxes, joints, idx, st));
       return 0;
@@ -1794,8 +1845,10 @@ int run_range(HrnetPlan* P, int first, int last, int n, const float* in_ext, flo
 
 }  // namespace
 
+// keep_hm: the caller will read the plan's internal heat-map tensor afterwards (host variants with heatmaps_h); with
+// neither that nor an external `heatmaps` buffer the head runs fused with the argmax and writes no heat-maps
 static int forward_impl(HrnetPlan* P, const float* in, int n, float* heatmaps, float* joints, int32_t* argmax_idx,
-                        const float* boxes, void* stream, bool in_u8) {
+                        const float* boxes, void* stream, bool in_u8, bool keep_hm = false) {
   if (!P) return fail(HRNET_E_INVALID, "null plan");
   if (!P->bound) return fail(HRNET_E_STATE, "hrnet_plan_bind must be called before hrnet_forward");
   if (n < 0 || n > P->desc.max_batch) return fail(HRNET_E_INVALID, "n out of range [0, max_batch]");
@@ -1844,7 +1897,7 @@ static int forward_impl(HrnetPlan* P, const float* in, int n, float* heatmaps, f
     if (P->desc.flags & HRNET_FLAG_NO_GRAPH)
       for (int dpi : op.deps)
         if (P->ops[dpi].stream != 0) CK(cudaStreamWaitEvent(s0, P->events[dpi], 0));
-    rc = launch_op(P, op, n, in, heatmaps, joints, argmax_idx, boxes, s0);
+    rc = launch_op(P, op, n, in, heatmaps, joints, argmax_idx, boxes, s0, false, heatmaps == nullptr && !keep_hm);
     if (rc) return rc;
   }
   return HRNET_OK;
@@ -1879,7 +1932,8 @@ static int forward_host_u8_impl(HrnetPlan* P, const uint8_t* images_h, int n, fl
   float* boxes_d = boxes_h ? (float*)(P->abase + P->off_boxes) : nullptr;
   CK(cudaMemcpyAsync(in_d, images_h, (size_t)n * 3 * P->desc.height * P->desc.width, cudaMemcpyHostToDevice, s0));
   if (boxes_h) CK(cudaMemcpyAsync(boxes_d, boxes_h, (size_t)n * 16, cudaMemcpyHostToDevice, s0));
-  int rc = hrnet_forward_u8(P, in_d, n, nullptr, joints_d, idx_d, boxes_d, stream);
+  if (P->desc.arch != HRNET_ARCH_HRNET) return fail(HRNET_E_INVALID, "uint8 image input is implemented for HRNet only");
+  int rc = forward_impl(P, reinterpret_cast<const float*>(in_d), n, nullptr, joints_d, idx_d, boxes_d, stream, true, heatmaps_h != nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(joints_h, joints_d, (size_t)n * J * 12, cudaMemcpyDeviceToHost, s0));
   if (idx_h) CK(cudaMemcpyAsync(idx_h, idx_d, (size_t)n * J * 4, cudaMemcpyDeviceToHost, s0));
@@ -1973,7 +2027,7 @@ int hrnet_profile_ops(HrnetPlan* P, const float* in, int n, float* usec_per_op, 
         i = j - 1;
         continue;
       }
-      int rc = launch_op(P, op, n, in, nullptr, joints, idx, nullptr, s0);
+      int rc = launch_op(P, op, n, in, nullptr, joints, idx, nullptr, s0, false, true);
       if (rc) return rc;
       CK(cudaEventRecord(ev[i + 1], s0));
     }
@@ -2086,7 +2140,7 @@ int hrnet_forward_host(HrnetPlan* P, const float* in_h, int n, float* heatmaps_h
   float* boxes_d = boxes_h ? (float*)(P->abase + P->off_boxes) : nullptr;
   CK(cudaMemcpyAsync(in_d, in_h, (size_t)n * 3 * P->desc.height * P->desc.width * 4, cudaMemcpyHostToDevice, s0));
   if (boxes_h) CK(cudaMemcpyAsync(boxes_d, boxes_h, (size_t)n * 16, cudaMemcpyHostToDevice, s0));
-  int rc = hrnet_forward(P, in_d, n, nullptr, joints_d, idx_d, boxes_d, stream);
+  int rc = forward_impl(P, in_d, n, nullptr, joints_d, idx_d, boxes_d, stream, false, heatmaps_h != nullptr);
   if (rc) return rc;
   CK(cudaMemcpyAsync(joints_h, joints_d, (size_t)n * J * 12, cudaMemcpyDeviceToHost, s0));
   if (idx_h) CK(cudaMemcpyAsync(idx_h, idx_d, (size_t)n * J * 4, cudaMemcpyDeviceToHost, s0));

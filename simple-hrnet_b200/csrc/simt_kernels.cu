@@ -382,6 +382,165 @@ argmax_decode_kernel(const float* __restrict__ hm, int J, int Hh, int Wh, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ head (+ argmax)
+// The head above is bound by the shared-memory broadcast reads of its weights (17 x 48 x 4 B per pixel-thread: an LDS.128
+// costs four L1 wavefronts even when every lane reads the same address -> 0.23 of the HBM roofline); here the weights
+// are kernel parameters: every FMA's second operand comes from the constant bank.  Same accumulation order as
+// head_conv1x1_kernel -> bit-identical heat-map values.  grid = (blocks of 128 pixels, person).
+// Every thread owns kHeadPix pixels: a broadcast shared-memory read of the weights (four L1 wavefronts per LDS.128) feeds
+// kHeadPix x 4 FMAs per lane instead of 4 -- head_conv1x1_kernel is bound by exactly those reads (816 wavefronts per 32
+// pixels = 42 us).  Weights straight from the constant bank were slower: one uniform load per FMA and warp 86 us, with four
+// pixels per thread still 64 us (the uniform loads are a latency chain; profiles/r02_s28_head_stem.log, r02_s29_*.log).
+constexpr int kHeadPix = 4;
+template <int CIN, int NJ>
+__global__ void __launch_bounds__(128) head_c_kernel(const __grid_constant__ HeadParams p) {
+  const int n = blockIdx.y;
+  const int hw0 = (int)blockIdx.x * (128 * kHeadPix) + (int)threadIdx.x;      // pixels hw0 + 128 * i
+  __shared__ __align__(16) float shw[NJ * CIN];
+  for (int i = threadIdx.x; i < NJ * CIN; i += 128) shw[i] = p.w[i];
+  __syncthreads();
+  float acc[kHeadPix][NJ];
+#pragma unroll
+  for (int i = 0; i < kHeadPix; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int c = 0; c < CIN; c += 8) {
+    float x[kHeadPix][8];
+#pragma unroll
+    for (int i = 0; i < kHeadPix; ++i) {
+      const int hw = hw0 + 128 * i;
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (hw < p.HW) u = __ldg(reinterpret_cast<const uint4*>(p.in + ((size_t)n * p.HW + hw) * CIN + c));
+      const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const float2 f = __half22float2(hh[k]); x[i][2 * k] = f.x; x[i][2 * k + 1] = f.y; }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      // two 16-byte broadcast reads feed 8 x kHeadPix FMAs per lane (a broadcast LDS.128 costs four L1 wavefronts)
+      const float4 w0 = *reinterpret_cast<const float4*>(shw + j * CIN + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(shw + j * CIN + c + 4);
+      const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int i = 0; i < kHeadPix; ++i) acc[i][j] = fmaf(x[i][k], wk[k], acc[i][j]);     // same order per pixel as head_conv1x1_kernel
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const float bj = p.bias[j];
+#pragma unroll
+    for (int i = 0; i < kHeadPix; ++i) acc[i][j] += bj;
+  }
+  if (p.out != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kHeadPix; ++i) {
+      const int hw = hw0 + 128 * i;
+      if (hw < p.HW) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) p.out[((size_t)n * NJ + j) * p.HW + hw] = acc[i][j];
+      }
+    }
+  }
+  if (p.pval == nullptr) return;
+  // per-joint candidate of this block: np.argmax order (first maximum, a NaN is the maximum) is a total order on
+  // (value, index), so partial results combine in any grouping
+  __shared__ float sv[4][NJ];
+  __shared__ int si[4][NJ];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    float best = 0.f;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kHeadPix; ++i) {
+      const int hw = hw0 + 128 * i;
+      if (hw < p.HW && (bi == 0x7fffffff || better(acc[i][j], hw, best, bi))) { best = acc[i][j]; bi = hw; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ob, oi, best, bi))) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { sv[warp][j] = best; si[warp][j] = bi; }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NJ) {
+    const int j = threadIdx.x;
+    float best = sv[0][j];
+    int bi = si[0][j];
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+      const float ob = sv[w][j];
+      const int oi = si[w][j];
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ob, oi, best, bi))) { best = ob; bi = oi; }
+    }
+    const size_t o = ((size_t)n * NJ + j) * p.nblk + blockIdx.x;
+    p.pval[o] = best;
+    p.pidx[o] = bi;
+  }
+}
+
+int head_c_blocks(int hw) { return (hw + 128 * kHeadPix - 1) / (128 * kHeadPix); }
+bool head_c_supported(int cin, int nj) { return nj == 17 && (cin == 48 || cin == 32); }
+cudaError_t launch_head_c(const HeadParams& p, cudaStream_t st) {
+  if (p.N == 0 || p.HW == 0) return cudaSuccess;
+  const dim3 grid((unsigned)p.nblk, (unsigned)p.N);
+  if (p.J == 17 && p.Cin == 48) head_c_kernel<48, 17><<<grid, 128, 0, st>>>(p);
+  else if (p.J == 17 && p.Cin == 32) head_c_kernel<32, 17><<<grid, 128, 0, st>>>(p);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// one warp per (person, joint): reduces the block candidates and decodes like argmax_decode_kernel
+__global__ void __launch_bounds__(128)
+head_argmax_finish_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, int NJ, int J, int nblk, int Hh, int Wh,
+                          const float* __restrict__ boxes, float* __restrict__ joints, int32_t* __restrict__ idx_out) {
+  const int pj = (int)blockIdx.x * 4 + (int)(threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pj >= NJ) return;
+  float best = 0.f;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < nblk; i += 32) {
+    const float v = pval[(size_t)pj * nblk + i];
+    const int vi = pidx[(size_t)pj * nblk + i];
+    if (vi != 0x7fffffff && (bi == 0x7fffffff || better(v, vi, best, bi))) { best = v; bi = vi; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ob, oi, best, bi))) { best = ob; bi = oi; }
+  }
+  if (lane == 0) {
+    const int person = pj / J;
+    const int r = bi / Wh, c = bi - r * Wh;
+    float x1 = 0.f, y1 = 0.f, x2 = (float)(Wh * 4), y2 = (float)(Hh * 4);
+    if (boxes != nullptr) {
+      x1 = boxes[person * 4 + 0]; y1 = boxes[person * 4 + 1];
+      x2 = boxes[person * 4 + 2]; y2 = boxes[person * 4 + 3];
+    }
+    const float dy = y2 - y1, dx = x2 - x1;  // float32 subtraction like the numpy f32 box array
+    const double y = (double)r * 1.0 / (double)Hh * (double)dy + (double)y1;
+    const double x = (double)c * 1.0 / (double)Wh * (double)dx + (double)x1;
+    joints[(size_t)pj * 3 + 0] = (float)y;
+    joints[(size_t)pj * 3 + 1] = (float)x;
+    joints[(size_t)pj * 3 + 2] = best;
+    if (idx_out != nullptr) idx_out[pj] = bi;
+  }
+}
+
+cudaError_t launch_head_argmax_finish(const float* pval, const int* pidx, int N, int J, int nblk, int Hh, int Wh,
+                                      const float* boxes, float* joints, int32_t* idx, cudaStream_t st) {
+  if (N * J == 0) return cudaSuccess;
+  head_argmax_finish_kernel<<<(unsigned)((N * J + 3) / 4), 128, 0, st>>>(pval, pidx, N * J, J, nblk, Hh, Wh, boxes, joints, idx);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_argmax(const float* hm, int N, int J, int Hh, int Wh, const float* boxes, float* joints,
                           int32_t* idx, cudaStream_t st) {
   if (N * J == 0) return cudaSuccess;

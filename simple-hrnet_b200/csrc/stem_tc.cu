@@ -40,7 +40,7 @@ __device__ __forceinline__ void st_chunk(uint8_t* blk, int row, int chunk, const
 // the same fp32 operation order (IEEE div / sub / div), so the result is bit-identical to feeding the host-normalised
 // fp32 tensor -- while the host->device copy shrinks 4x (3 B instead of 12 B per input pixel).
 template <bool kU8>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)      // four CTAs per SM: 128 registers per thread
 stem_conv3x3s2_tc_kernel(const void* __restrict__ in_any, const float* __restrict__ w, const float* __restrict__ scale,
                          const float* __restrict__ bias, __half* __restrict__ out, int N, int H, int W) {
   const float* in = static_cast<const float*>(in_any);
@@ -86,52 +86,56 @@ stem_conv3x3s2_tc_kernel(const void* __restrict__ in_any, const float* __restric
   const uint32_t tmem = *tslot;
   uint32_t phase = 0;
   const long ntiles = (total + 127) / 128;
+  // The 27 scattered input loads of a pixel are latency, not bandwidth: the NEXT tile's are issued right after this
+  // tile's MMAs and land while the MMA round trip and the epilogue run (software pipeline, 32 more registers).
+  auto gather = [&](long tile, float (&x)[32]) {
+    const long pix = tile * 128 + tid;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = 0.f;
+    if (tile < ntiles && pix < total) {
+      const int n = (int)(pix / (OH * OW));
+      const int rem = (int)(pix - (long)n * OH * OW);
+      const int oh = rem / OW, ow = rem - oh * OW;
+      const float* ip = in + (size_t)n * 3 * H * W;
+      const uint8_t* ip8 = in8 + (size_t)n * H * W * 3;
+      const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};   // RGB, SimpleHRNet.py:152
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int ih = oh * 2 - 1 + r;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int iw = ow * 2 - 1 + s;
+          const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) {
+            float v = 0.f;    // zero padding applies to the normalised tensor
+            if (ok) {
+              if constexpr (kU8) {
+                const float u = (float)__ldg(ip8 + ((size_t)ih * W + iw) * 3 + (2 - ci));   // BGR -> RGB
+                v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), mean[ci]), stdv[ci]);
+              } else {
+                v = __ldg(ip + ((size_t)ci * H + ih) * W + iw);
+              }
+            }
+            x[(r * 3 + s) * 3 + ci] = v;
+          }
+        }
+      }
+    }
+  };
+  float xc[32];
+  gather((long)blockIdx.x, xc);
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long pix = tile * 128 + tid;
     const bool valid = pix < total;
     // ---- A rows: one output pixel per thread
-    {
-      float x[32];
-  #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = 0.f;
-      if (valid) {
-        const int n = (int)(pix / (OH * OW));
-        const int rem = (int)(pix - (long)n * OH * OW);
-        const int oh = rem / OW, ow = rem - oh * OW;
-        const float* ip = in + (size_t)n * 3 * H * W;
-        const uint8_t* ip8 = in8 + (size_t)n * H * W * 3;
-        const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};   // RGB, SimpleHRNet.py:152
-  #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int ih = oh * 2 - 1 + r;
-  #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int iw = ow * 2 - 1 + s;
-            const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-  #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-              float v = 0.f;    // zero padding applies to the normalised tensor
-              if (ok) {
-                if constexpr (kU8) {
-                  const float u = (float)__ldg(ip8 + ((size_t)ih * W + iw) * 3 + (2 - ci));   // BGR -> RGB
-                  v = __fdiv_rn(__fsub_rn(__fdiv_rn(u, 255.f), mean[ci]), stdv[ci]);
-                } else {
-                  v = __ldg(ip + ((size_t)ci * H + ih) * W + iw);
-                }
-              }
-              x[(r * 3 + s) * 3 + ci] = v;
-            }
-          }
-        }
-      }
-  #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 hi, lo;
-        split_pack8(x + 8 * c, hi, lo);
-        st_chunk(A0, tid, c, hi);
-        st_chunk(A0, tid, 4 + c, lo);
-        st_chunk(A1, tid, c, hi);
-      }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 hi, lo;
+      split_pack8(xc + 8 * c, hi, lo);
+      st_chunk(A0, tid, c, hi);
+      st_chunk(A0, tid, 4 + c, lo);
+      st_chunk(A1, tid, c, hi);
     }
     ptx::fence_proxy_async_smem();     // generic-proxy stores -> visible to the tensor core (async proxy)
     ptx::tc_fence_before_sync();
@@ -152,6 +156,7 @@ stem_conv3x3s2_tc_kernel(const void* __restrict__ in_any, const float* __restric
       }
       __syncwarp();
     }
+    gather(tile + gridDim.x, xc);      // the next tile's inputs: in flight during the MMA round trip and the epilogue
     ptx::mbar_wait(ptx::smem_u32(bar), phase);
     phase ^= 1u;
     ptx::tc_fence_after_sync();
@@ -187,38 +192,31 @@ stem_conv3x3s2_tc_kernel(const void* __restrict__ in_any, const float* __restric
   if (warp == 0) { ptx::tc_fence_after_sync(); ptx::tmem_dealloc(tmem, 64); }
 }
 
+constexpr int kStemSmem = 1024 + 49152 + 512 + 64;
+cudaError_t stem_tc_set_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(stem_conv3x3s2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_conv3x3s2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmem);
+  return e;
+}
+
 static cudaError_t launch_stem_tc_any(const void* in, bool u8, const float* w, const float* scale, const float* bias,
-                                      __half* out, int N, int H, int W, cudaStream_t st) {
+                                      __half* out, int N, int H, int W, int num_sms, cudaStream_t st) {
   const long total = (long)N * (H / 2) * (W / 2);
   if (total == 0) return cudaSuccess;
-  const int smem = 1024 + 49152 + 512 + 64;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(stem_conv3x3s2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(stem_conv3x3s2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return cudaGetLastError();
-  }
-  const unsigned grid = (unsigned)std::min<long>((total + 127) / 128, (long)sms * 4);
-  if (u8) stem_conv3x3s2_tc_kernel<true><<<grid, 128, smem, st>>>(in, w, scale, bias, out, N, H, W);
-  else stem_conv3x3s2_tc_kernel<false><<<grid, 128, smem, st>>>(in, w, scale, bias, out, N, H, W);
+  const unsigned grid = (unsigned)std::min<long>((total + 127) / 128, (long)num_sms * 4);
+  if (u8) stem_conv3x3s2_tc_kernel<true><<<grid, 128, kStemSmem, st>>>(in, w, scale, bias, out, N, H, W);
+  else stem_conv3x3s2_tc_kernel<false><<<grid, 128, kStemSmem, st>>>(in, w, scale, bias, out, N, H, W);
   return cudaGetLastError();
 }
 
 cudaError_t launch_stem_tc(const float* in_nchw, const float* w, const float* scale, const float* bias, __half* out,
-                           int N, int H, int W, cudaStream_t st) {
-  return launch_stem_tc_any(in_nchw, false, w, scale, bias, out, N, H, W, st);
+                           int N, int H, int W, int num_sms, cudaStream_t st) {
+  return launch_stem_tc_any(in_nchw, false, w, scale, bias, out, N, H, W, num_sms, st);
 }
 
 cudaError_t launch_stem_tc_u8(const uint8_t* in_nhwc_bgr, const float* w, const float* scale, const float* bias,
-                              __half* out, int N, int H, int W, cudaStream_t st) {
-  return launch_stem_tc_any(in_nhwc_bgr, true, w, scale, bias, out, N, H, W, st);
+                              __half* out, int N, int H, int W, int num_sms, cudaStream_t st) {
+  return launch_stem_tc_any(in_nhwc_bgr, true, w, scale, bias, out, N, H, W, num_sms, st);
 }
 
 }  // namespace hrnet

@@ -309,3 +309,38 @@ def test_poseresnet_forward_matches_reference_fixture(golden_dir):
     err = float(np.abs(hm - g["heatmaps"]).max())
     _report(f"poseresnet50_256x192_n1_default: heat-map max-abs err {err:.3e}")
     assert err <= 1e-3
+
+
+def test_fused_head_argmax_equals_separate_kernels():
+    """Without a heat-map request the head runs fused with the argmax (head_c_kernel + head_argmax_finish_kernel: no
+    heat-maps written); with one it writes the maps and argmax_decode_kernel scans them (models_/hrnet.py:187 +
+    SimpleHRNet.py:296-308).  Same joints / indices bit for bit -- random weights, boxes, a head whose maps are constant
+    (all ties: first index), NaN maps (first NaN), +-inf, and the host entry point with and without heat-maps."""
+    import copy
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=21, bn="random")
+    x = torch.randn(5, 3, 128, 96, generator=torch.Generator().manual_seed(4)).cuda()
+    boxes = torch.tensor([[3.0, 5.0, 90.0, 120.0]] * 5, dtype=torch.float32).cuda()
+    variants = [("random", sd)]
+    s2 = copy.deepcopy(sd); s2["final_layer.weight"] = torch.zeros_like(torch.as_tensor(s2["final_layer.weight"]))
+    variants.append(("ties", s2))
+    s3 = copy.deepcopy(sd); b3 = torch.as_tensor(s3["final_layer.bias"]).clone(); b3[2] = float("nan"); b3[5] = float("inf"); b3[7] = float("-inf")
+    s3["final_layer.bias"] = b3
+    variants.append(("nan-inf", s3))
+    for name, w in variants:
+        e = B200Engine("hrnet", 32, 17, (128, 96), 8, torch.device("cuda:0"))
+        e.load_state_dict(w)
+        for bx in (None, boxes):
+            jf, idf, _ = e.forward_decode(x, boxes=bx)
+            js, ids, hm = e.forward_decode(x, boxes=bx, return_heatmaps=True)
+            assert torch.equal(idf, ids), name
+            assert torch.equal(torch.nan_to_num(jf, nan=-7.0), torch.nan_to_num(js, nan=-7.0)), name
+            ref_idx = torch.from_numpy(np.stack([[int(np.argmax(hm[n, j].cpu().numpy())) for j in range(17)] for n in range(5)]))
+            assert torch.equal(idf.cpu().to(torch.int64), ref_idx), name
+        if name == "ties":
+            assert int(idf.abs().max()) == 0
+        u8 = torch.randint(0, 256, (5, 128, 96, 3), generator=torch.Generator().manual_seed(6), dtype=torch.uint8)
+        j0, i0, _ = e.forward_host_u8(u8.numpy())
+        j1, i1, h1 = e.forward_host_u8(u8.numpy(), want_heatmaps=True)
+        assert np.array_equal(i0, i1) and np.array_equal(np.nan_to_num(j0, nan=-7.0), np.nan_to_num(j1, nan=-7.0)), name
+        assert h1 is not None and h1.shape == (5, 17, 32, 24)
+        e.close()
