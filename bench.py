@@ -547,9 +547,19 @@ def main():
             ach = f4 / t4 / 1e6
             what = f"all tensor-core convs of the network, N={n}, each timed with a CUDA event pair inside a serial pass"
             launches = sum(v for k, v in cls_n.items() if cls_f.get(k))
-        roofline = {"kernel": what, "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
+        # traffic: DRAM bytes (ncu dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the dominant kernel class =
+        # the four concurrent branch-chain kernels of stage4.0 (the unit `achieved` is timed on); details in traffic_detail
+        tdet = load_traffic()
+        tnum = None
+        if tdet and is_hrnet:
+            ch = [k for k in tdet.get("kernels", []) if "conv_chain" in k.get("kernel", "") and k.get("traffic") is not None]
+            if len(ch) >= 4:
+                tnum = int(sum(k["traffic"] for k in ch[:4]))
+        roofline = {"kernel": what.replace("each chain timed alone on the whole GPU with a CUDA event pair",
+                                           "the chains of a module launched together on their in-forward grids and timed with one CUDA event pair"),
+                    "bound": "tensor", "achieved": round(ach, 1), "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": round(ach / peaks["tflops"], 4),
-                    "frac_of_sustained_peak": round(ach / peaks["tflops_sustained"], 4), "traffic": load_traffic(),
+                    "frac_of_sustained_peak": round(ach / peaks["tflops_sustained"], 4), "traffic": tnum, "traffic_detail": tdet,
                     "peak_source": peaks["source"] + ", burst figure (the per-op timing pass lasts tens of milliseconds at boost clocks)",
                     "launches": launches, "us_total": round(cls_t[k4], 1),
                     "per_branch": [{"C": k[0], "map": k[1], "kernel": k[2], "convs": v[2], "us_per_conv": round(v[0] / v[2], 2),

@@ -217,6 +217,18 @@ int hrnet_flip_average(const float* output, const float* output_flipped, const i
  *   (simple_hrnet_b200.preprocess.cubic_tables restates OpenCV's float32 table computation). */
 int hrnet_resize_cubic_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, const int32_t* xofs,
                           const int16_t* xcoef, const int32_t* yofs, const int16_t* ycoef, void* stream);
+/* Multi-person crops on the device: `ToPILImage -> Resize((H, W))` of the reference's crop transform
+ * (SimpleHRNet.py:166-171) applied to `image[y1:y2, x1:x2]` (+ the zero padding of SimpleHRNet.py:262-270) -- Pillow's
+ * antialiased bilinear resample of an 8-bit image restated bit for bit (horizontal pass rounded to uint8, vertical pass,
+ * 22-bit fixed-point coefficients).  The output is the input of hrnet_forward_u8.
+ *   frames [n_frames, frame_h, frame_w, 3] uint8 (device); out [m, out_h, out_w, 3] uint8 (device)
+ *   crops  [m][12] int32 (device): frame | x0 y0 = frame coordinates of the padded crop's top-left | vx0 vy0 vx1 vy1 = the
+ *          frame rectangle that holds image data (zero outside) | offsets (in int32 units) of the crop's x and y tables in
+ *          `tables` | taps per output coordinate kx ky | 0
+ *   tables int32 (device): per axis [out][2] (first source index, tap count) then [out][k] coefficients, as built by
+ *          simple_hrnet_b200.preprocess.pil_bilinear_tables (= Pillow's precompute_coeffs + normalize_coeffs_8bpc). */
+int hrnet_crop_resize_bilinear_u8(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* crops,
+                                  const int32_t* tables, int m, uint8_t* out, int out_h, int out_w, void* stream);
 /* median device time in microseconds of `iters` launches of one conv (CUDA events on `stream`),
  * same arguments as hrnet_conv_bn_act; used by bench.py for the per-kernel roofline. */
 int hrnet_conv_bench(const void* in_nhwc_f16, const void* w_f16, const float* scale, const float* bias,

@@ -66,6 +66,7 @@ SYMBOLS = {
     "hrnet_final_preds": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "hrnet_flip_average": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_int32), _i, _i, _i, _i, _vp, _vp]),
     "hrnet_resize_cubic_u8": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hrnet_crop_resize_bilinear_u8": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _vp]),
     "hrnet_conv_bench": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                               ctypes.POINTER(ctypes.c_float), _vp]),
 }

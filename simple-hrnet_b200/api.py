@@ -21,7 +21,7 @@ class SimpleHRNet:
                  interpolation=None, multiperson=True, return_heatmaps=False, return_bounding_boxes=False,
                  max_batch_size=32, yolo_version='v3', yolo_model_def=None, yolo_class_path=None,
                  yolo_weights_path=None, device=torch.device("cuda"), enable_tensorrt=False, engine_flags=0,
-                 device_preprocess=True, detector=None, device_resize=False):
+                 device_preprocess=True, detector=None, device_resize=False, device_crops=False):
         self.c = c
         self.nof_joints = nof_joints
         self.checkpoint_path = checkpoint_path
@@ -73,6 +73,11 @@ class SimpleHRNet:
         # without its vendor path, one grey level away from the default cv2 call on a few per cent of the pixels -- hence opt-in)
         self._device_resize = bool(device_resize) and self._u8_path
         self._resizer = None
+        # device_crops=True (multiperson, HRNet): the frames go to the device as they are and the per-person crops -- slice,
+        # zero padding, `ToPILImage -> Resize` (Pillow's antialiased bilinear, restated bit for bit), ToTensor, Normalize --
+        # are made there (hrnet_crop_resize_bilinear_u8 + the uint8 stem); boxes outside the frame fall back to the host path
+        self._device_crops = bool(device_crops) and arch == "hrnet" and self.resolution is not None and bool(self.multiperson)
+        self._cropper = None
         self._mp_transform = None
         self._mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(3, 1, 1)
         self._std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(3, 1, 1)
@@ -167,6 +172,19 @@ class SimpleHRNet:
                 transforms.ToTensor(), transforms.Normalize(mean=list(IMAGENET_MEAN), std=list(IMAGENET_STD))])
         return self._mp_transform(crop_rgb)
 
+    def _crops_on_device(self, frames, specs):
+        """uint8 network inputs [m, H, W, 3] (BGR, device) for `specs` = (frame, x1, y1, x2, y2, pads...), or None when a box
+        does not lie inside its frame (numpy's slicing semantics for such boxes stay on the host path)."""
+        FH, FW = frames.shape[1], frames.shape[2]
+        for (_f, x1, y1, x2, y2, *_p) in specs:
+            if not (0 <= x1 < x2 <= FW and 0 <= y1 < y2 <= FH):
+                return None
+        if self._cropper is None:
+            from .preprocess import CropResizer
+            self._cropper = CropResizer(self.device)
+        dev = torch.from_numpy(np.ascontiguousarray(frames)).to(self.device)
+        return self._cropper(dev, specs, self.resolution[0], self.resolution[1])
+
     @staticmethod
     def _rounded_box(det):
         x1, y1, x2, y2 = [int(round(v.item() if hasattr(v, "item") else float(v))) for v in det[:4]]
@@ -180,6 +198,7 @@ class SimpleHRNet:
         m = len(detections) if detections is not None else 0
         boxes = np.empty((m, 4), dtype=np.int32)
         x = torch.empty((m, 3, self.resolution[0], self.resolution[1]))
+        specs, crops = [], []
         for i in range(m):
             x1, y1, x2, y2 = self._rounded_box(detections[i])
             cf = self._aspect(x1, y1, x2, y2)
@@ -192,13 +211,19 @@ class SimpleHRNet:
                 mid, length = x1 + (x2 - x1) // 2, int(round((x2 - x1) * 1 / cf))
                 nx1, nx2 = int(mid - length // 2), int(mid + length // 2)
                 pad = ((0, 0), (abs(nx1 - x1), int(abs(nx2 - x2))), (0, 0))
-            crop = image[y1:y2, x1:x2, ::-1]
-            if pad is not None:
-                crop = np.pad(crop, pad)
-            x[i] = self._crop_to_input(crop)
+            p = pad if pad is not None else ((0, 0), (0, 0), (0, 0))
+            specs.append((0, x1, y1, x2, y2, p[0][0], p[0][1], p[1][0], p[1][1]))
+            crops.append((x1, y1, x2, y2, pad))
             boxes[i] = [nx1, ny1, nx2, ny2]
+        x_u8 = self._crops_on_device(image[None], specs) if (getattr(self, "_device_crops", False) and m > 0) else None
+        if x_u8 is None:
+            for i, (x1, y1, x2, y2, pad) in enumerate(crops):
+                crop = image[y1:y2, x1:x2, ::-1]
+                if pad is not None:
+                    crop = np.pad(crop, pad)
+                x[i] = self._crop_to_input(crop)
         if m > 0:
-            heatmaps, pts = self._run(x, boxes)
+            heatmaps, pts = self._run_u8(x_u8, boxes) if x_u8 is not None else self._run(x, boxes)
         else:
             heatmaps = np.zeros((0, self.nof_joints, self.resolution[0] // 4, self.resolution[1] // 4), dtype=np.float32)
             pts = np.empty((0, 0, 3), dtype=np.float32)                  # SimpleHRNet.py:331
@@ -210,6 +235,7 @@ class SimpleHRNet:
         boxes = np.empty((m, 4), dtype=np.int32)
         x = torch.empty((m, 3, self.resolution[0], self.resolution[1]))
         base = 0
+        specs = []
         for d, detections in enumerate(image_detections):
             image = images[d]
             if detections is None or len(detections) == 0:
@@ -224,11 +250,15 @@ class SimpleHRNet:
                     mid, length = x1 + (x2 - x1) // 2, int(round((x2 - x1) * 1 / cf))
                     x1, x2 = max(0, mid - length // 2), min(image.shape[1], mid + length // 2)
                 boxes[base + i] = [x1, y1, x2, y2]
-                x[base + i] = self._crop_to_input(image[y1:y2, x1:x2, ::-1])
+                specs.append((d, x1, y1, x2, y2, 0, 0, 0, 0))
             base += len(detections)
+        x_u8 = self._crops_on_device(images, specs) if (getattr(self, "_device_crops", False) and m > 0) else None
+        if x_u8 is None:
+            for i, (d, x1, y1, x2, y2, *_p) in enumerate(specs):
+                x[i] = self._crop_to_input(images[d][y1:y2, x1:x2, ::-1])
         J, Hh, Wh = self.nof_joints, self.resolution[0] // 4, self.resolution[1] // 4
         if m > 0:
-            heatmaps, pts = self._run(x, boxes)
+            heatmaps, pts = self._run_u8(x_u8, boxes) if x_u8 is not None else self._run(x, boxes)
             hm_b, box_b, pts_b, index = [], [], [], 0
             for detections in image_detections:                          # re-add the per-frame axis (:448-470)
                 k = len(detections) if detections is not None else 0

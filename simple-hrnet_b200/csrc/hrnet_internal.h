@@ -301,8 +301,8 @@ struct HeadParams {
   float* pval;
   int* pidx;
   int N, HW, Cin, J, nblk, pad_;
+  const float* w_dev;                // [J][Cin] fp32 weights in the plan's weight buffer (staged in shared memory per block)
   float bias[kHeadMaxJc];
-  float w[kHeadMaxW];                // [J][Cin]
 };
 int head_c_blocks(int hw);                   // argmax candidates per (person, joint): blocks of 512 pixels
 bool head_c_supported(int cin, int nj);     // shapes with a compiled specialisation (HRNet-W48 / W32, 17 joints)
@@ -317,6 +317,8 @@ cudaError_t launch_final_preds(const float* hm, int N, int J, int Hh, int Wh, in
                                float* maxvals, cudaStream_t st);
 cudaError_t launch_flip_average(const float* a, const float* b, float* out, const int* perm, int N, int J, int Hh, int Wh,
                                 cudaStream_t st);
+cudaError_t launch_crop_resize_bilinear_u8(const uint8_t* frames, int FH, int FW, const int32_t* desc, const int32_t* tables,
+                                           int m, uint8_t* out, int OH, int OW, cudaStream_t st);
 cudaError_t launch_resize_cubic_u8(const uint8_t* src, uint8_t* dst, int n, int sh, int sw, int dh, int dw, const int32_t* xofs,
                                    const int16_t* xcoef, const int32_t* yofs, const int16_t* ycoef, cudaStream_t st);
 cudaError_t launch_maxpool(const __half* in, __half* out, int N, int IH, int IW, int C, cudaStream_t st);

@@ -1751,7 +1751,7 @@ int launch_op(HrnetPlan* P, const Op& op, int n, const float* in_ext, float* hm_
         hp.pidx = no_hm ? (int*)(P->abase + P->off_pidx) : nullptr;
         hp.N = n; hp.HW = ti.H * ti.W; hp.Cin = op.cin; hp.J = op.cout; hp.nblk = P->head_nblk; hp.pad_ = 0;
         memcpy(hp.bias, P->head_b.data(), P->head_b.size() * 4);
-        memcpy(hp.w, P->head_w.data(), P->head_w.size() * 4);
+        hp.w_dev = (const float*)(P->wbase + pi.w_offset);
         CK(launch_head_c(hp, st));
         return 0;
       }
@@ -2335,6 +2335,15 @@ int hrnet_resize_cubic_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* ds
   if (n == 0) return HRNET_OK;
   if (!src || !dst || !xofs || !xcoef || !yofs || !ycoef) return fail(HRNET_E_INVALID, "null argument");
   CK(launch_resize_cubic_u8(src, dst, n, sh, sw, dh, dw, xofs, xcoef, yofs, ycoef, (cudaStream_t)stream));
+  return HRNET_OK;
+}
+
+int hrnet_crop_resize_bilinear_u8(const uint8_t* frames, int n_frames, int frame_h, int frame_w, const int32_t* crops,
+                                  const int32_t* tables, int m, uint8_t* out, int out_h, int out_w, void* stream) {
+  if (n_frames <= 0 || frame_h <= 0 || frame_w <= 0 || m < 0 || out_h <= 0 || out_w <= 0) return fail(HRNET_E_INVALID, "bad shape");
+  if (m == 0) return HRNET_OK;
+  if (!frames || !crops || !tables || !out) return fail(HRNET_E_INVALID, "null argument");
+  CK(launch_crop_resize_bilinear_u8(frames, frame_h, frame_w, crops, tables, m, out, out_h, out_w, (cudaStream_t)stream));
   return HRNET_OK;
 }
 

@@ -387,17 +387,18 @@ argmax_decode_kernel(const float* __restrict__ hm, int J, int Hh, int Wh, const 
 // costs four L1 wavefronts even when every lane reads the same address -> 0.23 of the HBM roofline); here the weights
 // are kernel parameters: every FMA's second operand comes from the constant bank.  Same accumulation order as
 // head_conv1x1_kernel -> bit-identical heat-map values.  grid = (blocks of 128 pixels, person).
-// Every thread owns kHeadPix pixels: a broadcast shared-memory read of the weights (four L1 wavefronts per LDS.128) feeds
-// kHeadPix x 4 FMAs per lane instead of 4 -- head_conv1x1_kernel is bound by exactly those reads (816 wavefronts per 32
-// pixels = 42 us).  Weights straight from the constant bank were slower: one uniform load per FMA and warp 86 us, with four
-// pixels per thread still 64 us (the uniform loads are a latency chain; profiles/r02_s28_head_stem.log, r02_s29_*.log).
-constexpr int kHeadPix = 4;
+// head_conv1x1_kernel is bound by the shared-memory broadcast reads of its weights (816 L1 wavefronts per 32 pixels = 42 us
+// at W48 / 64 crops), not by HBM.  What was tried against that, all slower on B200 (profiles/r02_s28_head_stem.log,
+// r02_s29_head_four_pixels.log): weights from the constant bank (one uniform load per FMA: 86 us; four pixels per thread:
+// 64 us -- the uniform loads form a latency chain) and four pixels per thread with shared-memory weights (76 us: 135
+// registers, 896 blocks = 2.02 waves).  Kept: the original mapping (kHeadPix = 1) with the argmax candidates fused in.
+constexpr int kHeadPix = 1;
 template <int CIN, int NJ>
 __global__ void __launch_bounds__(128) head_c_kernel(const __grid_constant__ HeadParams p) {
   const int n = blockIdx.y;
   const int hw0 = (int)blockIdx.x * (128 * kHeadPix) + (int)threadIdx.x;      // pixels hw0 + 128 * i
   __shared__ __align__(16) float shw[NJ * CIN];
-  for (int i = threadIdx.x; i < NJ * CIN; i += 128) shw[i] = p.w[i];
+  for (int i = threadIdx.x; i < NJ * CIN; i += 128) shw[i] = __ldg(p.w_dev + i);      // (per-lane indexed reads of the constant bank serialise)
   __syncthreads();
   float acc[kHeadPix][NJ];
 #pragma unroll
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(128) head_c_kernel(const __grid_constant__ Hea
   }
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const float bj = p.bias[j];
+    const float bj = p.bias[j];      // (compile-time index: a constant-bank operand)
 #pragma unroll
     for (int i = 0; i < kHeadPix; ++i) acc[i][j] += bj;
   }
@@ -451,22 +452,22 @@ __global__ void __launch_bounds__(128) head_c_kernel(const __grid_constant__ Hea
   __shared__ float sv[4][NJ];
   __shared__ int si[4][NJ];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp stage with the hardware reduction (redux.sync) on an order-preserving 32-bit key: NaN -> the largest key (a NaN
+  // is np.argmax's maximum), -0.0 == +0.0 (same key), ties -> the lowest lane = the lowest pixel index of the warp.
+  // (Five shuffle rounds of (value, index) pairs per joint cost more than the 816 FMAs of the head itself.)
+  static_assert(kHeadPix == 1, "the warp stage assumes one pixel per lane, consecutive lanes = consecutive pixels");
+  const bool valid0 = hw0 < p.HW;
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    float best = 0.f;
-    int bi = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < kHeadPix; ++i) {
-      const int hw = hw0 + 128 * i;
-      if (hw < p.HW && (bi == 0x7fffffff || better(acc[i][j], hw, best, bi))) { best = acc[i][j]; bi = hw; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (oi != 0x7fffffff && (bi == 0x7fffffff || better(ob, oi, best, bi))) { best = ob; bi = oi; }
-    }
-    if (lane == 0) { sv[warp][j] = best; si[warp][j] = bi; }
+    const float v = acc[0][j];
+    const uint32_t u = __float_as_uint(v + 0.f);                      // -0.0 + 0.0 = +0.0
+    uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);        // monotone in v for non-NaN
+    if (v != v) key = 0xffffffffu;
+    if (!valid0) key = 0u;                                            // (below every real key: ~(-NaN bits) is >= 0x00400000)
+    const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+    const uint32_t who = __ballot_sync(0xffffffffu, key == kmax && valid0);
+    if (who != 0u && lane == __ffs((int)who) - 1) { sv[warp][j] = v; si[warp][j] = hw0; }
+    else if (who == 0u && lane == 0) { sv[warp][j] = 0.f; si[warp][j] = 0x7fffffff; }
   }
   __syncthreads();
   if ((int)threadIdx.x < NJ) {
@@ -806,6 +807,68 @@ cudaError_t launch_resize_cubic_u8(const uint8_t* src, uint8_t* dst, int n, int 
   const long total = (long)n * dh * dw;
   if (total == 0) return cudaSuccess;
   resize_cubic_u8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, dst, n, sh, sw, dh, dw, xofs, xcoef, yofs, ycoef);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ multi-person crops
+// `ToPILImage -> Resize((H, W))` of the reference's crop transform (SimpleHRNet.py:166-171) = Pillow's antialiased
+// bilinear resample of an 8-bit image (libImaging/Resample.c: horizontal pass rounded to uint8, then vertical pass; both
+// with 22-bit fixed-point coefficients and a rounding shift) applied to `image[y1:y2, x1:x2]` (+ zero padding,
+// SimpleHRNet.py:262-270).  One thread = one output pixel (3 channels); the horizontal pass of the rows a pixel needs is
+// recomputed (ky x kx taps, a few dozen integer MACs).  desc[m][kCropDescInts]:
+//   0 frame | 1,2 x0, y0: frame coordinates of the padded crop's top-left | 3..6 the frame rectangle [vx0, vx1) x [vy0, vy1)
+//   that holds image data (zero outside) | 7,8 offsets (ints) of the x / y tables | 9,10 taps per output coordinate kx, ky
+// tables (int32): per axis [out][2] (first source index, tap count) followed by [out][k] coefficients
+// (simple_hrnet_b200.preprocess.pil_bilinear_tables restates Pillow's precompute_coeffs / normalize_coeffs_8bpc).
+constexpr int kCropDescInts = 12;
+__global__ void __launch_bounds__(256)
+crop_resize_bilinear_u8_kernel(const uint8_t* __restrict__ frames, int FH, int FW, const int32_t* __restrict__ desc,
+                               const int32_t* __restrict__ tables, uint8_t* __restrict__ out, int OH, int OW) {
+  const int m = blockIdx.y;
+  const int t = (int)blockIdx.x * 256 + (int)threadIdx.x;
+  if (t >= OH * OW) return;
+  const int oy = t / OW, ox = t - oy * OW;
+  const int32_t* d = desc + (size_t)m * kCropDescInts;
+  const int frame = d[0], x0 = d[1], y0 = d[2], vx0 = d[3], vy0 = d[4], vx1 = d[5], vy1 = d[6];
+  const int kx = d[9], ky = d[10];
+  const int32_t* bx = tables + d[7];
+  const int32_t* cx = bx + 2 * OW + (size_t)ox * kx;
+  const int32_t* by = tables + d[8];
+  const int32_t* cy = by + 2 * OH + (size_t)oy * ky;
+  const int xmin = bx[2 * ox], nx = bx[2 * ox + 1];
+  const int ymin = by[2 * oy], ny = by[2 * oy + 1];
+  const uint8_t* img = frames + (size_t)frame * FH * FW * 3;
+  constexpr int kHalf = 1 << 21;
+  int acc[3] = {kHalf, kHalf, kHalf};
+  for (int ty = 0; ty < ny; ++ty) {
+    const int fy = y0 + ymin + ty;
+    int h[3] = {kHalf, kHalf, kHalf};
+    if (fy >= vy0 && fy < vy1) {
+      const uint8_t* row = img + (size_t)fy * FW * 3;
+      for (int tx = 0; tx < nx; ++tx) {
+        const int fx = x0 + xmin + tx;
+        if (fx >= vx0 && fx < vx1) {
+          const int k = __ldg(cx + tx);
+          h[0] += (int)__ldg(row + 3 * fx + 0) * k;
+          h[1] += (int)__ldg(row + 3 * fx + 1) * k;
+          h[2] += (int)__ldg(row + 3 * fx + 2) * k;
+        }
+      }
+    }
+    const int k = __ldg(cy + ty);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += min(max(h[c] >> 22, 0), 255) * k;
+  }
+  uint8_t* o = out + (((size_t)m * OH + oy) * OW + ox) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = (uint8_t)min(max(acc[c] >> 22, 0), 255);
+}
+
+cudaError_t launch_crop_resize_bilinear_u8(const uint8_t* frames, int FH, int FW, const int32_t* desc, const int32_t* tables,
+                                           int m, uint8_t* out, int OH, int OW, cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  crop_resize_bilinear_u8_kernel<<<dim3((unsigned)((OH * OW + 255) / 256), (unsigned)m), 256, 0, st>>>(frames, FH, FW, desc, tables,
+                                                                                                      out, OH, OW);
   return cudaGetLastError();
 }
 

@@ -98,3 +98,118 @@ class CubicResizer:
                                             _vp(xa.data_ptr()), _vp(yo.data_ptr()), _vp(ya.data_ptr()),
                                             _vp(torch.cuda.current_stream(self.device).cuda_stream)), lib)
         return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Multi-person crops: `ToPILImage -> Resize((H, W))` of SimpleHRNet.py:166-171 is Pillow's
+# antialiased bilinear resample of an 8-bit image (ImagingResample, libImaging/Resample.c): per axis a triangle filter
+# whose support grows with the down-scale factor, coefficients normalised in double precision and rounded to 22-bit
+# fixed point, a horizontal pass rounded to uint8, then a vertical pass.  `pil_bilinear_tables` restates the coefficient
+# builder (precompute_coeffs + normalize_coeffs_8bpc), `resize_pil_bilinear_reference` the two passes; the CPU tests pin
+# both against Pillow itself, the CUDA kernel (hrnet_crop_resize_bilinear_u8) evaluates the same integers.
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def pil_bilinear_tables(in_size, out_size):
+    """(bounds [out, 2] int32 = (first source index, tap count), coefficients [out, ksize] int32) for one axis."""
+    scale = float(in_size) / float(out_size)
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale                      # bilinear: support 1.0
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)           # C cast: truncation (the argument is never below -0.5 ... see max)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        w = np.zeros(ksize, dtype=np.float64)
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            if a < 0.0:
+                a = -a
+            v = 1.0 - a if a < 1.0 else 0.0
+            w[x] = v
+            ww += v
+        if ww != 0.0:
+            for x in range(xmax):
+                w[x] /= ww
+        for x in range(ksize):
+            p = w[x] * float(1 << PIL_PRECISION_BITS)
+            kk[xx, x] = int(-0.5 + p) if w[x] < 0 else int(0.5 + p)
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk
+
+
+def resize_pil_bilinear_reference(img_u8, out_h, out_w):
+    """numpy restatement of Image.resize((out_w, out_h), BILINEAR) for an HxWxC uint8 image (horizontal pass first)."""
+    img = np.asarray(img_u8)
+    h, w, c = img.shape
+    half = 1 << (PIL_PRECISION_BITS - 1)
+    tmp = img
+    if out_w != w:
+        bx, kx = pil_bilinear_tables(w, out_w)
+        tmp = np.empty((h, out_w, c), dtype=np.uint8)
+        for xx in range(out_w):
+            x0, n = int(bx[xx, 0]), int(bx[xx, 1])
+            acc = (img[:, x0:x0 + n, :].astype(np.int64) * kx[xx, :n].astype(np.int64)[None, :, None]).sum(1) + half
+            tmp[:, xx, :] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255)
+    out = tmp
+    if out_h != h:
+        by, ky = pil_bilinear_tables(h, out_h)
+        out = np.empty((out_h, tmp.shape[1], c), dtype=np.uint8)
+        for yy in range(out_h):
+            y0, n = int(by[yy, 0]), int(by[yy, 1])
+            acc = (tmp[y0:y0 + n].astype(np.int64) * ky[yy, :n].astype(np.int64)[:, None, None]).sum(0) + half
+            out[yy] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255)
+    return out
+
+
+class CropResizer:
+    """Device-side `image[y1:y2, x1:x2]` (+ zero padding) -> Pillow bilinear resize to the network resolution for a list of
+    boxes (hrnet_crop_resize_bilinear_u8).  Tables are cached per source extent."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.lib = load_library()
+        self._cache = {}
+
+    def _axis(self, in_size, out_size):
+        key = (in_size, out_size)
+        if key not in self._cache:
+            b, k = pil_bilinear_tables(in_size, out_size)
+            self._cache[key] = (np.concatenate([b.reshape(-1), k.reshape(-1)]).astype(np.int32), k.shape[1])
+        return self._cache[key]
+
+    def __call__(self, frames_dev, specs, out_h, out_w):
+        """frames_dev: uint8 [F, FH, FW, 3] on the device.  specs: list of (frame, x1, y1, x2, y2, pad_top, pad_bottom,
+        pad_left, pad_right) with the box inside the frame.  Returns uint8 [m, out_h, out_w, 3] on the device."""
+        m = len(specs)
+        out = torch.empty((m, out_h, out_w, 3), dtype=torch.uint8, device=self.device)
+        if m == 0:
+            return out
+        F, FH, FW, _ = frames_dev.shape
+        desc = np.zeros((m, 12), dtype=np.int32)
+        chunks, off = [], 0
+        for i, (f, x1, y1, x2, y2, pt, pb, pl, pr) in enumerate(specs):
+            if not (0 <= x1 < x2 <= FW and 0 <= y1 < y2 <= FH and 0 <= f < F):
+                raise ValueError("crop box outside the frame")
+            cw, ch = (x2 - x1) + pl + pr, (y2 - y1) + pt + pb
+            tx, kx = self._axis(cw, out_w)
+            ty, ky = self._axis(ch, out_h)
+            desc[i] = [f, x1 - pl, y1 - pt, x1, y1, x2, y2, off, off + tx.size, kx, ky, 0]
+            chunks += [tx, ty]
+            off += tx.size + ty.size
+        tables = torch.from_numpy(np.concatenate(chunks)).to(self.device)
+        desc_d = torch.from_numpy(desc).to(self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.hrnet_crop_resize_bilinear_u8(frames_dev.data_ptr(), F, FH, FW, desc_d.data_ptr(), tables.data_ptr(), m,
+                                                         out.data_ptr(), out_h, out_w,
+                                                         torch.cuda.current_stream(self.device).cuda_stream), self.lib)
+        return out

@@ -344,3 +344,38 @@ def test_fused_head_argmax_equals_separate_kernels():
         assert np.array_equal(i0, i1) and np.array_equal(np.nan_to_num(j0, nan=-7.0), np.nan_to_num(j1, nan=-7.0)), name
         assert h1 is not None and h1.shape == (5, 17, 32, 24)
         e.close()
+
+
+class _BoxDetector:
+    """Stands in for the reference's YOLO wrappers (models_/detectors/YOLOv3.py:88,117): fixed boxes per frame."""
+
+    def __init__(self, per_frame):
+        self.per_frame = per_frame
+
+    def predict_single(self, image):
+        return [torch.tensor(b, dtype=torch.float32) for b in self.per_frame[0]]
+
+    def predict(self, images):
+        return [[torch.tensor(b, dtype=torch.float32) for b in self.per_frame[i % len(self.per_frame)]] for i in range(len(images))]
+
+
+def test_multiperson_device_crops_equal_host_crops():
+    """`SimpleHRNet(multiperson=True, device_crops=True)`: crops, zero padding, Pillow resize, ToTensor and Normalize on the
+    device give the same network inputs as the reference's host transform, hence the same joints / boxes -- single frame
+    (padding branch, SimpleHRNet.py:244-276) and a stack of frames (clamped enlargement, :395-405)."""
+    sd = O.make_state_dict(O.hrnet_param_spec(32, 17), seed=2, bn="random")
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (2, 300, 400, 3), dtype=np.uint8)
+    det = _BoxDetector([[[20.2, 30.7, 140.1, 280.9, 0.9], [200.0, 50.0, 380.0, 120.0, 0.8], [150.4, 10.2, 190.6, 290.0, 0.7]],
+                        [[5.0, 5.0, 395.0, 295.0, 0.9]]])
+    kw = dict(model_name="HRNet", resolution=(128, 96), multiperson=True, return_bounding_boxes=True, max_batch_size=4,
+              device=torch.device("cuda:0"), detector=det)
+    host = SimpleHRNet(32, 17, sd, **kw)
+    dev = SimpleHRNet(32, 17, sd, device_crops=True, **kw)
+    for inp in (frames[0], frames):
+        bh, ph = host.predict(inp)
+        bd, pd = dev.predict(inp)
+        if inp.ndim == 3:
+            assert np.array_equal(bh, bd) and np.array_equal(ph, pd)
+        else:
+            assert all(np.array_equal(a, b) for a, b in zip(bh, bd)) and all(np.array_equal(a, b) for a, b in zip(ph, pd))

@@ -251,3 +251,27 @@ def test_device_cubic_resize_equals_opencv_kernel(shape):
     finally:
         cv2.setUseOptimized(was)
     assert np.array_equal(out, want)
+
+
+def test_device_crops_equal_pillow_resize():
+    """hrnet_crop_resize_bilinear_u8: `image[y1:y2, x1:x2]` (+ zero padding) -> `ToPILImage -> Resize((H, W))` of the
+    reference's multi-person crop transform (SimpleHRNet.py:166-171, 244-276) on the device == Pillow, bit for bit; boxes
+    of every aspect, up- and down-scaling, crops touching the frame border, several frames."""
+    from PIL import Image
+    from simple_hrnet_b200.preprocess import CropResizer
+    rng = np.random.default_rng(9)
+    frames = rng.integers(0, 256, (3, 480, 640, 3), dtype=np.uint8)
+    frames[1, :160] = 255; frames[1, 160:320] = 0
+    specs = [(0, 10, 20, 210, 420, 0, 0, 0, 0), (0, 0, 0, 640, 480, 0, 0, 0, 0), (1, 300, 100, 340, 400, 0, 0, 93, 92),
+             (1, 100, 200, 500, 260, 236, 237, 0, 0), (2, 600, 440, 640, 480, 0, 0, 0, 0), (2, 5, 7, 28, 37, 0, 0, 0, 1),
+             (0, 17, 33, 305, 417, 0, 0, 0, 0), (2, 0, 100, 639, 479, 3, 0, 0, 0)]
+    dev = torch.from_numpy(frames).cuda()
+    cr = CropResizer(torch.device("cuda:0"))
+    for (oh, ow) in ((384, 288), (256, 192)):
+        out = cr(dev, specs, oh, ow).cpu().numpy()
+        for i, (f, x1, y1, x2, y2, pt, pb, pl, pr) in enumerate(specs):
+            crop = np.pad(frames[f][y1:y2, x1:x2], ((pt, pb), (pl, pr), (0, 0)))
+            want = np.asarray(Image.fromarray(np.ascontiguousarray(crop)).resize((ow, oh), Image.BILINEAR))
+            assert np.array_equal(out[i], want), (i, oh, ow, int(np.abs(out[i].astype(int) - want.astype(int)).max()))
+    with pytest.raises(ValueError):
+        cr(dev, [(0, -3, 0, 10, 10, 0, 0, 0, 0)], 384, 288)

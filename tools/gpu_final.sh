@@ -13,15 +13,15 @@ import json; d=json.load(open('gpurun_out/bench.json')); print('BENCH', d['value
 tail -3 gpurun_out/bench.err
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
    --log-file gpurun_out/launches.csv python tools/profile_forward.py 64 > gpurun_out/prof_forward.log 2>&1; echo "ncu launches rc=$?"
-# ncu --set full of the stage-4.0 kernels + the HBM-bound ends.  A forward has 18 halo-patch chains (stage4.0 = launches
-# 10-11), 10 im2col chains (stage4.0 = 4-5), 8 exchange units (stage4.0 = 5), 23 sums (stage4.0 = 14-17).
+# ncu --set full of the stage-4.0 kernels + the HBM-bound ends.  A forward has 16 halo-patch chains (stage4.0 = launches
+# 10-11), 10 im2col chains (stage4.0 = 4-5), 20 exchange units (stage4.0 = 12-15), 23 sums (stage4.0 = 14-17).
 prof() { timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"$1" -s $2 -c $3 \
    -o gpurun_out/prof_$4 -f python tools/profile_forward.py 64 > gpurun_out/prof_$4.log 2>&1; echo "ncu $4 rc=$?"; }
 prof "conv_chain_patch" 10 2 chain_patch
 prof "conv_chain_igemm" 4 2 chain_igemm
-prof "conv_xunit" 5 1 xunit
+prof "conv_xunit" 12 4 xunit
 prof "fuse_sum" 14 4 fuse
-prof "argmax_decode|head_conv1x1|stem_conv3x3s2_tc" 0 3 ends
+prof "head_c_kernel|head_argmax_finish|stem_conv3x3s2_tc" 0 3 ends
 timeout 300 python tools/op_roofline.py > gpurun_out/op_roofline.txt 2>&1
 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 3 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/racecheck.log
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 3 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/memcheck.log

@@ -44,6 +44,10 @@ def alg_bytes(name, idx_of_kind):
         return None      # filled from the grid: see below
     if "fuse_sum" in name:
         return None
+    if "head_argmax_finish" in name:
+        return n * 17 * 54 * 8 + n * 204
+    if "head_c_kernel" in name:           # fused with the argmax: reads the 48-channel map, writes 54 candidates per joint
+        return n * 96 * 72 * 48 * 2 + n * 17 * 54 * 8
     if "argmax" in name:
         return n * (4 * 17 * 96 * 72 + 204)
     if "head_conv1x1" in name:
