@@ -1,0 +1,9 @@
+#!/bin/bash
+# Round 2, session 28: head with constant-bank weights + fused argmax, software-pipelined stem gather.
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x --timeout=600 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python tools/op_roofline.py > gpurun_out/op_roofline.txt 2>&1; grep "^conv1 \|final_layer\|argmax\|serial total" gpurun_out/op_roofline.txt
+timeout 300 python tools/chain_probe.py dual 2>/dev/null | grep "one forward"
+timeout 600 python bench.py --config w48 --steps 20 --warmup 5 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('BENCH', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'])"
