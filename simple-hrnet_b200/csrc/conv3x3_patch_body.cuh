@@ -51,12 +51,13 @@ struct PatchMaps {
 
 // All MMAs of one channel chunk: tap (r, s) = the same patch viewed from pixel row r * 10 + s (8-row core groups are one
 // patch row apart); K advances 32 B (+2 in the descriptor's address field) per K16 step.
-template <int NK, bool kPair>
+// kRowUnits: 16-byte units per patch row (8 = 128-byte rows, 4 = 64-byte rows of a 32-channel slot)
+template <int NK, bool kPair, int kRowUnits = 8>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint64_t a0, uint64_t b0, uint32_t bstep, uint32_t idesc,
                                            uint32_t accumulate_first) {
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
-    const uint64_t at = a0 + (uint64_t)(((t / 3) * kPatchPW + (t % 3)) * 8);
+    const uint64_t at = a0 + (uint64_t)(((t / 3) * kPatchPW + (t % 3)) * kRowUnits);
     const uint64_t bt = b0 + (uint64_t)(t * bstep);
 #pragma unroll
     for (int k = 0; k < NK; ++k) {

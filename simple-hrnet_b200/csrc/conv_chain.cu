@@ -335,14 +335,15 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const __gri
       e.row_off = (size_t)m * p.C + n0;
       e.ch0 = n0; e.ncols = p.n_tile; e.relu = cv.relu; e.out_f32 = 0; e.valid = m < p.M_total;
       U256 rres[4];
-      if (p.skip == 0 || p.skip == 3) chain_load_residual(rres, e, 0);
+      const int eskip = p.skip >= 8 ? 0 : p.skip;      // (8, 9 select other experiments)
+      if (eskip == 0 || eskip == 3) chain_load_residual(rres, e, 0);
       long long tq = p.dbg ? clock64() : 0;
       ptx::mbar_wait(ptx::smem_u32(&bars->tmem_full[accb]), acc_phase);
       if (p.dbg) { const long long t = clock64(); dbg_wait += t - tq; tq = t; }
       ptx::tc_fence_after_sync();
-      if (p.skip == 0) {
+      if (eskip == 0) {
         chain_store_row_c(rres, e, t_row, p.sb[k]);
-      } else if (p.skip == 2) {            // experiment (results invalid): accumulator loads only
+      } else if (eskip == 2) {            // experiment (results invalid): accumulator loads only
         uint32_t acc = 0;
         for (int c = 0; c < e.ncols; c += 16) {
           uint32_t v[16];
@@ -352,7 +353,7 @@ conv_chain_igemm_kernel(const __grid_constant__ ChainIgemmMaps maps, const __gri
           for (int i = 0; i < 16; ++i) acc ^= v[i];
         }
         if (acc == 0x12345679u && e.valid) reinterpret_cast<__half*>(e.out)[e.row_off] = __float2half(0.f);
-      } else if (p.skip == 3) {            // experiment (results invalid): residual loads and output stores only
+      } else if (eskip == 3) {            // experiment (results invalid): residual loads and output stores only
         if (e.valid)
           for (int c = 0; c < e.ncols; c += 64) {
             if (c) chain_load_residual(rres, e, c);
@@ -422,7 +423,9 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const __gri
 
   const uint32_t b_base = smem_base;
   const uint32_t a_base = smem_base + (uint32_t)p.b_bytes;
-  ChainPatchBars* bars = reinterpret_cast<ChainPatchBars*>(smem_aligned + (size_t)p.b_bytes + (size_t)p.nslots * p.slot_bytes);
+  // tail64: two 128-byte-row slots + one 64-byte-row slot (180 x 64 B rounded up to 12 KB) instead of p.nslots equal slots
+  const size_t slots_bytes = cp.tail64 ? (size_t)2 * p.slot_bytes + 12288u : (size_t)p.nslots * p.slot_bytes;
+  ChainPatchBars* bars = reinterpret_cast<ChainPatchBars*>(smem_aligned + (size_t)p.b_bytes + slots_bytes);
   const int n_issuers = p.mma_warps == 2 ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
@@ -431,7 +434,7 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const __gri
     }
     ptx::mbar_init(ptx::smem_u32(&bars->b_full), 1);
     ptx::mbar_init(ptx::smem_u32(&bars->b_empty), (uint32_t)n_issuers);
-    for (int i = 0; i < p.nslots; ++i) {
+    for (int i = 0; i < (cp.tail64 ? 3 : p.nslots); ++i) {
       ptx::mbar_init(ptx::smem_u32(&bars->a_full[i]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->a_empty[i]), 1);
     }
@@ -540,6 +543,22 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const __gri
         const int w = nw == 2 ? (it & 1) : 0;
         const int sbase = w * ring;
         const int img = (int)(coord >> 16), th = (int)((coord >> 8) & 255u), tw = (int)(coord & 255u);
+        if (cp.tail64) {
+          // three slots: chunk 0 (64 channels, 128-byte rows) alternates between slots 0 and 2, chunk 1 (32 channels,
+          // 64-byte rows) lives in slot 1 -- the next tile's chunk 0 loads while this tile's is still being multiplied
+          const int s0 = (it & 1) ? 2 : 0;
+          const uint32_t a1_off = 2u * (uint32_t)p.slot_bytes;                       // slot 1 sits behind the two wide slots
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[s0]), (uint32_t)((it >> 1) & 1) ^ 1u);
+          uint32_t full = ptx::smem_u32(&bars->a_full[s0]);
+          ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 128));
+          ptx::tma_load_4d(a_base + (uint32_t)((s0 >> 1) * p.slot_bytes), &maps.a[k], full, p.c0[0], tw * kPatchTW - 1,
+                           th * kPatchTH - 1, img);
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[1]), (uint32_t)(it & 1) ^ 1u);
+          full = ptx::smem_u32(&bars->a_full[1]);
+          ptx::mbar_expect_tx(full, (uint32_t)(kPatchRows * 64));
+          ptx::tma_load_4d(a_base + a1_off, &maps.a2[k], full, p.c0[1], tw * kPatchTW - 1, th * kPatchTH - 1, img);
+          continue;
+        }
         for (int j = 0; j < p.nchunks; ++j) {
           const int L = w ? L1++ : L0++;
           const int slot = sbase + L % ring;
@@ -581,6 +600,46 @@ conv_chain_patch_kernel(const __grid_constant__ ChainPatchMaps maps, const __gri
       // their ~150 clk answers arrive under the MMAs.  The general loop below re-reads every chunk constant from the
       // constant bank and pays each barrier round trip serially: ~800 clk per 27-MMA tile (profiles/r02_s16_*.log:
       // a single issuer needed 2,220 clk per C = 48 tile, 82 clk per MMA, where the tensor pipe needs 44).
+      if (cp.tail64) {
+        // three-slot layout (see the producer): chunk 0 from slot 0 / 2 (tile parity), chunk 1 from the 64-byte-row slot 1
+        const uint64_t a_hi = ptx::umma_desc_kmajor(0u, 128u, (uint32_t)kPatchPW * 128u);
+        const uint64_t a_hi64 = ptx::umma_desc_kmajor(0u, 64u, (uint32_t)kPatchPW * 64u);
+        const uint32_t enc_s0 = (a_base & 0x3FFFFu) >> 4, enc_s2 = ((a_base + (uint32_t)p.slot_bytes) & 0x3FFFFu) >> 4;
+        const uint32_t enc_s1 = ((a_base + 2u * (uint32_t)p.slot_bytes) & 0x3FFFFu) >> 4;
+        const uint32_t brow0 = (uint32_t)p.bkc[0] * 2u, brow1 = (uint32_t)p.bkc[1] * 2u;
+        const uint64_t bd0 = ptx::umma_desc_kmajor(b_base + (uint32_t)p.boff[0], brow0, 8u * brow0);
+        const uint64_t bd1 = ptx::umma_desc_kmajor(b_base + (uint32_t)p.boff[1], brow1, 8u * brow1);
+        const uint32_t bs0 = (uint32_t)p.bblk[0] >> 4, bs1 = (uint32_t)p.bblk[1] >> 4;
+        const uint32_t afull0 = ptx::smem_u32(&bars->a_full[0]), aempty0 = ptx::smem_u32(&bars->a_empty[0]);
+        const uint32_t tfull0 = ptx::smem_u32(&bars->tmem_full[0]), tempty0 = ptx::smem_u32(&bars->tmem_empty[0]);
+        const int nacc_mask = p.nacc - 1, nacc_log2 = p.nacc_log2;
+        for (int it = 0;; ++it) {
+          const uint32_t info = rr.next();
+          if (info == kChainDone) break;
+          const int k = (int)(info >> 28);
+          if (k != cur_k) {                   // (see the general loop)
+            cur_k = k;
+            ptx::mma_commit(bempty);
+            ++nswitch;
+            ptx::mbar_wait(bfull, (uint32_t)(nswitch & 1));
+            ptx::tc_fence_after_sync();
+          }
+          const int acc = it & nacc_mask;
+          ptx::mbar_wait(tempty0 + 8u * (uint32_t)acc, (uint32_t)((it >> nacc_log2) & 1) ^ 1u);
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+          const int s0 = (it & 1) ? 2 : 0;
+          ptx::mbar_wait(afull0 + 8u * (uint32_t)s0, (uint32_t)((it >> 1) & 1));
+          ptx::tc_fence_after_sync();
+          issue_taps<4, false>(d_tmem, a_hi | (uint64_t)(s0 ? enc_s2 : enc_s0), bd0, bs0, idesc, 0u);
+          ptx::mma_commit(aempty0 + 8u * (uint32_t)s0);
+          ptx::mbar_wait(afull0 + 8u, (uint32_t)(it & 1));
+          ptx::tc_fence_after_sync();
+          issue_taps<2, false, 4>(d_tmem, a_hi64 | (uint64_t)enc_s1, bd1, bs1, idesc, 1u);
+          ptx::mma_commit(aempty0 + 8u);
+          ptx::mma_commit(tfull0 + 8u * (uint32_t)acc);
+        }
+      } else
       if (p.nchunks <= 2 && cp.skip != 9) {      // (skip == 9: experiment, the general loop)
         const int nch = p.nchunks;
         const uint64_t a_hi = ptx::umma_desc_kmajor(0u, 128u, (uint32_t)kPatchPW * 128u);

@@ -162,6 +162,8 @@ struct ChainPatchParams {
   int unit_stride;           // counters per conv (tile rows at max batch)
   int chunk;                 // tiles per ticket: a divisor of pp.tiles_w (neighbouring tiles of one tile row)
   int skip;                  // experiments only (HRNET_TUNE_CHAIN_SKIP): 9 = the general MMA issue loop
+  int tail64;                // two-chunk chains whose second chunk has 32 channels: THREE slots -- two 128-byte-row slots for chunk 0
+                             // (alternate tiles) and one 64-byte-row slot for chunk 1 (conv_chain.cu)
   int pdl;                   // host side: launch with programmatic stream serialization
   unsigned* ctrl;
   unsigned* counters;
@@ -169,7 +171,7 @@ struct ChainPatchParams {
   ChainConv conv[kChainMaxConv];
   float2 sb[kChainMaxConv][kChainMaxCoutP];   // (BN scale, bias) per conv and output channel (see ChainIgemmParams)
 };
-struct ChainPatchMaps { CUtensorMap a[kChainMaxConv]; CUtensorMap b[kChainMaxConv][2]; };
+struct ChainPatchMaps { CUtensorMap a[kChainMaxConv]; CUtensorMap b[kChainMaxConv][2]; CUtensorMap a2[kChainMaxConv]; };   // a2: 32-channel patch box (tail64)
 cudaError_t launch_chain_igemm(const ChainIgemmMaps& maps, const ChainIgemmParams& p, int smem_bytes, int grid, cudaStream_t st);
 cudaError_t launch_chain_patch(const ChainPatchMaps& maps, const ChainPatchParams& p, int smem_bytes, int grid, cudaStream_t st);
 cudaError_t conv_chain_set_attributes(int max_smem);

@@ -52,6 +52,7 @@ struct ChainInfo {
   int flag_stride = 0;             // unit counters per conv (at max batch)
   int m2 = 1, stages = 0;          // im2col chain: M-tiles per ticket, pipeline stages
   bool pair = false;               // im2col chain on CTA pairs (cta_group::2): a unit = two M-tiles, one per CTA
+  bool tail64 = false;             // halo-patch chain with a 64 + 32 channel split: three patch slots (conv_chain.cu)
   std::vector<float> sb;           // host copy of the member convs' BN (scale, bias) pairs [conv][cout][2], read back by
                                    // hrnet_plan_bind: they travel to the chain kernels as kernel parameters (constant bank)
   size_t ctrl_off = 0, flags_off = 0;   // bytes into the activation workspace
@@ -674,13 +675,22 @@ void plan_chains(HrnetPlan& P) {
     const TensorInfo& ti = P.tensors[o0.in];
     const double k16 = 9.0 * ((o0.cin + 15) / 16);
     if (ch.patch) {
-      ch.smem = o0.patch_smem + (int)(ch.ops.size() - 1) * 2 * o0.cout * 4;   // BN constants of every conv stay in shared memory
+      ch.smem = o0.patch_smem + (int)(ch.ops.size() - 1) * 2 * o0.cout * 4;   // (room the BN constants used to need)
       if (ch.smem > kMaxDynSmem) { ch.enabled = false; continue; }
+      // 64 + 32 input channels (C = 96), one issuer, two slots: the second chunk only needs 64-byte rows -- a third slot
+      // fits (2 x 23 KB + 12 KB) and the next tile's chunk 0 loads while this tile's is multiplied (the reload of the only
+      // chunk-0 slot cost ~700 clk per 4,380-clk tile).  HRNET_TUNE_CHAIN_SKIP = 8 keeps the two-slot layout (experiment).
+      ch.tail64 = o0.pp.nchunks == 2 && o0.pp.kreal[0] == 64 && o0.pp.kreal[1] == 32 && o0.pp.mma_warps == 1 && o0.pp.nslots == 2 &&
+                  P.desc.tune[HRNET_TUNE_CHAIN_SKIP] != 8;
+      if (ch.tail64) {
+        const int smem3 = o0.patch_smem + 12288;      // (kPatchRows x 64 B = 11,520 rounded up: the third, narrow slot)
+        if (smem3 <= kMaxDynSmem) ch.smem = std::max(ch.smem, smem3); else ch.tail64 = false;
+      }
       ch.flag_stride = P.desc.max_batch * o0.pp.tiles_h;             // one counter per row of tiles of an image
       // per-MMA costs calibrated on the in-situ module times of SM-split sweeps (profiles/r02_s26_split_sweep.log: per
-      // mille 365 / 265 / 185 / 185 for C = 48 / 96 / 192 / 384 is 6 % faster than the isolated per-tile times suggest --
+      // mille 375 / 235 / 195 / 195 for C = 48 / 96 / 192 / 384 (after the three-slot layout of the C = 96 chains, r02_s35) is 6 % faster than the isolated per-tile times suggest --
       // 1,973 clk per 128 x 48 x 432 tile, 4,380 per 128 x 96 x 864 tile -- because the chains also share L2 and power)
-      ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * k16 * (o0.cout <= 64 ? 65.5 : 85.5);
+      ch.cost = (double)ch.ops.size() * P.desc.max_batch * o0.pp.tiles_w * o0.pp.tiles_h * k16 * (o0.cout <= 64 ? 67.3 : 75.8);
     } else {
       for (int i : ch.ops) P.ops[i].tc.mma_warps = 1;
       const int n_tiles = o0.cout / o0.tc.n_tile;
@@ -708,7 +718,7 @@ void plan_chains(HrnetPlan& P) {
       ch.flag_stride = (m_tiles + tpu - 1) / tpu;                    // one counter per ticket (tpu M-tiles x n_tiles arrivals)
       // measured inside the per-conv kernels: ~200 clk per K16 step of a 128 x 192 tile (profiles/r01_exp_gridcap_pair_sweep.log)
       // ... and ~490 clk per 128 x 192 x 64 k-block of the im2col chains (four K16 steps; CTA pairs ~470)
-      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * ((ch.pair ? 128.0 : 133.0) * o0.tc.n_tile / 192.0);
+      ch.cost = (double)ch.ops.size() * m_tiles * n_tiles * k16 * ((ch.pair ? 135.0 : 140.0) * o0.tc.n_tile / 192.0);
     }
     ch.ctrl_off = cur; cur += 256;
     ch.flags_off = cur; cur += ((size_t)ch.ops.size() * ch.flag_stride * 4 + 255) / 256 * 256;
@@ -1174,7 +1184,7 @@ int hrnet_plan_describe(const HrnetPlan* P, char* buf, size_t cap, size_t* neede
     if (!first_chain) o << ",";
     first_chain = false;
     o << "{\"module\":" << ch.module << ",\"branch\":" << ch.branch << ",\"patch\":" << (ch.patch ? 1 : 0) << ",\"smem\":" << ch.smem
-      << ",\"share_permille\":" << ch.share << ",\"grid\":" << ch.grid << ",\"m2\":" << ch.m2 << ",\"pair\":" << (ch.pair ? 1 : 0) << ",\"stages\":" << ch.stages << ",\"flag_stride\":" << ch.flag_stride << ",\"ctrl_off\":" << ch.ctrl_off
+      << ",\"share_permille\":" << ch.share << ",\"grid\":" << ch.grid << ",\"m2\":" << ch.m2 << ",\"pair\":" << (ch.pair ? 1 : 0) << ",\"tail64\":" << (ch.tail64 ? 1 : 0) << ",\"stages\":" << ch.stages << ",\"flag_stride\":" << ch.flag_stride << ",\"ctrl_off\":" << ch.ctrl_off
       << ",\"flags_off\":" << ch.flags_off << ",\"ops\":[";
     for (size_t k = 0; k < ch.ops.size(); ++k) o << (k ? "," : "") << ch.ops[k];
     o << "]}";
@@ -1273,6 +1283,12 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
           ch.pmaps.a[k] = op.tmPA[0];
           ch.pmaps.b[k][0] = op.tmPB[0];
           ch.pmaps.b[k][1] = op.tmPB[tail];
+          ch.pmaps.a2[k] = op.tmPA[0];
+          if (ch.tail64) {      // 32-channel patch box with 64-byte swizzled rows for the second chunk
+            const TensorInfo& ti = P->tensors[op.in];
+            rc = encode_patch(&ch.pmaps.a2[k], P->abase + ti.offset, P->desc.max_batch, op.pp.H, op.pp.W, op.pp.Cin, 32);
+            if (rc) return rc;
+          }
         } else {
           ch.imaps.a[k] = op.tmA;
           ch.imaps.b[k] = op.tmB;
@@ -1296,7 +1312,7 @@ int hrnet_plan_bind(HrnetPlan* P, void* weights_dev, size_t weight_bytes, void* 
         }
       }
       for (size_t k = ch.ops.size(); k < (size_t)kChainMaxConv; ++k) {   // unused slots: any valid descriptor
-        if (ch.patch) { ch.pmaps.a[k] = ch.pmaps.a[0]; ch.pmaps.b[k][0] = ch.pmaps.b[0][0]; ch.pmaps.b[k][1] = ch.pmaps.b[0][1]; }
+        if (ch.patch) { ch.pmaps.a[k] = ch.pmaps.a[0]; ch.pmaps.a2[k] = ch.pmaps.a2[0]; ch.pmaps.b[k][0] = ch.pmaps.b[0][0]; ch.pmaps.b[k][1] = ch.pmaps.b[0][1]; }
         else { ch.imaps.a[k] = ch.imaps.a[0]; ch.imaps.b[k] = ch.imaps.b[0]; }
       }
     }
@@ -1535,6 +1551,7 @@ int launch_chain_op(HrnetPlan* P, int c, int n, int grid, cudaStream_t st, long 
     p.unit_stride = ch.flag_stride;
     p.chunk = p.pp.tiles_w;   // one ticket = one tile row
     p.skip = P->desc.tune[HRNET_TUNE_CHAIN_SKIP];
+    p.tail64 = ch.tail64 ? 1 : 0;
     p.pdl = P->desc.tune[HRNET_TUNE_NO_PDL] ? 0 : 1;
     p.ctrl = (unsigned*)(P->abase + ch.ctrl_off);
     p.counters = (unsigned*)(P->abase + ch.flags_off);

@@ -25,6 +25,7 @@ PER_CONV = _lib.FLAG_NO_CHAIN      # with NO_XUNIT: every conv its own launch (r
 NO_XUNIT = {_lib.TUNE_XUNIT: 3}
 XUNIT_CONVS, XUNIT_ALL = {_lib.TUNE_XUNIT: 1}, {_lib.TUNE_XUNIT: 2}   # exchange units per source branch (default) / per module + sums
 PAIR = {_lib.TUNE_CHAIN_PAIR: 2}       # im2col chains on CTA pairs (cta_group::2)
+TWO_SLOTS = {_lib.TUNE_CHAIN_SKIP: 8}  # C = 96 halo-patch chains with two equal patch slots instead of the 2 + 1 narrow layout
 
 
 def test_chain_plan_is_active():
@@ -68,7 +69,7 @@ def test_chain_full_size_headline_and_grid_splits():
     hr = _engine(48, (384, 288), 64, sd, PER_CONV, NO_XUNIT)(x)
     for tune in (None, {_lib.TUNE_CHAIN_SHARE0: 100, 1: 100, 2: 400, 3: 400}, {_lib.TUNE_CHAIN_GRID_CAP: 3}, {_lib.TUNE_CHAIN_M2: 2},
                  PAIR, {**PAIR, _lib.TUNE_CHAIN_GRID_CAP: 5}, {**PAIR, _lib.TUNE_CHAIN_SHARE0: 100, 1: 100, 2: 400, 3: 400},
-                 NO_XUNIT, XUNIT_ALL):
+                 NO_XUNIT, XUNIT_ALL, TWO_SLOTS):
         e = _engine(48, (384, 288), 64, sd, 0, tune)
         for rep in range(2):
             h = e(x)

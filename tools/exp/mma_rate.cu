@@ -7,7 +7,7 @@
 #include <stdio.h>
 #include "../../simple-hrnet_b200/csrc/ptx.cuh"
 
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int a_stride_rows, int a_row_off, int d_col, int taps, long long* out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int a_stride_rows, int a_row_off, int d_col, int taps, int a_sw, long long* out) {
   extern __shared__ uint8_t raw[];
   const uint32_t base = (ptx::smem_u32(raw) + 1023u) & ~1023u;
   __shared__ uint64_t bar;
@@ -23,12 +23,12 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int 
   const uint32_t tmem = tslot;
   if (warp == 0) {
     const uint32_t idesc = ptx::umma_idesc_f16(128, N);
-    const uint64_t adesc = ptx::umma_desc_kmajor(base + (uint32_t)a_row_off * 128u, 128u, (uint32_t)a_stride_rows * 128u);
+    const uint64_t adesc = ptx::umma_desc_kmajor(base + (uint32_t)a_row_off * (uint32_t)a_sw, (uint32_t)a_sw, (uint32_t)a_stride_rows * (uint32_t)a_sw);
     const uint64_t bdesc = ptx::umma_desc_kmajor(base + 32768u, 128u, 1024u);
     long long t0 = clock64();
     if (ptx::elect_one()) {
       if (!taps) {
-        for (int i = 0; i < iters; ++i) ptx::mma_f16_ss(tmem + (uint32_t)d_col, adesc + (uint64_t)(2 * (i & 3)), bdesc + (uint64_t)(2 * (i & 3)), idesc, 1u);
+        for (int i = 0; i < iters; ++i) ptx::mma_f16_ss(tmem + (uint32_t)d_col, adesc + (uint64_t)(2 * (i & (a_sw == 128 ? 3 : 1))), bdesc + (uint64_t)(2 * (i & 1)), idesc, 1u);
       } else {
         // the halo-patch kernel's sequence: 9 taps x 3 K16 steps, A shifted by (r * 10 + s) rows, B block t of 6 KB
         for (int i = 0; i < iters; i += 27)
@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int 
   if (warp == 0) { ptx::tc_fence_after_sync(); ptx::tmem_dealloc(tmem, 256); }
 }
 
-extern "C" int exp_mma_rate(int N, int iters, int a_stride_rows, int a_row_off, int d_col, int taps, long long* out_dev) {
+extern "C" int exp_mma_rate(int N, int iters, int a_stride_rows, int a_row_off, int d_col, int taps, int a_sw, long long* out_dev) {
   const int smem = 1024 + 128 * 1024;
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  mma_rate_kernel<<<1, 128, smem>>>(N, iters, a_stride_rows, a_row_off, d_col, taps, out_dev);
+  mma_rate_kernel<<<1, 128, smem>>>(N, iters, a_stride_rows, a_row_off, d_col, taps, a_sw, out_dev);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { fprintf(stderr, "exp_mma_rate: %s\n", cudaGetErrorString(e)); return -4; }
   return 0;
