@@ -168,3 +168,35 @@ def test_two_issuer_pipelines_keep_their_ring_depth(arch, c, res):
         else:
             assert t["mma_warps"] == 1, op["name"]
     assert n2 > 0
+
+
+def test_chain_and_exchange_unit_planning():
+    """Host-side planning of round 2 (no GPU): 26 branch chains of 8 convs, their SM shares (per mille, each module's sum
+    to 1000, calibrated 375 / 235 / 195 / 195 in a 4-branch module), the three-slot layout of the 64 + 32-channel chains,
+    exchange units per source branch, launch counts of the variants, CTA pairs only on the im2col chains."""
+    from simple_hrnet_b200 import _lib
+    from simple_hrnet_b200.engine import Plan
+    p = Plan("hrnet", 48, 17, (384, 288), 64)
+    d = p.describe()
+    chains = d["chains"]
+    assert len(chains) == 26 and all(len(c["ops"]) == 8 for c in chains)
+    by_mod = {}
+    for c in chains:
+        by_mod.setdefault(c["module"], []).append(c)
+    for m, cs in by_mod.items():
+        assert abs(sum(c["share_permille"] for c in cs) - 1000) <= len(cs), (m, [c["share_permille"] for c in cs])
+    four = [c["share_permille"] for c in sorted(by_mod[max(by_mod)], key=lambda c: c["branch"])]
+    assert four == [375, 235, 195, 195]
+    assert [c["tail64"] for c in sorted(by_mod[max(by_mod)], key=lambda c: c["branch"])] == [0, 1, 0, 0]      # C = 96 only
+    assert all(c["patch"] == (1 if c["branch"] < 2 else 0) for c in chains) and all(c["pair"] == 0 for c in chains)
+    assert all(c["smem"] <= 227 * 1024 for c in chains)
+    assert sorted(len(x["ops"]) for x in d["xunits"]) == sorted([3, 2, 2] * 4 + [6, 4, 3, 3] * 2)
+    assert p.launch_count == 317 - 26 * 7 - (60 - 20)
+    assert Plan("hrnet", 48, 17, (384, 288), 64, tune={_lib.TUNE_XUNIT: 3}).launch_count == 317 - 26 * 7
+    assert Plan("hrnet", 48, 17, (384, 288), 64, flags=_lib.FLAG_NO_CHAIN, tune={_lib.TUNE_XUNIT: 3}).launch_count == 317
+    pp = Plan("hrnet", 48, 17, (384, 288), 64, tune={_lib.TUNE_CHAIN_PAIR: 2}).describe()["chains"]
+    assert all(c["pair"] == (0 if c["patch"] else 1) for c in pp) and all(c["stages"] == 8 for c in pp if c["pair"])
+    two = Plan("hrnet", 48, 17, (384, 288), 64, tune={_lib.TUNE_CHAIN_SKIP: 8}).describe()["chains"]
+    assert all(c["tail64"] == 0 for c in two)
+    w32 = Plan("hrnet", 32, 17, (256, 192), 32).describe()["chains"]
+    assert len(w32) == 26 and all(c["tail64"] == 0 for c in w32)              # C = 32 / 64: one chunk
