@@ -172,6 +172,9 @@ class B200Engine(Plan):
         with torch.cuda.device(self.device):
             self._weights_base, self._weights = _aligned_empty(self.weight_bytes, self.device)
             self._weights.copy_(torch.from_numpy(host))
+            # hrnet_plan_bind reads the BN constants / head weights back with synchronous copies on the legacy default
+            # stream, which does not wait for torch's non-blocking streams: the upload must have landed
+            torch.cuda.current_stream(self.device).synchronize()
             if self._workspace is None:
                 self._workspace_base, self._workspace = _aligned_empty(self.act_bytes, self.device, zero=True)
             check(self.lib.hrnet_plan_bind(self._plan, self._weights.data_ptr(), self.weight_bytes,
