@@ -43,7 +43,7 @@ def test_chain_plan_is_active():
     assert xa.launch_count == 317 - 26 * 7 - (65 - 8) - 23    # sums as tickets
 
 
-@pytest.mark.parametrize("c,res,n", [(32, (64, 64), 2), (32, (128, 96), 5), (32, (256, 192), 32), (48, (384, 288), 16)])
+@pytest.mark.parametrize("c,res,n", [(32, (64, 64), 2), (32, (128, 96), 5), (32, (256, 192), 32), (48, (384, 288), 16), (48, (256, 192), 9)])
 def test_chain_equals_per_conv_launches(c, res, n):
     sd = O.make_state_dict(O.hrnet_param_spec(c, 17), seed=5, bn="random")
     x = torch.randn(n, 3, *res, generator=torch.Generator().manual_seed(2)).cuda()
