@@ -102,7 +102,7 @@ __device__ __forceinline__ void epi_store_row(uint4 (&r)[8], const EpiRow& e, ui
   }
 }
 
-// kEpi == 3 (opt-in, HRNET_B200_EPI=batch; NOT yet run on hardware): the same thread-per-row epilogue for tiles at most 64
+// kEpi == 3 (opt-in, HRNET_TUNE_EPILOGUE = batch; in the GPU test matrix, no gain measured): the same thread-per-row epilogue for tiles at most 64
 // channels wide with all tcgen05.ld of the tile issued before ONE tcgen05.wait::ld (epi_store_row waits once per 32
 // columns: two TMEM round trips for a 48-channel tile).  `r` holds the residual of channels [0, 64) like above.
 __device__ __forceinline__ void epi_store_row_batched(uint4 (&r)[8], const EpiRow& e, uint32_t t_row) {

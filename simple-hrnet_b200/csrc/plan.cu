@@ -216,7 +216,7 @@ void choose_tc_cfg(Op& op, uint32_t flags, const int32_t* tune, int max_nt = 256
   c.cs = tune[HRNET_TUNE_IGEMM_PAIR] == 2 ? 2 : 1;
   if (op.k * op.k * op.cin < tune[HRNET_TUNE_IGEMM_PAIR_MIN_K]) c.cs = 1;   // pair mode only for convs with at least this K
   if (nt % 16 || (nt / 2) % 8) c.cs = 1;
-  // two MMA-issuing warps on alternate tiles (conv_igemm_body.cuh): HRNET_B200_IGEMM_MMA2=1 (all convs) or =<max N>
+  // two MMA-issuing warps on alternate tiles (conv_igemm_body.cuh): HRNET_TUNE_IGEMM_MMA2 = 1 (all convs) or = <max N>
   // (only tiles at most that wide, where the issue side rather than shared-memory bandwidth sets the pace)
   const int a_blk = (int)align_up((size_t)128 * c.kc * 2, 1024);
   const int b_blk = (int)align_up((size_t)(nt / c.cs) * c.kc * 2, 1024);
@@ -2169,7 +2169,7 @@ int hrnet_forward_host(HrnetPlan* P, const float* in_h, int n, float* heatmaps_h
 }
 
 
-// Debug only (HRNET_B200_DBG=1, single-op entry points): per-CTA role timers of the tcgen05 kernels.
+// Debug only (HRNET_TUNE_DEBUG through hrnet_debug_set_tune, single-op entry points): per-CTA role timers of the tcgen05 kernels.
 struct DbgTimers {
   long long* dev = nullptr;
   int grid = 0;

@@ -1,4 +1,4 @@
-"""Role timers (HRNET_B200_DBG=1) for arbitrary conv shapes: n,h,w,cin,cout,k,stride,residual,kernel"""
+"""Role timers (HRNET_TUNE_DEBUG via _lib.set_debug_tune) for arbitrary conv shapes: n,h,w,cin,cout,k,stride,residual,kernel"""
 import ctypes, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
